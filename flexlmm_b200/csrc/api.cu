@@ -1,0 +1,811 @@
+// api.cu — the C ABI (include/flexlmm_cuda.h): per-task state and the batch pipeline
+//   K1 decode -> K2 whiten -> K3a gram -> K3b solve -> K4 permutation contraction (+ min-p finalise)
+// over SNP batches of (SM count) column tiles, on one CUDA stream with double-buffered H2D staging.
+#include <cublas_v2.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/flexlmm_cuda.h"
+#include "common.cuh"
+#include "host_math.h"
+#include "kernels.h"
+
+namespace flx {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace flx
+
+using namespace flx;
+
+#define FLX_CUBLAS_TRY(expr)                                                             \
+    do {                                                                                 \
+        cublasStatus_t _s = (expr);                                                      \
+        if (_s != CUBLAS_STATUS_SUCCESS) {                                               \
+            set_error("%s:%d: %s failed: cublas status %d", __FILE__, __LINE__, #expr, (int)_s); \
+            return FLX_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+#define FLX_TRY(expr)              \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != 0) return _r;    \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    int ensure(size_t count) {
+        if (count <= cap && p) return 0;
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return FLX_ERR_OOM; }
+        cap = count;
+        return 0;
+    }
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    int ensure(size_t count) {
+        if (count <= cap && p) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; set_error("cudaMallocHost(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return FLX_ERR_OOM; }
+        cap = count;
+        return 0;
+    }
+};
+
+struct flx_handle {
+    flx_config cfg{};
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cublasHandle_t cublas = nullptr;
+    ncclComm_t comm = nullptr;
+    int nranks = 1;
+
+    // whitening
+    int64_t n = 0, n_pad = 0;
+    int KC = 0, T = 0;
+    DevBuf<double> linv;     // triangular packed panels
+    // null model
+    bool have_null = false;
+    std::vector<double> X_null, y_mm;
+    int c_null = 0, df_null = 0;
+    double ll_null = 0;
+    // design
+    bool have_design = false;
+    int k = 0;
+    std::vector<double> M0, M1, M2;
+    // permutations (raw inputs kept until finalisation)
+    bool have_perm = false;
+    std::vector<double> y_pred, e_p;
+    const double* U1_host = nullptr;  // caller-owned until finalise
+    std::vector<double> U1_copy;
+    int64_t m = 0;
+    std::vector<int32_t> seeds;
+    int P = 0;
+
+    // derived
+    bool dirty = true;
+    int s = 0, ncf = 0, cr = 0, cn = 0;
+    FitConst fc{};
+    DevBuf<double> Qc, Qn, r, lut;
+    double uni[8][3]{};
+    uint32_t uniform_mask = 0;
+    int64_t P_pad = 0;
+    int NP = 0;
+    DevBuf<double> Rpk, inv_rss, lrs0p, maxratio, minp_d;
+    DevBuf<int> df_count, missing;
+
+    // genotype source
+    int src = 0;  // 0 none, 1 pgen file, 2 host packed
+    PgenFile* pgen = nullptr;
+    const uint8_t* packed_host = nullptr;
+    int64_t src_variants = 0, bpv = 0, raw_n = 0;
+    std::vector<int32_t> order0;
+    bool identity_order = true;
+    DevBuf<int32_t> order_d;
+    DevBuf<uint8_t> resident;
+    bool is_resident = false;
+
+    // batch buffers
+    DevBuf<uint8_t> packed_d[2];
+    PinBuf<uint8_t> staging[2];
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    cudaEvent_t ev_used[2] = {nullptr, nullptr};
+    DevBuf<int32_t> vmap_d;
+    DevBuf<double> X, W, nrm2, u, Ag, b, snp_sm;
+    DevBuf<int32_t> snp_df;
+    // run-wide results
+    DevBuf<double> chisq, pval, coef;
+    DevBuf<int32_t> df, rank, pivot;
+
+    flx_stats stats{};
+
+    ~flx_handle() {
+        if (pgen) delete pgen;
+        for (int i = 0; i < 2; i++) {
+            if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
+            if (ev_used[i]) cudaEventDestroy(ev_used[i]);
+        }
+        if (comm) ncclCommDestroy(comm);
+        if (cublas) cublasDestroy(cublas);
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+
+extern "C" const char* flx_last_error(void) { return g_err; }
+extern "C" const char* flx_version(void) { return "flexlmm_b200 0.1.0 (sm_100a)"; }
+extern "C" int flx_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+
+extern "C" int flx_create(const flx_config* cfg, flx_handle** out) {
+    if (!out) { set_error("flx_create: out is NULL"); return FLX_ERR_BAD_ARG; }
+    *out = nullptr;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        set_error("flx_create: no CUDA device available (this library has no CPU fallback)");
+        return FLX_ERR_NO_DEVICE;
+    }
+    flx_handle* h = new flx_handle();
+    if (cfg) h->cfg = *cfg;
+    if (h->cfg.device < 0 || h->cfg.device >= cnt) { set_error("flx_create: device %d out of range (%d devices)", h->cfg.device, cnt); delete h; return FLX_ERR_BAD_ARG; }
+    cudaError_t e = cudaSetDevice(h->cfg.device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); delete h; return FLX_ERR_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, h->cfg.device);
+    if (prop.major != 10) {
+        set_error("flx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", h->cfg.device, prop.major, prop.minor);
+        delete h;
+        return FLX_ERR_NO_DEVICE;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        delete h;
+        return FLX_ERR_CUDA;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming);
+    }
+    if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); delete h; return FLX_ERR_CUDA; }
+    cublasSetStream(h->cublas, h->stream);
+    *out = h;
+    return FLX_OK;
+}
+
+extern "C" void flx_destroy(flx_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse) {
+    if (!h || !L || n <= 0 || ld < n) { set_error("flx_set_whitening: bad arguments"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->n = n;
+    h->n_pad = (n + TJ - 1) / TJ * TJ;
+    h->KC = (int)(h->n_pad / KCH);
+    h->T = (int)(h->n_pad / TJ);
+    h->dirty = true;
+    DevBuf<double> Ld, Z;
+    FLX_TRY(Ld.ensure((size_t)n * n));
+    FLX_CUDA_TRY(cudaMemcpy2DAsync(Ld.p, n * sizeof(double), L, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
+    const double* inv = Ld.p;
+    if (!is_inverse) {
+        // Z = L^-1 by a triangular solve against the identity (setup only; library call outside the hot loop)
+        FLX_TRY(Z.ensure((size_t)n * n));
+        FLX_TRY(launch_set_identity(Z.p, n, n, h->stream));
+        const double one = 1.0;
+        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)n, &one, Ld.p, (int)n, Z.p, (int)n));
+        inv = Z.p;
+    }
+    FLX_TRY(h->linv.ensure((size_t)tri_chunks_before(h->T) * CHUNK));
+    FLX_TRY(launch_pack_tri(inv, n, n, h->T, h->linv.p, h->stream));
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLX_OK;
+}
+
+extern "C" int flx_set_null(flx_handle* h, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null) {
+    if (!h || !y_mm || c < 0 || (c > 0 && !X_null) || c > FLX_MAX_K) { set_error("flx_set_null: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (h->n <= 0) { set_error("flx_set_null: call flx_set_whitening first"); return FLX_ERR_STATE; }
+    h->X_null.assign(X_null, X_null + (size_t)h->n * c);
+    h->y_mm.assign(y_mm, y_mm + h->n);
+    h->c_null = c; h->ll_null = ll_null; h->df_null = df_null;
+    h->have_null = true; h->dirty = true;
+    return FLX_OK;
+}
+
+extern "C" int flx_set_design(flx_handle* h, const double* M0, const double* M1, const double* M2, int32_t k) {
+    if (!h || !M0 || !M1 || !M2 || k <= 0) { set_error("flx_set_design: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (k > FLX_MAX_K) { set_error("flx_set_design: k=%d exceeds FLX_MAX_K=%d", k, FLX_MAX_K); return FLX_ERR_BAD_ARG; }
+    if (h->n <= 0) { set_error("flx_set_design: call flx_set_whitening first"); return FLX_ERR_STATE; }
+    const size_t sz = (size_t)h->n * k;
+    h->M0.assign(M0, M0 + sz); h->M1.assign(M1, M1 + sz); h->M2.assign(M2, M2 + sz);
+    h->k = k; h->have_design = true; h->dirty = true;
+    return FLX_OK;
+}
+
+extern "C" int flx_set_perm(flx_handle* h, const double* y_pred, const double* U1, const double* e_p, int64_t m, const int32_t* seeds, int32_t P) {
+    if (!h) { set_error("flx_set_perm: NULL handle"); return FLX_ERR_BAD_ARG; }
+    if (P == 0) { h->have_perm = false; h->P = 0; h->dirty = true; return FLX_OK; }
+    if (!y_pred || !U1 || !e_p || !seeds || m <= 0 || P < 0) { set_error("flx_set_perm: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (h->n <= 0) { set_error("flx_set_perm: call flx_set_whitening first"); return FLX_ERR_STATE; }
+    h->y_pred.assign(y_pred, y_pred + h->n);
+    h->e_p.assign(e_p, e_p + m);
+    h->U1_copy.assign(U1, U1 + (size_t)h->n * m);  // R owns U1 only for the duration of the call
+    h->m = m;
+    h->seeds.assign(seeds, seeds + P);
+    h->P = P; h->have_perm = true; h->dirty = true;
+    return FLX_OK;
+}
+
+static int set_order(flx_handle* h, const int32_t* pgen_order, int64_t n, int64_t raw_n) {
+    if (h->n > 0 && n != h->n) { set_error("genotype source: n=%lld does not match the whitening matrix (%lld)", (long long)n, (long long)h->n); return FLX_ERR_BAD_ARG; }
+    h->order0.resize(n);
+    h->identity_order = true;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t o = pgen_order ? (int64_t)pgen_order[i] - 1 : i;
+        if (o < 0 || o >= raw_n) { set_error("pgen_order[%lld]=%lld out of range 1..%lld", (long long)i, (long long)o + 1, (long long)raw_n); return FLX_ERR_BAD_ARG; }
+        h->order0[i] = (int32_t)o;
+        if (o != i) h->identity_order = false;
+    }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    FLX_TRY(h->order_d.ensure(n));
+    FLX_CUDA_TRY(cudaMemcpy(h->order_d.p, h->order0.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->is_resident = false;
+    return FLX_OK;
+}
+
+extern "C" int flx_open_pgen(flx_handle* h, const char* path, const int32_t* pgen_order, int64_t n) {
+    if (!h || !path || n <= 0) { set_error("flx_open_pgen: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (h->pgen) { delete h->pgen; h->pgen = nullptr; }
+    h->pgen = new PgenFile();
+    std::string e = h->pgen->open(path);
+    if (!e.empty()) { set_error("flx_open_pgen(%s): %s", path, e.c_str()); delete h->pgen; h->pgen = nullptr; return FLX_ERR_PGEN; }
+    h->src = 1;
+    h->src_variants = h->pgen->variant_ct();
+    h->raw_n = h->pgen->sample_ct();
+    h->bpv = h->pgen->bytes_per_variant();
+    return set_order(h, pgen_order, n, h->raw_n);
+}
+
+extern "C" int flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n) {
+    if (!h || !packed || n_variants < 0 || raw_sample_ct <= 0 || bytes_per_variant < (raw_sample_ct + 3) / 4 || n <= 0) { set_error("flx_set_packed: bad arguments"); return FLX_ERR_BAD_ARG; }
+    h->src = 2;
+    h->packed_host = packed;
+    h->src_variants = n_variants;
+    h->raw_n = raw_sample_ct;
+    h->bpv = bytes_per_variant;
+    return set_order(h, pgen_order, n, raw_sample_ct);
+}
+
+extern "C" int flx_make_resident(flx_handle* h) {
+    if (!h || h->src != 2) { set_error("flx_make_resident: needs flx_set_packed first"); return FLX_ERR_STATE; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    FLX_TRY(h->resident.ensure((size_t)h->src_variants * h->bpv));
+    FLX_CUDA_TRY(cudaMemcpy(h->resident.p, h->packed_host, (size_t)h->src_variants * h->bpv, cudaMemcpyHostToDevice));
+    h->is_resident = true;
+    return FLX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whiten `ncols` dense columns (device, n x ncols, ld) -> dense (device). Used for the constant design columns.
+static int whiten_dense(flx_handle* h, const double* Xd, int64_t ld, int64_t ncols, double* Wd, int64_t ldw) {
+    const int NJ = (int)((ncols + TJ - 1) / TJ);
+    DevBuf<double> Xp, Wp;
+    FLX_TRY(Xp.ensure((size_t)NJ * h->KC * CHUNK));
+    FLX_TRY(Wp.ensure((size_t)NJ * h->KC * CHUNK));
+    FLX_TRY(launch_pack_cols(Xd, h->n, ld, ncols, h->KC, Xp.p, h->stream));
+    GemmArgs g{};
+    g.A = h->linv.p; g.B = Xp.p; g.Out = Wp.p;
+    g.T = h->T; g.NJ = NJ; g.KC = h->KC; g.n_items = (int64_t)h->T * NJ;
+    FLX_TRY(launch_whiten(g, h->num_sms, h->stream));
+    FLX_TRY(launch_unpack_cols(Wp.p, h->n, ldw, ncols, h->KC, Wd, h->stream));
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLX_OK;
+}
+
+extern "C" int flx_whiten(flx_handle* h, const double* X, int64_t ncols, double* W) {
+    if (!h || !X || !W || ncols <= 0) { set_error("flx_whiten: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (!h->linv.p) { set_error("flx_whiten: call flx_set_whitening first"); return FLX_ERR_STATE; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DevBuf<double> Xd, Wd;
+    FLX_TRY(Xd.ensure((size_t)h->n * ncols));
+    FLX_TRY(Wd.ensure((size_t)h->n * ncols));
+    FLX_CUDA_TRY(cudaMemcpyAsync(Xd.p, X, (size_t)h->n * ncols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FLX_TRY(whiten_dense(h, Xd.p, h->n, ncols, Wd.p, h->n));
+    FLX_CUDA_TRY(cudaMemcpy(W, Wd.p, (size_t)h->n * ncols * sizeof(double), cudaMemcpyDeviceToHost));
+    return FLX_OK;
+}
+
+static void upload_rowmajor_padded(const std::vector<double>& Q, int64_t n, int r, int64_t n_pad, std::vector<double>& out) {
+    const int rp = (r + 3) & ~3;
+    out.assign((size_t)n_pad * (rp > 0 ? rp : 4) + 8, 0.0);
+    for (int j = 0; j < r; j++)
+        for (int64_t i = 0; i < n; i++) out[i * rp + j] = Q[i + (int64_t)j * n];
+}
+
+// derive everything that depends on (L, null, design, perm): once per task
+static int finalize_setup(flx_handle* h) {
+    if (!h->linv.p || !h->have_null || !h->have_design) { set_error("flx_run: whitening, null model and design must be set first"); return FLX_ERR_STATE; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int64_t n = h->n, n_pad = h->n_pad;
+    const int k = h->k;
+    // ---- split the design into SNP-independent columns and SNP-dependent terms (fit_model.nf:124-127)
+    std::vector<int> const_cols, snp_cols;
+    for (int j = 0; j < k; j++) {
+        bool same = true;
+        const double *a = h->M0.data() + (size_t)j * n, *b = h->M1.data() + (size_t)j * n, *c = h->M2.data() + (size_t)j * n;
+        for (int64_t i = 0; i < n && same; i++) same = (a[i] == b[i]) && (a[i] == c[i]);
+        (same ? const_cols : snp_cols).push_back(j);
+    }
+    h->s = (int)snp_cols.size();
+    h->ncf = (int)const_cols.size();
+    if (h->s < 1) { set_error("flx_set_design: no design column depends on the genotype x"); return FLX_ERR_BAD_ARG; }
+    if (h->s > FLX_MAX_S) { set_error("flx_set_design: %d SNP-dependent columns exceed FLX_MAX_S=%d", h->s, FLX_MAX_S); return FLX_ERR_BAD_ARG; }
+    FitConst& fc = h->fc;
+    memset(&fc, 0, sizeof(fc));
+    for (int ci = 0; ci < h->ncf; ci++) fc.col_kind[const_cols[ci]] = ci;
+    for (int t = 0; t < h->s; t++) fc.col_kind[snp_cols[t]] = -(t + 1);
+    // ---- lookup tables of the SNP terms
+    h->uniform_mask = 0;
+    std::vector<double> lut((size_t)h->s * 3 * n_pad, 0.0);
+    for (int t = 0; t < h->s; t++) {
+        const double* src[3] = {h->M0.data() + (size_t)snp_cols[t] * n, h->M1.data() + (size_t)snp_cols[t] * n, h->M2.data() + (size_t)snp_cols[t] * n};
+        bool uniform = true;
+        for (int g = 0; g < 3; g++) {
+            h->uni[t][g] = src[g][0];
+            for (int64_t i = 0; i < n; i++) {
+                lut[((size_t)t * 3 + g) * n_pad + i] = src[g][i];
+                if (src[g][i] != src[g][0]) uniform = false;
+            }
+        }
+        if (uniform) h->uniform_mask |= 1u << t;
+    }
+    FLX_TRY(h->lut.ensure(lut.size()));
+    FLX_CUDA_TRY(cudaMemcpy(h->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // ---- whiten the constant columns of the real model, orthonormal basis Qc
+    std::vector<double> Cw((size_t)n * std::max(h->ncf, 1));
+    if (h->ncf > 0) {
+        std::vector<double> C((size_t)n * h->ncf);
+        for (int ci = 0; ci < h->ncf; ci++) memcpy(C.data() + (size_t)ci * n, h->M0.data() + (size_t)const_cols[ci] * n, n * sizeof(double));
+        DevBuf<double> Cd, Wd;
+        FLX_TRY(Cd.ensure(C.size()));
+        FLX_TRY(Wd.ensure(C.size()));
+        FLX_CUDA_TRY(cudaMemcpy(Cd.p, C.data(), C.size() * sizeof(double), cudaMemcpyHostToDevice));
+        FLX_TRY(whiten_dense(h, Cd.p, n, h->ncf, Wd.p, n));
+        FLX_CUDA_TRY(cudaMemcpy(Cw.data(), Wd.p, C.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    std::vector<double> Qc, Rc;
+    h->cr = orth_basis(Cw.data(), n, h->ncf, Qc, Rc);
+    const int cr = h->cr;
+    for (int ci = 0; ci < h->ncf; ci++)
+        for (int i = 0; i < cr; i++) fc.Rc[i + ci * 24] = Rc[i + (size_t)ci * cr];
+    // qcy, residual r (two projection passes), rss_f
+    std::vector<double> r(h->y_mm);
+    std::vector<long double> qcy(std::max(cr, 1), 0.0L);
+    for (int pass = 0; pass < 2; pass++)
+        for (int j = 0; j < cr; j++) {
+            const double* q = Qc.data() + (size_t)j * n;
+            long double t = 0.0L;
+            for (int64_t i = 0; i < n; i++) t += (long double)q[i] * r[i];
+            qcy[j] += t;
+            for (int64_t i = 0; i < n; i++) r[i] -= (double)t * q[i];
+        }
+    long double rss_f = 0.0L;
+    for (int64_t i = 0; i < n; i++) rss_f += (long double)r[i] * r[i];
+    for (int j = 0; j < cr; j++) fc.qcy[j] = (double)qcy[j];
+    fc.rss_f = (double)rss_f;
+    fc.n = (int)n; fc.s = h->s; fc.k = k; fc.cr = cr; fc.ncf = h->ncf; fc.df_null = h->df_null;
+    // lrt_chisq = 2 (ll - ll.null):  log RSS0 := -2 ll.null / N - (log 2 pi + 1 - log N)   (stats:::logLik.lm)
+    {
+        const long double N = (long double)n;
+        const long double log_rss0 = -2.0L * (long double)h->ll_null / N - (logl(2.0L * 3.14159265358979323846264338327950288L) + 1.0L - logl(N));
+        fc.lrs0 = (double)(log_rss0 - logl(rss_f));
+    }
+    std::vector<double> tmp;
+    upload_rowmajor_padded(Qc, n, cr, n_pad, tmp);
+    FLX_TRY(h->Qc.ensure(tmp.size()));
+    FLX_CUDA_TRY(cudaMemcpy(h->Qc.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    r.resize(n_pad, 0.0);
+    FLX_TRY(h->r.ensure(n_pad));
+    FLX_CUDA_TRY(cudaMemcpy(h->r.p, r.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
+    // null-model basis (for the permutation null refit, fit_model.nf:100-101)
+    std::vector<double> Qn, Rn;
+    h->cn = orth_basis(h->X_null.data(), n, h->c_null, Qn, Rn);
+    upload_rowmajor_padded(Qn, n, h->cn, n_pad, tmp);
+    FLX_TRY(h->Qn.ensure(tmp.size()));
+    FLX_CUDA_TRY(cudaMemcpy(h->Qn.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+    // ---- permutation prologue (fit_model.nf:96-101) for all seeds at once
+    h->P_pad = 0; h->NP = 0;
+    if (h->have_perm && h->P > 0) {
+        const int P = h->P;
+        const int64_t m = h->m;
+        h->NP = (P + TJ - 1) / TJ;
+        h->P_pad = (int64_t)h->NP * TJ;
+        std::vector<int32_t> idx((size_t)P * m);
+        {
+            const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+            const unsigned nt = std::min<unsigned>(hw, (unsigned)P);
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; t++)
+                th.emplace_back([&, t]() { for (int p = (int)t; p < P; p += (int)nt) r_sample_int(h->seeds[p], m, idx.data() + (size_t)p * m); });
+            for (auto& x : th) x.join();
+        }
+        DevBuf<int32_t> idx_d;
+        DevBuf<double> ep_d, E, U1d, UE, ypred_d, rssf_d, rss0_d;
+        FLX_TRY(idx_d.ensure(idx.size()));
+        FLX_TRY(ep_d.ensure(m));
+        FLX_TRY(E.ensure((size_t)m * P));
+        FLX_TRY(U1d.ensure((size_t)n * m));
+        FLX_TRY(UE.ensure((size_t)n_pad * h->P_pad));
+        FLX_TRY(ypred_d.ensure(n));
+        FLX_TRY(rssf_d.ensure(P));
+        FLX_TRY(rss0_d.ensure(P));
+        FLX_CUDA_TRY(cudaMemcpyAsync(idx_d.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUDA_TRY(cudaMemcpyAsync(ep_d.p, h->e_p.data(), m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUDA_TRY(cudaMemcpyAsync(U1d.p, h->U1_copy.data(), (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUDA_TRY(cudaMemcpyAsync(ypred_d.p, h->y_pred.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUDA_TRY(cudaMemsetAsync(UE.p, 0, (size_t)n_pad * h->P_pad * sizeof(double), h->stream));
+        FLX_TRY(launch_gather_ep(ep_d.p, idx_d.p, m, P, E.p, h->stream));
+        const double one = 1.0, zero = 0.0;
+        // U1 %*% sample(e.p) for every seed: one plain library GEMM (setup, outside the hot loop)
+        FLX_CUBLAS_TRY(cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, U1d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
+        PermPrepArgs pa{};
+        pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.Qn = h->Qn.p; pa.cn = h->cn;
+        pa.n = n; pa.n_pad = n_pad; pa.P = P; pa.rss_f = rssf_d.p; pa.rss0 = rss0_d.p;
+        FLX_TRY(launch_perm_prep(pa, h->stream));
+        FLX_TRY(h->Rpk.ensure((size_t)h->NP * h->KC * CHUNK));
+        FLX_TRY(launch_pack_cols(UE.p, n, n_pad, h->P_pad, h->KC, h->Rpk.p, h->stream));
+        std::vector<double> rssf(P), rss0(P);
+        FLX_CUDA_TRY(cudaMemcpyAsync(rssf.data(), rssf_d.p, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        FLX_CUDA_TRY(cudaMemcpyAsync(rss0.data(), rss0_d.p, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        std::vector<double> inv(h->P_pad, 0.0), lr(P);
+        for (int p = 0; p < P; p++) {
+            inv[p] = 1.0 / rssf[p];
+            lr[p] = (double)(logl((long double)rss0[p]) - logl((long double)rssf[p]));
+        }
+        FLX_TRY(h->inv_rss.ensure(h->P_pad));
+        FLX_TRY(h->lrs0p.ensure(P));
+        FLX_TRY(h->maxratio.ensure((size_t)h->s * h->P_pad));
+        FLX_TRY(h->minp_d.ensure(P));
+        FLX_CUDA_TRY(cudaMemcpy(h->inv_rss.p, inv.data(), h->P_pad * sizeof(double), cudaMemcpyHostToDevice));
+        FLX_CUDA_TRY(cudaMemcpy(h->lrs0p.p, lr.data(), P * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double>().swap(h->U1_copy);
+    }
+    FLX_TRY(h->df_count.ensure(16));
+    FLX_TRY(h->missing.ensure(1));
+    h->dirty = false;
+    return FLX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool want_results, bool do_perm,
+                       double* X_out_dense, uint8_t* codes_out) {
+    const TileShape ts = make_tile_shape(h->s);
+    const int tiles_per_batch = h->cfg.batch_tiles > 0 ? h->cfg.batch_tiles : h->num_sms;
+    const int64_t snps_per_batch = (int64_t)tiles_per_batch * ts.snps;
+    const int64_t nbatch = (M + snps_per_batch - 1) / snps_per_batch;
+    const int64_t bpv = h->bpv;
+    const int nsym = h->s * (h->s + 1) / 2;
+    const int cr = h->cr;
+    const bool decode_only = (X_out_dense != nullptr) || (codes_out != nullptr);
+
+    // validate indices; contiguity lets the resident path skip the index map
+    bool contiguous = true;
+    for (int64_t i = 0; i < M; i++) {
+        if (var_idx[i] < 1 || var_idx[i] > h->src_variants) { set_error("var_idx[%lld]=%d out of range 1..%lld", (long long)i, var_idx[i], (long long)h->src_variants); return FLX_ERR_BAD_ARG; }
+        if (i > 0 && var_idx[i] != var_idx[i - 1] + 1) contiguous = false;
+    }
+    const size_t tile_elems = (size_t)h->KC * CHUNK;
+    FLX_TRY(h->X.ensure((size_t)tiles_per_batch * tile_elems));
+    if (!decode_only) {
+        FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
+        FLX_TRY(h->nrm2.ensure((size_t)snps_per_batch * h->s));
+        FLX_TRY(h->u.ensure((size_t)snps_per_batch * h->s * std::max(cr, 1)));
+        FLX_TRY(h->Ag.ensure((size_t)snps_per_batch * nsym));
+        FLX_TRY(h->b.ensure((size_t)snps_per_batch * h->s));
+        FLX_TRY(h->snp_sm.ensure((size_t)snps_per_batch * nsym));
+        FLX_TRY(h->snp_df.ensure((size_t)snps_per_batch));
+        FLX_TRY(h->chisq.ensure(M)); FLX_TRY(h->pval.ensure(M)); FLX_TRY(h->df.ensure(M)); FLX_TRY(h->rank.ensure(M));
+        FLX_TRY(h->pivot.ensure((size_t)M * h->k)); FLX_TRY(h->coef.ensure((size_t)M * h->k));
+    }
+    DevBuf<uint8_t> codes_d;
+    if (codes_out) FLX_TRY(codes_d.ensure((size_t)snps_per_batch * h->n));
+    const bool use_resident = h->is_resident;
+    if (use_resident && !contiguous) {
+        std::vector<int32_t> v0(M);
+        for (int64_t i = 0; i < M; i++) v0[i] = var_idx[i] - 1;
+        FLX_TRY(h->vmap_d.ensure(M));
+        FLX_CUDA_TRY(cudaMemcpyAsync(h->vmap_d.p, v0.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (!use_resident)
+        for (int i = 0; i < 2; i++) {
+            FLX_TRY(h->packed_d[i].ensure((size_t)snps_per_batch * bpv));
+            FLX_TRY(h->staging[i].ensure((size_t)snps_per_batch * bpv));
+        }
+    const int int_max = INT_MAX;
+    FLX_CUDA_TRY(cudaMemcpyAsync(h->missing.p, &int_max, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    FLX_CUDA_TRY(cudaMemsetAsync(h->df_count.p, 0, 16 * sizeof(int), h->stream));
+    if (do_perm) FLX_CUDA_TRY(cudaMemsetAsync(h->maxratio.p, 0, (size_t)h->s * h->P_pad * sizeof(double), h->stream));
+    if (!decode_only) FLX_TRY(upload_fit_const(h->fc));
+
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); evs.push_back(e); };
+    std::vector<uint8_t> xhost;
+
+    for (int64_t bi = 0; bi < nbatch; bi++) {
+        const int64_t s0 = bi * snps_per_batch;
+        const int64_t nsnp = std::min(snps_per_batch, M - s0);
+        const int NJ = (int)((nsnp + ts.snps - 1) / ts.snps);
+        const int buf = (int)(bi & 1);
+        const uint8_t* packed_dev;
+        const int32_t* vmap = nullptr;
+        mark();  // [0] batch start / h2d start
+        if (use_resident) {
+            if (contiguous) packed_dev = h->resident.p + (size_t)(var_idx[s0] - 1) * bpv;
+            else { packed_dev = h->resident.p; vmap = h->vmap_d.p + s0; }
+        } else {
+            // stage the batch's records in pinned memory (host work overlaps the previous batch's kernels)
+            if (bi >= 2) FLX_CUDA_TRY(cudaEventSynchronize(h->ev_used[buf]));
+            uint8_t* st = h->staging[buf].p;
+            if (h->src == 2) {
+                if (contiguous) memcpy(st, h->packed_host + (size_t)(var_idx[s0] - 1) * bpv, (size_t)nsnp * bpv);
+                else for (int64_t i = 0; i < nsnp; i++) memcpy(st + i * bpv, h->packed_host + (size_t)(var_idx[s0 + i] - 1) * bpv, bpv);
+            } else if (h->src == 1) {
+                for (int64_t i = 0; i < nsnp; i++) {
+                    std::string e = h->pgen->read_packed((uint32_t)(var_idx[s0 + i] - 1), st + i * bpv);
+                    if (!e.empty()) { set_error("pgen variant %d: %s", var_idx[s0 + i], e.c_str()); return FLX_ERR_PGEN; }
+                }
+            } else { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->packed_d[buf].p, st, (size_t)nsnp * bpv, cudaMemcpyHostToDevice, h->stream));
+            h->stats.h2d_bytes += nsnp * bpv;
+            packed_dev = h->packed_d[buf].p;
+        }
+        mark();  // [1] decode start
+        DecodeArgs da{};
+        da.packed = packed_dev; da.bpv = bpv; da.vmap = vmap;
+        da.order = h->identity_order ? nullptr : h->order_d.p;
+        da.n = h->n; da.KC = h->KC; da.nsnp = nsnp; da.snp_offset = s0; da.s = h->s;
+        da.lut = h->lut.p; memcpy(da.uni, h->uni, sizeof(da.uni)); da.uniform_mask = h->uniform_mask;
+        da.n_pad = h->n_pad; da.X = h->X.p; da.NJ = NJ; da.missing_flag = h->missing.p;
+        da.codes_out = codes_out ? codes_d.p : nullptr;
+        FLX_TRY(launch_decode(da, h->stream));
+        h->stats.launches++;
+        if (!use_resident) FLX_CUDA_TRY(cudaEventRecord(h->ev_used[buf], h->stream));
+        mark();  // [2] whiten start
+        if (decode_only) {
+            if (X_out_dense) {
+                // test hook: unpack the design tile on the host
+                std::vector<double> xp((size_t)NJ * tile_elems);
+                FLX_CUDA_TRY(cudaMemcpyAsync(xp.data(), h->X.p, xp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+                for (int64_t q = 0; q < nsnp; q++) {
+                    const int64_t J = q / ts.snps; const int ql = (int)(q % ts.snps);
+                    const int gi = ql / 8, g8 = ql % 8;
+                    for (int t = 0; t < h->s; t++) {
+                        const int col = 8 * (h->s * gi + t) + g8;
+                        double* dst = X_out_dense + ((size_t)(s0 + q) * h->s + t) * h->n;
+                        for (int64_t i = 0; i < h->n; i++) dst[i] = xp[(size_t)(J * h->KC + i / KCH) * CHUNK + chunk_off((int)(i % KCH), col)];
+                    }
+                }
+            }
+            if (codes_out) {
+                FLX_CUDA_TRY(cudaMemcpyAsync(codes_out + (size_t)s0 * h->n, codes_d.p, (size_t)nsnp * h->n, cudaMemcpyDeviceToHost, h->stream));
+                FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            }
+            mark(); mark(); mark();
+            continue;
+        }
+        GemmArgs g{};
+        g.A = h->linv.p; g.B = h->X.p; g.Out = h->W.p;
+        g.T = h->T; g.NJ = NJ; g.KC = h->KC; g.n_items = (int64_t)h->T * NJ;
+        FLX_TRY(launch_whiten(g, h->num_sms, h->stream));
+        h->stats.launches++; h->stats.launches_whiten++;
+        mark();  // [3] fit start
+        GramArgs ga{};
+        ga.W = h->W.p; ga.Qc = h->Qc.p; ga.r = h->r.p; ga.KC = h->KC; ga.cr = cr; ga.s = h->s; ga.nsnp = nsnp;
+        ga.nrm2 = h->nrm2.p; ga.u = h->u.p; ga.Ag = h->Ag.p; ga.b = h->b.p;
+        FLX_TRY(launch_snp_gram(ga, h->stream));
+        if (do_perm) {
+            FLX_CUDA_TRY(cudaMemsetAsync(h->snp_df.p, 0, (size_t)snps_per_batch * sizeof(int32_t), h->stream));
+            FLX_CUDA_TRY(cudaMemsetAsync(h->snp_sm.p, 0, (size_t)snps_per_batch * nsym * sizeof(double), h->stream));
+        }
+        SolveArgs sa{};
+        sa.nrm2 = h->nrm2.p; sa.u = h->u.p; sa.Ag = h->Ag.p; sa.b = h->b.p; sa.nsnp = nsnp; sa.out_offset = s0;
+        sa.chisq = h->chisq.p; sa.pval = h->pval.p; sa.df = h->df.p; sa.rank = h->rank.p; sa.pivot = h->pivot.p; sa.coef = h->coef.p;
+        sa.snp_df = do_perm ? h->snp_df.p : nullptr; sa.snp_sm = do_perm ? h->snp_sm.p : nullptr;
+        sa.df_count = h->df_count.p;
+        FLX_TRY(launch_snp_solve(sa, h->stream));
+        h->stats.launches += 2;
+        mark();  // [4] perm start
+        if (do_perm) {
+            GemmArgs gp{};
+            gp.A = h->W.p; gp.B = h->Rpk.p; gp.NJ = NJ; gp.NP = h->NP; gp.KC = h->KC; gp.n_items = (int64_t)NJ * h->NP;
+            gp.snp_df = h->snp_df.p; gp.snp_sm = h->snp_sm.p; gp.perm_inv_rss = h->inv_rss.p; gp.perm_maxratio = h->maxratio.p; gp.P_pad = h->P_pad;
+            FLX_TRY(launch_perm_contract(gp, h->s, h->num_sms, h->stream));
+            h->stats.launches++;
+        }
+        mark();  // [5] batch end
+    }
+    if (do_perm && !decode_only) {
+        FLX_TRY(launch_minp_finalize(h->maxratio.p, h->P_pad, h->P, h->s, h->lrs0p.p, (double)h->n, h->df_count.p, h->minp_d.p, h->stream));
+        h->stats.launches++;
+    }
+    mark();
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // accumulate per-stage device times
+    for (int64_t bi = 0; bi < nbatch; bi++) {
+        float ms;
+        cudaEvent_t* e = &evs[(size_t)bi * 6];
+        cudaEventElapsedTime(&ms, e[0], e[1]); h->stats.ms_h2d += ms;
+        cudaEventElapsedTime(&ms, e[1], e[2]); h->stats.ms_decode += ms;
+        cudaEventElapsedTime(&ms, e[2], e[3]); h->stats.ms_whiten += ms;
+        cudaEventElapsedTime(&ms, e[3], e[4]); h->stats.ms_fit += ms;
+        cudaEventElapsedTime(&ms, e[4], e[5]); h->stats.ms_perm += ms;
+    }
+    if (!evs.empty()) { float ms; cudaEventElapsedTime(&ms, evs.front(), evs.back()); h->stats.ms_total = ms; }
+    for (auto e : evs) cudaEventDestroy(e);
+    int miss = INT_MAX;
+    FLX_CUDA_TRY(cudaMemcpy(&miss, h->missing.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (miss != INT_MAX && !decode_only) {
+        set_error("missing genotype (NA hard call) in tested variant var_idx[%d]=%d: the reference aborts on it (no imputation anywhere in the pipeline)", miss, var_idx[miss]);
+        return FLX_ERR_MISSING_GENOTYPE;
+    }
+    (void)want_results;
+    return FLX_OK;
+}
+
+extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const flx_snp_out* out, double* minp, int64_t* nvars_tested) {
+    if (!h || (M > 0 && !var_idx) || M < 0) { set_error("flx_run: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (M >= INT_MAX) { set_error("flx_run: M too large"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->src == 0) { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
+    if (h->dirty) FLX_TRY(finalize_setup(h));
+    memset(&h->stats, 0, sizeof(h->stats));
+    const bool do_perm = h->have_perm && h->P > 0;
+    if (minp && !do_perm) { set_error("flx_run: minp requested but no permutations were set (flx_set_perm)"); return FLX_ERR_STATE; }
+    h->stats.snps = M; h->stats.n_pad = h->n_pad; h->stats.cols_per_tile = make_tile_shape(h->s).blocks * 8;
+    if (M > 0) FLX_TRY(run_batches(h, var_idx, M, out != nullptr, do_perm, nullptr, nullptr));
+    // ---- results D2H
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    if (out && M > 0) {
+        auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
+            if (!dst) return 0;
+            FLX_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+            h->stats.d2h_bytes += (int64_t)bytes;
+            return 0;
+        };
+        FLX_TRY(d2h(out->lrt_chisq, h->chisq.p, M * sizeof(double)));
+        FLX_TRY(d2h(out->pval, h->pval.p, M * sizeof(double)));
+        FLX_TRY(d2h(out->lrt_df, h->df.p, M * sizeof(int32_t)));
+        FLX_TRY(d2h(out->rank, h->rank.p, M * sizeof(int32_t)));
+        FLX_TRY(d2h(out->pivot, h->pivot.p, (size_t)M * h->k * sizeof(int32_t)));
+        FLX_TRY(d2h(out->coef, h->coef.p, (size_t)M * h->k * sizeof(double)));
+    }
+    int64_t nv = M;
+    if (do_perm) {
+        if (M == 0) {
+            std::vector<double> two(h->P, 2.0);
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->minp_d.p, two.data(), h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
+        if (h->comm && h->nranks > 1) {
+            // the only collective of the design: min over SNP shards of the length-P vector (get_null_p_dist.nf:77)
+            DevBuf<long long> nvd;
+            FLX_TRY(nvd.ensure(1));
+            long long nvl = M;
+            FLX_CUDA_TRY(cudaMemcpyAsync(nvd.p, &nvl, sizeof(nvl), cudaMemcpyHostToDevice, h->stream));
+            ncclResult_t r1 = ncclAllReduce(h->minp_d.p, h->minp_d.p, (size_t)h->P, ncclDouble, ncclMin, h->comm, h->stream);
+            ncclResult_t r2 = ncclAllReduce(nvd.p, nvd.p, 1, ncclInt64, ncclSum, h->comm, h->stream);
+            if (r1 != ncclSuccess || r2 != ncclSuccess) { set_error("ncclAllReduce failed: %s", ncclGetErrorString(r1 != ncclSuccess ? r1 : r2)); return FLX_ERR_NCCL; }
+            FLX_CUDA_TRY(cudaMemcpyAsync(&nvl, nvd.p, sizeof(nvl), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            nv = nvl;
+        }
+        if (minp) {
+            FLX_CUDA_TRY(cudaMemcpyAsync(minp, h->minp_d.p, h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            h->stats.d2h_bytes += h->P * (int64_t)sizeof(double);
+        }
+    }
+    cudaEventRecord(e1, h->stream);
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    h->stats.ms_d2h = ms;
+    h->stats.ms_total += ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (nvars_tested) *nvars_tested = nv;
+    return FLX_OK;
+}
+
+extern "C" int flx_get_stats(flx_handle* h, flx_stats* out) {
+    if (!h || !out) { set_error("flx_get_stats: bad arguments"); return FLX_ERR_BAD_ARG; }
+    *out = h->stats;
+    return FLX_OK;
+}
+
+extern "C" int flx_perm_indices(int32_t seed, int64_t m, int32_t* out) {
+    if (!out || m < 0) { set_error("flx_perm_indices: bad arguments"); return FLX_ERR_BAD_ARG; }
+    r_sample_int(seed, m, out);
+    return FLX_OK;
+}
+
+extern "C" int flx_decode_tile(flx_handle* h, const int32_t* var_idx, int64_t M, double* X, uint8_t* codes) {
+    if (!h || !var_idx || M <= 0 || (!X && !codes)) { set_error("flx_decode_tile: bad arguments"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->src == 0) { set_error("flx_decode_tile: no genotype source"); return FLX_ERR_STATE; }
+    if (h->dirty) FLX_TRY(finalize_setup(h));
+    if (codes) memset(codes, 3, (size_t)M * h->n);
+    return run_batches(h, var_idx, M, false, false, X, codes);
+}
+
+extern "C" int flx_comm_unique_id(uint8_t id[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId u;
+    ncclResult_t r = ncclGetUniqueId(&u);
+    if (r != ncclSuccess) { set_error("ncclGetUniqueId: %s", ncclGetErrorString(r)); return FLX_ERR_NCCL; }
+    memcpy(id, &u, 128);
+    return FLX_OK;
+}
+
+extern "C" int flx_comm_attach(flx_handle* h, const uint8_t id[128], int32_t rank, int32_t nranks) {
+    if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) { set_error("flx_comm_attach: bad arguments"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclResult_t r = ncclCommInitRank(&h->comm, nranks, u, rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", ncclGetErrorString(r)); h->comm = nullptr; return FLX_ERR_NCCL; }
+    h->nranks = nranks;
+    return FLX_OK;
+}
+
+extern "C" double flx_minp_threshold(const double* min_pval, int64_t P, double p_thr) {
+    if (!min_pval || P <= 0) return NAN;
+    std::vector<double> x(min_pval, min_pval + P);
+    std::sort(x.begin(), x.end());
+    const double hh = (double)(P - 1) * p_thr;
+    int64_t lo = (int64_t)std::floor(hh);
+    if (lo < 0) lo = 0;
+    if (lo > P - 1) lo = P - 1;
+    const int64_t hi = std::min(lo + 1, P - 1);
+    return x[lo] + (hh - (double)lo) * (x[hi] - x[lo]);
+}

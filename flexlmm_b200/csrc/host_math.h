@@ -1,0 +1,51 @@
+// host_math.h — host-side (C++) pieces of the hot path that are inherently sequential or once-per-task:
+// R-exact permutation indices, the QR of the SNP-independent design columns, .pgen record access.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace flx {
+
+// set.seed(seed); sample.int(m) — R >= 3.6 defaults (Mersenne-Twister, Inversion, Rejection).
+// fit_model.nf:97-98.  out: 1-based.
+void r_sample_int(int32_t seed, int64_t m, int32_t* out);
+
+// Orthonormal basis of the column space of C (n x nc, col-major, ld = n) with LINPACK dqrdc2's rank rule
+// (limited pivoting, tol 1e-7).  Returns rank r; Q: n x r (col-major); R: r x nc coordinates of ALL original
+// columns in that basis (col-major, ld = r).
+int orth_basis(const double* C, int64_t n, int nc, std::vector<double>& Q, std::vector<double>& R);
+
+// .pgen access for hard calls (pgenlibr::NewPgen / ReadHardcalls, fit_model.nf:39-40,123).
+class PgenFile {
+public:
+    ~PgenFile();
+    // returns "" on success, else an error message
+    std::string open(const char* path);
+    std::string open_memory(const uint8_t* data, int64_t len);  // not owned
+    uint32_t variant_ct() const { return variant_ct_; }
+    uint32_t sample_ct() const { return sample_ct_; }
+    int64_t bytes_per_variant() const { return ((int64_t)sample_ct_ + 3) / 4; }
+    int mode() const { return mode_; }
+    // If the file is mode 0x02 the records are already packed 2-bit: pointer to record v (0-based).
+    const uint8_t* fixed_record(uint32_t v) const { return data_ + 12 + (int64_t)v * bytes_per_variant(); }
+    // Expand variant v (0-based) to packed 2-bit (bytes_per_variant() bytes, pad bits 0). Any mode.
+    std::string read_packed(uint32_t v, uint8_t* out);
+private:
+    struct Rec { uint64_t off; uint32_t len; uint8_t vrtype; };
+    std::string parse();
+    std::string decode_main(const Rec& r, uint8_t* out) const;
+    std::string apply_difflist(const uint8_t*& p, const uint8_t* end, uint8_t* geno) const;
+    const uint8_t* data_ = nullptr;
+    int64_t len_ = 0;
+    bool mapped_ = false;
+    int fd_ = -1;
+    uint32_t variant_ct_ = 0, sample_ct_ = 0;
+    int mode_ = 0;
+    std::vector<Rec> recs_;           // mode 0x10
+    std::vector<uint32_t> ldbase_;    // mode 0x10: index of the LD base record for LD-compressed variants
+    int64_t cached_base_ = -1;
+    std::vector<uint8_t> base_geno_;
+};
+
+}  // namespace flx

@@ -1,0 +1,113 @@
+// kernels.h — launch interfaces of the sm_100a kernels (host side of csrc/*.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace flx {
+
+// ---------------------------------------------------------------- K2 / K4 (panel_gemm.cu)
+struct GemmArgs {
+    const double* A;          // packed panels (K2: triangular L^-1 by row tile; K4: W tiles)
+    const double* B;          // packed panels (K2: X tiles; K4: R permutation tiles)
+    double* Out;              // K2: packed W tiles
+    int64_t n_items;
+    int T;                    // K2: row tiles
+    int NJ;                   // design-column tiles in the batch
+    int NP;                   // K4: permutation tiles
+    int KC;                   // k-chunks (n_pad / 16)
+    // K4 epilogue
+    const int32_t* snp_df;    // per SNP in batch: lrt_df (0 => skip)
+    const double* snp_sm;     // per SNP: s(s+1)/2 packed symmetric matrix Sm, dSS = b' Sm b
+    const double* perm_inv_rss;  // per permutation column: 1 / RSS_f,p (0 for padding)
+    double* perm_maxratio;    // [s][P_pad] running max of dSS / RSS_f,p per (df, permutation)
+    int64_t P_pad;
+};
+int launch_whiten(const GemmArgs& g, int num_sms, cudaStream_t st);
+int launch_perm_contract(const GemmArgs& g, int s, int num_sms, cudaStream_t st);
+
+// ---------------------------------------------------------------- K1 (decode.cu)
+struct DecodeArgs {
+    const uint8_t* packed;    // device: 2-bit records of the batch's variants, record v at packed + v*bpv
+    int64_t bpv;              // bytes per variant record
+    const int32_t* vmap;      // device: record index of batch SNP q (nullptr => q)
+    const int32_t* order;     // device: 0-based raw sample index of model sample i (nullptr => identity)
+    int64_t n;                // model samples
+    int KC;                   // k-chunks (n_pad/16)
+    int64_t nsnp;             // SNPs in this batch
+    int64_t snp_offset;       // index of the batch's first SNP in the run (for missing_flag)
+    int s;                    // SNP-dependent terms
+    const double* lut;        // device: [s][3][n_pad] term value by genotype code and sample (nullptr if all uniform)
+    double uni[8][3];         // per term: value by code when the term is sample-independent
+    uint32_t uniform_mask;    // bit t set: term t uses uni[t][code]
+    int64_t n_pad;
+    double* X;                // out: packed X tiles of the batch
+    int NJ;                   // tiles in batch
+    int* missing_flag;        // out: atomicMin(run-wide index of a SNP holding a missing call); INT_MAX = none
+    uint8_t* codes_out;       // optional (tests): nsnp x n gathered codes
+};
+int launch_decode(const DecodeArgs& a, cudaStream_t st);
+
+// ---------------------------------------------------------------- K3 (snp_fit.cu)
+struct FitConst {
+    int n;                    // samples (N of logLik)
+    int s, k, cr;             // SNP terms, design columns, rank of the constant columns
+    int col_kind[24];         // model column j: >=0 -> constant column index (into Rc columns); <0 -> -(t+1) SNP term t
+    int ncf;                  // number of constant columns
+    double Rc[24 * 24];       // cr x ncf (column-major, ld = 24): coordinates of constant columns in the Qc basis
+    double qcy[24];           // Qc' y
+    double rss_f;             // || y - Qc Qc' y ||^2
+    double lrs0;              // log(RSS0 / rss_f), RSS0 from the given ll_null
+    int df_null;
+};
+struct GramArgs {
+    const double* W;          // packed W tiles of the batch
+    const double* Qc;         // device [n_pad][crp] row-major, crp = cr rounded up to 4, zero padded rows/cols
+    const double* r;          // device [n_pad] residual of y on Qc (zero padded)
+    int KC; int cr; int s;
+    int64_t nsnp;
+    // per SNP outputs
+    double* nrm2;             // [nsnp][s]      ||w_t||^2
+    double* u;                // [nsnp][s][cr]  Qc' w_t
+    double* Ag;               // [nsnp][s(s+1)/2] residualised Gram
+    double* b;                // [nsnp][s]      w_r' r
+};
+int launch_snp_gram(const GramArgs& a, cudaStream_t st);
+
+struct SolveArgs {
+    const double* nrm2; const double* u; const double* Ag; const double* b;
+    int64_t nsnp;
+    int64_t out_offset;       // first SNP of this batch in the run-wide outputs
+    // outputs (run-wide arrays)
+    double* chisq; double* pval; int32_t* df; int32_t* rank; int32_t* pivot; double* coef;  // pivot/coef: [M][k]
+    // batch-local outputs for K4
+    int32_t* snp_df; double* snp_sm;
+    int* df_count;            // [9] run-wide count of SNPs per lrt_df (1..8)
+};
+int upload_fit_const(const FitConst& c);
+int launch_snp_solve(const SolveArgs& a, cudaStream_t st);
+
+// ---------------------------------------------------------------- setup kernels (setup.cu)
+// dense column-major (n x ncols, ld) -> packed panel with k = row index, j = column index (tiles of 128 columns)
+int launch_pack_cols(const double* dense, int64_t n, int64_t ld, int64_t ncols, int KC, double* packed, cudaStream_t st);
+// packed panel tiles -> dense column-major
+int launch_unpack_cols(const double* packed, int64_t n, int64_t ld, int64_t ncols, int KC, double* dense, cudaStream_t st);
+// dense lower-triangular inverse Z (n x n col-major) -> triangular packed A panels (k = column of Z, j = row of Z)
+int launch_pack_tri(const double* Z, int64_t n, int64_t ld, int T, double* packed, cudaStream_t st);
+// Y[:, p] = y_pred + UE[:, p]  then  Rf[:, p] = Y - Qc Qc' Y ; rss_f[p] = ||Rf||^2 ; rss0[p] = || Y - Qn Qn' Y ||^2
+struct PermPrepArgs {
+    double* UE;               // in: U1 * E (n x P col-major, ld = n_pad) ; out: residual Rf (in place)
+    const double* y_pred;     // [n]
+    const double* Qc; int cr; // [n_pad][crp] row-major (crp = cr rounded up to 4)
+    const double* Qn; int cn; // [n_pad][cnp] row-major (null model basis)
+    int64_t n, n_pad; int P;
+    double* rss_f; double* rss0;  // [P]
+};
+int launch_perm_prep(const PermPrepArgs& a, cudaStream_t st);
+// E[j, p] = e_p[idx[p*m + j] - 1]
+int launch_gather_ep(const double* e_p, const int32_t* idx, int64_t m, int P, double* E, cudaStream_t st);
+// fill identity
+int launch_set_identity(double* Z, int64_t n, int64_t ld, cudaStream_t st);
+// finalize min-p: minp[p] = min over df of pchisq_upper(N*(lrs0p[p] - log1p(-maxratio[df][p])), df)
+int launch_minp_finalize(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp, cudaStream_t st);
+
+}  // namespace flx

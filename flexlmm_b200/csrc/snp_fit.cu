@@ -1,0 +1,510 @@
+// snp_fit.cu — K3: the per-SNP fit, LRT and chi-square tail (sm_100a).
+//
+// Replaces .lm.fit + stats:::logLik.lm + pchisq for every SNP (fit_model.nf:133-139) without ever
+// forming the n x k whitened design:
+//
+//   K3a snp_gram   (HBM-bound, one CTA per 8-SNP group, quad-per-SNP shuffle reductions)
+//        u_t = Qc' w_t,  ||w_t||^2                       (pass 1)
+//        w_r,t = w_t - Qc u_t ;  A = W_r' W_r ;  b = W_r' r   (pass 2, explicit residualisation)
+//        where Qc is an orthonormal basis of the whitened SNP-independent design columns and r the
+//        residual of y.mm on them.  Algorithmic bytes: 8 n s per SNP per pass.
+//   K3b snp_solve  (one thread per SNP, register/local k x k work)
+//        Every whitened design column is a vector of coordinates in the orthonormal basis [Qc, Qs]
+//        (Qs from the Cholesky of A), so the n x k least-squares problem equals a (cr+s) x k one.
+//        On that small matrix the kernel runs the SAME algorithm the reference runs on the n x k
+//        matrix: LINPACK dqrdc2 as modified for R (limited column pivoting, tol 1e-7, norm
+//        down-dating) and dqrsl.  Column norms are preserved by the change of basis, so rank, pivot
+//        and the pivoted coefficients follow the reference's rule, and
+//            lrt_chisq = 2 (ll - ll.null) = N [ log(RSS0/RSS_f) - log1p(-dSS/RSS_f) ]
+//        with dSS the drop in residual sum of squares due to the SNP columns.
+//        It also emits, per SNP, the symmetric matrix Sm with dSS(y*) = b*' Sm b* for ANY phenotype
+//        y* — what the permutation kernel K4 needs.
+#include <cmath>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace flx {
+
+__constant__ FitConst c_fit;
+
+int upload_fit_const(const FitConst& c) {
+    cudaError_t e = cudaMemcpyToSymbol(c_fit, &c, sizeof(FitConst));
+    if (e != cudaSuccess) { set_error("upload_fit_const: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3a
+// ------------------------------------------------------------------------------------------------
+constexpr int GRAM_WARPS = 4;
+constexpr int GRAM_THREADS = GRAM_WARPS * 32;
+constexpr int GRAM_JB = 8;
+
+template <int S>
+__global__ void __launch_bounds__(GRAM_THREADS) snp_gram_kernel(const GramArgs a) {
+    constexpr int NSYM = S * (S + 1) / 2;
+    const TileShape ts = make_tile_shape(S);
+    const int J = blockIdx.x / ts.groups;
+    const int gi = blockIdx.x % ts.groups;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 2, kp = lane & 3;
+    const int cr = a.cr;
+    const int crp = (cr + 3) & ~3;  // Qc row stride (padded to 4)
+    const double* wt = a.W + (int64_t)J * a.KC * CHUNK + ((S * gi) << 5) + lane;
+
+    extern __shared__ __align__(16) double sm[];
+    double* u_s = sm;                         // [8][S][crp]
+    double* red = sm + 8 * S * crp;           // [GRAM_WARPS][8][max(S*GRAM_JB, NSYM + S) ]
+    constexpr int REDW = (S * GRAM_JB > NSYM + 2 * S) ? S * GRAM_JB : NSYM + 2 * S;
+
+    // ---------------- pass 1: u = Qc' w in blocks of GRAM_JB basis vectors; column norms on the first sweep
+    double nrm[S];
+#pragma unroll
+    for (int t = 0; t < S; t++) nrm[t] = 0.0;
+    for (int jb = 0; jb < crp || jb == 0; jb += GRAM_JB) {
+        double acc[S][GRAM_JB];
+#pragma unroll
+        for (int t = 0; t < S; t++)
+#pragma unroll
+            for (int j = 0; j < GRAM_JB; j++) acc[t][j] = 0.0;
+        const int jn = min(GRAM_JB, crp - jb);  // multiple of 4 (or <= 0 when cr == 0)
+#pragma unroll 2
+        for (int kc = warp; kc < a.KC; kc += GRAM_WARPS) {
+            const double* wc = wt + (int64_t)kc * CHUNK;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+                const int64_t k = (int64_t)kc * KCH + 4 * ks + kp;
+                double w[S];
+#pragma unroll
+                for (int t = 0; t < S; t++) w[t] = wc[(ks * 16 + t) << 5];
+                if (jb == 0) {
+#pragma unroll
+                    for (int t = 0; t < S; t++) nrm[t] = fma(w[t], w[t], nrm[t]);
+                }
+                const double* q = a.Qc + k * crp + jb;
+                if (jn > 0) {
+                    const double2 q01 = __ldg(reinterpret_cast<const double2*>(q));
+                    const double2 q23 = __ldg(reinterpret_cast<const double2*>(q + 2));
+#pragma unroll
+                    for (int t = 0; t < S; t++) {
+                        acc[t][0] = fma(w[t], q01.x, acc[t][0]); acc[t][1] = fma(w[t], q01.y, acc[t][1]);
+                        acc[t][2] = fma(w[t], q23.x, acc[t][2]); acc[t][3] = fma(w[t], q23.y, acc[t][3]);
+                    }
+                }
+                if (jn > 4) {
+                    const double2 q45 = __ldg(reinterpret_cast<const double2*>(q + 4));
+                    const double2 q67 = __ldg(reinterpret_cast<const double2*>(q + 6));
+#pragma unroll
+                    for (int t = 0; t < S; t++) {
+                        acc[t][4] = fma(w[t], q45.x, acc[t][4]); acc[t][5] = fma(w[t], q45.y, acc[t][5]);
+                        acc[t][6] = fma(w[t], q67.x, acc[t][6]); acc[t][7] = fma(w[t], q67.y, acc[t][7]);
+                    }
+                }
+            }
+        }
+        // reduce over the 4 sample phases of the quad, then across warps through shared memory
+#pragma unroll
+        for (int t = 0; t < S; t++)
+#pragma unroll
+            for (int j = 0; j < GRAM_JB; j++) {
+                double v = acc[t][j];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (kp == 0) red[(warp * 8 + grp) * REDW + t * GRAM_JB + j] = v;
+            }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 8 * S * GRAM_JB; e += GRAM_THREADS) {
+            const int g8 = e / (S * GRAM_JB), rem = e % (S * GRAM_JB);
+            const int t = rem / GRAM_JB, j = rem % GRAM_JB;
+            if (jb + j < crp) {
+                double v = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < GRAM_WARPS; w2++) v += red[(w2 * 8 + g8) * REDW + rem];
+                u_s[(g8 * S + t) * crp + jb + j] = v;
+            }
+        }
+        __syncthreads();
+        if (crp == 0) break;
+    }
+
+    // ---------------- pass 2: explicit residualisation, Gram and right-hand side
+    double ag[NSYM], bb[S];
+#pragma unroll
+    for (int q = 0; q < NSYM; q++) ag[q] = 0.0;
+#pragma unroll
+    for (int t = 0; t < S; t++) bb[t] = 0.0;
+    const double* ug = u_s + (grp * S) * crp;
+#pragma unroll 2
+    for (int kc = warp; kc < a.KC; kc += GRAM_WARPS) {
+        const double* wc = wt + (int64_t)kc * CHUNK;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            const int64_t k = (int64_t)kc * KCH + 4 * ks + kp;
+            double w[S];
+#pragma unroll
+            for (int t = 0; t < S; t++) w[t] = wc[(ks * 16 + t) << 5];
+            const double* q = a.Qc + k * crp;
+            for (int j = 0; j < crp; j += 2) {
+                const double2 qq = __ldg(reinterpret_cast<const double2*>(q + j));
+#pragma unroll
+                for (int t = 0; t < S; t++) {
+                    const double2 uu = *reinterpret_cast<const double2*>(ug + t * crp + j);
+                    w[t] = fma(-qq.x, uu.x, w[t]);
+                    w[t] = fma(-qq.y, uu.y, w[t]);
+                }
+            }
+            const double rk = __ldg(a.r + k);
+            int qi = 0;
+#pragma unroll
+            for (int t = 0; t < S; t++) {
+                bb[t] = fma(w[t], rk, bb[t]);
+#pragma unroll
+                for (int v = t; v < S; v++) { ag[qi] = fma(w[t], w[v], ag[qi]); qi++; }
+            }
+        }
+    }
+    // reduce: quad lanes, then warps
+#pragma unroll
+    for (int q = 0; q < NSYM + 2 * S; q++) {
+        double v = (q < NSYM) ? ag[q < NSYM ? q : 0] : (q < NSYM + S ? bb[(q - NSYM) < S ? (q - NSYM) : 0] : nrm[(q - NSYM - S) < S ? (q - NSYM - S) : 0]);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (kp == 0) red[(warp * 8 + grp) * REDW + q] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 8 * (NSYM + 2 * S); e += GRAM_THREADS) {
+        const int g8 = e / (NSYM + 2 * S), q = e % (NSYM + 2 * S);
+        const int64_t snp = (int64_t)J * ts.snps + 8 * gi + g8;
+        if (snp < a.nsnp) {
+            double v = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < GRAM_WARPS; w2++) v += red[(w2 * 8 + g8) * REDW + q];
+            if (q < NSYM) a.Ag[snp * NSYM + q] = v;
+            else if (q < NSYM + S) a.b[snp * S + (q - NSYM)] = v;
+            else a.nrm2[snp * S + (q - NSYM - S)] = v;
+        }
+    }
+    for (int e = threadIdx.x; e < 8 * S * cr; e += GRAM_THREADS) {
+        const int g8 = e / (S * cr), rem = e % (S * cr);
+        const int t = rem / cr, j = rem % cr;
+        const int64_t snp = (int64_t)J * ts.snps + 8 * gi + g8;
+        if (snp < a.nsnp) a.u[(snp * S + t) * cr + j] = u_s[(g8 * S + t) * crp + j];
+    }
+}
+
+template <int S>
+static int launch_gram_s(const GramArgs& a, cudaStream_t st) {
+    constexpr int NSYM = S * (S + 1) / 2;
+    constexpr int REDW = (S * GRAM_JB > NSYM + 2 * S) ? S * GRAM_JB : NSYM + 2 * S;
+    const TileShape ts = make_tile_shape(S);
+    const int crp = (a.cr + 3) & ~3;
+    const int64_t NJ = (a.nsnp + ts.snps - 1) / ts.snps;
+    const size_t smem = sizeof(double) * (8 * S * crp + GRAM_WARPS * 8 * REDW);
+    snp_gram_kernel<S><<<(unsigned)(NJ * ts.groups), GRAM_THREADS, smem, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("snp_gram launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+int launch_snp_gram(const GramArgs& a, cudaStream_t st) {
+    if (a.nsnp <= 0) return 0;
+    switch (a.s) {
+        case 1: return launch_gram_s<1>(a, st);
+        case 2: return launch_gram_s<2>(a, st);
+        case 3: return launch_gram_s<3>(a, st);
+        case 4: return launch_gram_s<4>(a, st);
+        case 5: return launch_gram_s<5>(a, st);
+        case 6: return launch_gram_s<6>(a, st);
+        case 7: return launch_gram_s<7>(a, st);
+        case 8: return launch_gram_s<8>(a, st);
+    }
+    set_error("snp_gram: unsupported s=%d", a.s);
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chi-square upper tail for integer df (pchisq(q, df, lower.tail = FALSE), fit_model.nf:138)
+// ------------------------------------------------------------------------------------------------
+__device__ double chisq_upper_tail(double q, int df) {
+    if (df <= 0 || isnan(q)) return nan("");
+    if (q <= 0.0) return 1.0;
+    const double h = 0.5 * q;
+    if ((df & 1) == 0) {
+        double term = 1.0, sum = 1.0;
+        for (int i = 1; i < df / 2; i++) { term *= h / i; sum += term; }
+        return exp(-h) * sum;
+    }
+    const double tail = erfc(sqrt(h));
+    const int j = (df - 1) / 2;
+    if (j == 0) return tail;
+    double term = 1.0, sum = 1.0;
+    for (int i = 1; i < j; i++) { term *= q / (2 * i + 1); sum += term; }
+    return tail + exp(-h) * sqrt(2.0 * q / 3.14159265358979323846) * sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXK = 24;
+constexpr int MAXS = 8;
+constexpr int LDT = MAXK + 1;
+
+// Apply Householder reflector l (stored LINPACK style: v = column l of T from row l, with T[l][l] replaced by qraux[l])
+__device__ __forceinline__ void apply_reflector(const double* T, const double* qraux, int l, int nrow, double* v) {
+    if (qraux[l] == 0.0) return;
+    const double* x = T + l * LDT;
+    double t = qraux[l] * v[l];
+    for (int i = l + 1; i < nrow; i++) t += x[i] * v[i];
+    t = -t / qraux[l];
+    v[l] += t * qraux[l];
+    for (int i = l + 1; i < nrow; i++) v[i] += t * x[i];
+}
+
+__global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
+    const int64_t snp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (snp >= a.nsnp) return;
+    const FitConst& c = c_fit;
+    const int s = c.s, k = c.k, cr = c.cr;
+    const int nr = cr + s;
+    const int nrow = nr + 1;  // one zero row: the small problem must behave like n > p (dqrdc2's l == n exit never fires)
+    const int nsym = s * (s + 1) / 2;
+
+    double A[MAXS][MAXS], Rs[MAXS][MAXS], Mq[MAXS][MAXS];
+    double bq[MAXS], qsr[MAXS], nrm2[MAXS];
+    bool alive[MAXS];
+    {
+        int q = 0;
+        for (int t = 0; t < s; t++)
+            for (int v = t; v < s; v++) { A[t][v] = A[v][t] = a.Ag[snp * nsym + q]; q++; }
+        for (int t = 0; t < s; t++) { bq[t] = a.b[snp * s + t]; nrm2[t] = a.nrm2[snp * s + t]; }
+    }
+    // guarded Cholesky A = Rs' Rs in term order; a vanished pivot leaves a zero row (direction dropped)
+    for (int l = 0; l < s; l++) {
+        double d = A[l][l];
+        for (int i = 0; i < l; i++) d -= Rs[i][l] * Rs[i][l];
+        alive[l] = (d > 0.0) && (d > 1e-22 * nrm2[l]);
+        for (int j = 0; j < s; j++) Rs[l][j] = 0.0;
+        if (alive[l]) {
+            const double rll = sqrt(d);
+            Rs[l][l] = rll;
+            for (int j = l + 1; j < s; j++) {
+                double v = A[l][j];
+                for (int i = 0; i < l; i++) v -= Rs[i][l] * Rs[i][j];
+                Rs[l][j] = v / rll;
+            }
+        }
+    }
+    // Mq: q = Rs^-T b as a linear map (lower triangular), qsr = Mq b
+    for (int l = 0; l < s; l++) {
+        for (int cidx = 0; cidx < s; cidx++) Mq[l][cidx] = 0.0;
+        if (alive[l]) {
+            for (int cidx = 0; cidx <= l; cidx++) {
+                double v = (cidx == l) ? 1.0 : 0.0;
+                for (int i = cidx; i < l; i++) v -= Rs[i][l] * Mq[i][cidx];
+                Mq[l][cidx] = v / Rs[l][l];
+            }
+        }
+    }
+    double qq = 0.0;
+    for (int l = 0; l < s; l++) {
+        double v = 0.0;
+        for (int cidx = 0; cidx <= l; cidx++) v += Mq[l][cidx] * bq[cidx];
+        qsr[l] = v;
+        qq += v * v;
+    }
+
+    // ---- the small design T (nrow x k, column-major, ld LDT) and response ty
+    double T[MAXK * LDT];
+    double ty[LDT];
+    for (int j = 0; j < k; j++) {
+        double* col = T + j * LDT;
+        for (int i = 0; i < nrow; i++) col[i] = 0.0;
+        const int kind = c.col_kind[j];
+        if (kind >= 0) {
+            for (int i = 0; i < cr; i++) col[i] = c.Rc[i + kind * MAXK];
+        } else {
+            const int t = -kind - 1;
+            for (int i = 0; i < cr; i++) col[i] = a.u[(snp * s + t) * cr + i];
+            for (int i = 0; i <= t; i++) col[cr + i] = Rs[i][t];
+        }
+    }
+    for (int i = 0; i < cr; i++) ty[i] = c.qcy[i];
+    for (int i = 0; i < s; i++) ty[cr + i] = qsr[i];
+    ty[nr] = 0.0;
+
+    // ---- dqrdc2 (R's LINPACK variant): limited column pivoting with tol = 1e-7
+    const double tol = 1e-7;
+    double qraux[MAXK], w1[MAXK], w2[MAXK];
+    int jpvt[MAXK];
+    for (int j = 0; j < k; j++) {
+        double ss = 0.0;
+        for (int i = 0; i < nrow; i++) ss += T[i + j * LDT] * T[i + j * LDT];
+        qraux[j] = sqrt(ss);
+        w1[j] = qraux[j];
+        w2[j] = (qraux[j] == 0.0) ? 1.0 : qraux[j];
+        jpvt[j] = j + 1;
+    }
+    const int lup = (nrow < k) ? nrow : k;
+    int kk = k + 1;
+    for (int l = 1; l <= lup; l++) {
+        while (l < kk && qraux[l - 1] < w2[l - 1] * tol) {
+            // rotate column l to the end
+            for (int i = 0; i < nrow; i++) {
+                const double t = T[i + (l - 1) * LDT];
+                for (int j = l; j < k; j++) T[i + (j - 1) * LDT] = T[i + j * LDT];
+                T[i + (k - 1) * LDT] = t;
+            }
+            const int ii = jpvt[l - 1];
+            const double t0 = qraux[l - 1], t1 = w1[l - 1], t2 = w2[l - 1];
+            for (int j = l; j < k; j++) { jpvt[j - 1] = jpvt[j]; qraux[j - 1] = qraux[j]; w1[j - 1] = w1[j]; w2[j - 1] = w2[j]; }
+            jpvt[k - 1] = ii; qraux[k - 1] = t0; w1[k - 1] = t1; w2[k - 1] = t2;
+            kk--;
+        }
+        if (l == nrow) break;
+        double* xl = T + (l - 1) * LDT;
+        double ss = 0.0;
+        for (int i = l - 1; i < nrow; i++) ss += xl[i] * xl[i];
+        double nrmxl = sqrt(ss);
+        if (nrmxl == 0.0) continue;
+        if (xl[l - 1] != 0.0) nrmxl = copysign(nrmxl, xl[l - 1]);
+        const double sc = 1.0 / nrmxl;
+        for (int i = l - 1; i < nrow; i++) xl[i] *= sc;
+        xl[l - 1] += 1.0;
+        for (int j = l + 1; j <= k; j++) {
+            double* xj = T + (j - 1) * LDT;
+            double dot = 0.0;
+            for (int i = l - 1; i < nrow; i++) dot += xl[i] * xj[i];
+            const double t = -dot / xl[l - 1];
+            for (int i = l - 1; i < nrow; i++) xj[i] += t * xl[i];
+            if (qraux[j - 1] != 0.0) {
+                const double r = fabs(xj[l - 1]) / qraux[j - 1];
+                double tt = 1.0 - r * r;
+                if (tt < 0.0) tt = 0.0;
+                if (fabs(tt) < 1e-6) {
+                    double s2 = 0.0;
+                    for (int i = l; i < nrow; i++) s2 += xj[i] * xj[i];
+                    qraux[j - 1] = sqrt(s2);
+                    w1[j - 1] = qraux[j - 1];
+                } else {
+                    qraux[j - 1] *= sqrt(tt);
+                }
+            }
+        }
+        qraux[l - 1] = xl[l - 1];
+        xl[l - 1] = -nrmxl;
+    }
+    int rank = kk - 1;
+    if (rank > nrow) rank = nrow;
+
+    // ---- dqrsl: qty, coefficients (pivoted order)
+    const int ju = (rank < nrow - 1) ? rank : nrow - 1;
+    for (int l = 0; l < ju; l++) apply_reflector(T, qraux, l, nrow, ty);
+    double coef[MAXK];
+    for (int j = 0; j < k; j++) coef[j] = (j < rank) ? ty[j] : 0.0;
+    for (int j = rank - 1; j >= 0; j--) {
+        const double d = T[j + j * LDT];
+        if (d == 0.0) break;
+        coef[j] /= d;
+        const double t = -coef[j];
+        for (int i = 0; i < j; i++) coef[i] += t * T[i + j * LDT];
+    }
+    double rss_small = 0.0;
+    for (int i = rank; i < nr; i++) rss_small += ty[i] * ty[i];
+
+    // ---- LRT
+    double dss = qq - rss_small;
+    if (dss < 0.0) dss = 0.0;
+    const double ratio = dss / c.rss_f;
+    const double N = (double)c.n;
+    const double chisq = N * (c.lrs0 - log1p(-ratio));
+    const int df = rank + 1 - c.df_null;
+    const double p = (df > 0) ? chisq_upper_tail(chisq, df) : nan("");
+
+    const int64_t o = a.out_offset + snp;
+    a.chisq[o] = chisq;
+    a.pval[o] = p;
+    a.df[o] = df;
+    a.rank[o] = rank;
+    for (int j = 0; j < k; j++) {
+        a.pivot[o * k + j] = jpvt[j];
+        a.coef[o * k + j] = coef[j];
+    }
+
+    // ---- Sm for the permutation kernel: dSS(y*) = q*' (I - N N') q*, q* = Mq b*, N = rows >= rank of H' restricted to the Qs block
+    if (a.snp_sm) {
+        double G[MAXS][MAXS];
+        for (int i = 0; i < s; i++)
+            for (int j = 0; j < s; j++) G[i][j] = (i == j) ? 1.0 : 0.0;
+        if (rank < nr) {
+            double Nm[MAXS][MAXS + MAXK];  // [i][row - rank]
+            const int nn = nr - rank;
+            for (int i = 0; i < s; i++) {
+                double v[LDT];
+                for (int r2 = 0; r2 < nrow; r2++) v[r2] = 0.0;
+                v[cr + i] = 1.0;
+                for (int l = 0; l < ju; l++) apply_reflector(T, qraux, l, nrow, v);
+                for (int r2 = 0; r2 < nn; r2++) Nm[i][r2] = v[rank + r2];
+            }
+            for (int i = 0; i < s; i++)
+                for (int j = 0; j < s; j++) {
+                    double v = 0.0;
+                    for (int r2 = 0; r2 < nn; r2++) v += Nm[i][r2] * Nm[j][r2];
+                    G[i][j] -= v;
+                }
+        }
+        // Sm = Mq' G Mq
+        double GM[MAXS][MAXS];
+        for (int i = 0; i < s; i++)
+            for (int j = 0; j < s; j++) {
+                double v = 0.0;
+                for (int l = 0; l < s; l++) v += G[i][l] * Mq[l][j];
+                GM[i][j] = v;
+            }
+        int q = 0;
+        for (int t = 0; t < s; t++)
+            for (int v2 = t; v2 < s; v2++) {
+                double v = 0.0;
+                for (int l = 0; l < s; l++) v += Mq[l][t] * GM[l][v2];
+                a.snp_sm[snp * nsym + q] = (df > 0) ? v : 0.0;
+                q++;
+            }
+        a.snp_df[snp] = df > 0 ? df : 0;
+    }
+    if (a.df_count && df > 0 && df <= MAXS) atomicAdd(&a.df_count[df], 1);
+}
+
+int launch_snp_solve(const SolveArgs& a, cudaStream_t st) {
+    if (a.nsnp <= 0) return 0;
+    const int threads = 64;
+    snp_solve_kernel<<<(unsigned)((a.nsnp + threads - 1) / threads), threads, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("snp_solve launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// min-p finalisation: one thread per permutation
+// ------------------------------------------------------------------------------------------------
+__global__ void minp_finalize_kernel(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double best = 2.0;  // "an impossibly large value" (fit_model.nf:104)
+    for (int t = 0; t < s; t++) {
+        const double mr = maxratio[(int64_t)t * P_pad + p];
+        if (df_count[t + 1] == 0) continue;  // no SNP with this df in the run
+        const double chisq = N * (lrs0p[p] - log1p(-mr));
+        const double pv = chisq_upper_tail(chisq, t + 1);
+        if (pv < best) best = pv;
+    }
+    minp[p] = best;
+}
+
+int launch_minp_finalize(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp, cudaStream_t st) {
+    if (P <= 0) return 0;
+    minp_finalize_kernel<<<(P + 127) / 128, 128, 0, st>>>(maxratio, P_pad, P, s, lrs0p, N, df_count, minp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("minp_finalize launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+}  // namespace flx

@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's FIT_MODEL process (/root/reference/modules/local/r/fit_model.nf).
+
+Same inputs (whitened y / null design / Cholesky factor from DECORRELATE, null fit from FIT_NULL_MODEL, variant
+indices, the real model as a genotype lookup, pgen + sample order, permutation seeds), same outputs (per-SNP
+`chr pos id ref alt lrt_chisq lrt_df pval beta` table, per-permutation `seed chr min_pval nvars` lines).  All
+numerical work happens in libflexlmm_cuda.so through the C ABI; nothing here computes on the CPU.
+"""
+import ctypes as C
+import gzip
+
+import numpy as np
+
+from . import _capi
+from ._capi import FlxConfig, FlxSnpOut, FlxStats, check, f64, ptr
+
+
+def perm_indices(seed, m):
+    """R's `set.seed(seed); sample.int(m)` (fit_model.nf:97-98), 1-based int32."""
+    out = np.empty(int(m), dtype=np.int32)
+    check(_capi.load().flx_perm_indices(int(seed), int(m), out.ctypes.data))
+    return out
+
+
+def minp_threshold(min_pval, p_thr=0.05):
+    """quantile(min_pval, p_thr), R type 7 — the Westfall-Young threshold (make_plots.nf:31)."""
+    x = f64(min_pval)
+    return _capi.load().flx_minp_threshold(x.ctypes.data, x.size, float(p_thr))
+
+
+class FitModel:
+    """One FIT_MODEL task bound to one B200.  Method order mirrors the R script: inputs (:30-66), then run (:120-171)."""
+
+    def __init__(self, device=0, batch_tiles=0, verbose=0):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        cfg = FlxConfig(int(device), int(batch_tiles), int(verbose), 0)
+        check(self._lib.flx_create(C.byref(cfg), C.byref(self._h)))
+        self._keep = {}
+        self.n = None
+        self.k = None
+        self.P = 0
+
+    def close(self):
+        if self._h:
+            self._lib.flx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs
+    def set_whitening(self, L, is_inverse=False):
+        """L = l.mm[["L"]] (fit_model.nf:61), lower Cholesky factor of the phenotype covariance."""
+        L = f64(L, fortran=True)
+        assert L.ndim == 2 and L.shape[0] == L.shape[1]
+        self.n = L.shape[0]
+        check(self._lib.flx_set_whitening(self._h, ptr(L), self.n, self.n, int(bool(is_inverse))))
+
+    def set_null(self, X_null, y_mm, ll_null, df_null):
+        """X.mm, y.mm (fit_model.nf:59-60) and ll.null with attr df (fit_model.nf:63)."""
+        X = f64(X_null, fortran=True).reshape(self.n, -1, order="F")
+        y = f64(y_mm)
+        check(self._lib.flx_set_null(self._h, ptr(X), X.shape[1], ptr(y), float(ll_null), int(df_null)))
+
+    def set_design(self, M0, M1, M2):
+        """model.matrix(model[-2], .) evaluated with x = 0, 1, 2 (fit_model.nf:124-127)."""
+        M0, M1, M2 = (f64(m, fortran=True) for m in (M0, M1, M2))
+        self.k = M0.shape[1]
+        self.s = int(sum(not (np.array_equal(M0[:, j], M1[:, j]) and np.array_equal(M0[:, j], M2[:, j])) for j in range(self.k)))
+        check(self._lib.flx_set_design(self._h, ptr(M0), ptr(M1), ptr(M2), self.k))
+
+    def set_perm(self, y_pred, U1, e_p, seeds):
+        """y.mm.pred, U1, e.p (fit_model.nf:64-66) and the seeds (workflows/flexlmm.nf:67)."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        self.P = int(seeds.size)
+        if self.P == 0:
+            check(self._lib.flx_set_perm(self._h, None, None, None, 0, None, 0))
+            return
+        y_pred = f64(y_pred); U1 = f64(U1, fortran=True); e_p = f64(np.ravel(e_p))
+        check(self._lib.flx_set_perm(self._h, ptr(y_pred), ptr(U1), ptr(e_p), e_p.size, ptr(seeds), self.P))
+
+    def open_pgen(self, path, pgen_order=None, n=None):
+        """pgenlibr::NewPgen + match(samples, psam$IID) (fit_model.nf:40,70). pgen_order is 1-based."""
+        n = self.n if n is None else n
+        po = None if pgen_order is None else np.ascontiguousarray(pgen_order, dtype=np.int32)
+        check(self._lib.flx_open_pgen(self._h, str(path).encode(), ptr(po), int(n)))
+
+    def set_packed(self, packed, raw_sample_ct, pgen_order=None, n=None):
+        """Packed 2-bit records (M_total x bytes_per_variant uint8) already in host memory."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        assert packed.ndim == 2
+        n = self.n if n is None else n
+        po = None if pgen_order is None else np.ascontiguousarray(pgen_order, dtype=np.int32)
+        self._keep["packed"] = packed  # the library reads it during run
+        check(self._lib.flx_set_packed(self._h, ptr(packed), packed.shape[0], packed.shape[1], int(raw_sample_ct), ptr(po), int(n)))
+
+    def make_resident(self):
+        check(self._lib.flx_make_resident(self._h))
+
+    def comm_attach(self, unique_id, rank, nranks):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        check(self._lib.flx_comm_attach(self._h, ptr(uid), int(rank), int(nranks)))
+
+    # ---- the hot loop
+    def run(self, var_idx, per_snp=True, minp=None):
+        """var_idx: 1-based variant numbers (get_var_idx.nf:34-35).  Returns a dict."""
+        var_idx = np.ascontiguousarray(var_idx, dtype=np.int32)
+        M = var_idx.size
+        res = {}
+        out = None
+        if per_snp:
+            res = dict(lrt_chisq=np.empty(M), pval=np.empty(M), lrt_df=np.empty(M, dtype=np.int32), rank=np.empty(M, dtype=np.int32),
+                       pivot=np.empty((M, self.k), dtype=np.int32), coef=np.empty((M, self.k)))
+            out = FlxSnpOut(*(res[f].ctypes.data for f in ("lrt_chisq", "pval", "lrt_df", "rank", "pivot", "coef")))
+        want_minp = (self.P > 0) if minp is None else bool(minp)
+        mp = np.empty(self.P) if want_minp else None
+        nv = C.c_int64(0)
+        check(self._lib.flx_run(self._h, ptr(var_idx), M, C.byref(out) if out is not None else None, ptr(mp), C.byref(nv)))
+        res["nvars_tested"] = nv.value
+        if want_minp:
+            res["min_pval"] = mp
+        return res
+
+    def stats(self):
+        st = FlxStats()
+        check(self._lib.flx_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    # ---- test hooks
+    def decode_tile(self, var_idx, want_X=True, want_codes=True):
+        var_idx = np.ascontiguousarray(var_idx, dtype=np.int32)
+        M = var_idx.size
+        X = np.empty((self.n, M * self.s), order="F") if want_X else None
+        codes = np.empty((M, self.n), dtype=np.uint8) if want_codes else None
+        check(self._lib.flx_decode_tile(self._h, ptr(var_idx), M, ptr(X), ptr(codes)))
+        return X, codes
+
+    def whiten(self, X):
+        X = f64(X, fortran=True).reshape(self.n, -1, order="F")
+        W = np.empty_like(X, order="F")
+        check(self._lib.flx_whiten(self._h, ptr(X), X.shape[1], ptr(W)))
+        return W
+
+
+def _r_num(x):
+    """as.character(<double>) as used by sprintf("%s", .) in fit_model.nf:157-168: 15 significant digits."""
+    if np.isnan(x):
+        return "NA"
+    if np.isinf(x):
+        return "Inf" if x > 0 else "-Inf"
+    if x == int(x) and abs(x) < 1e15:
+        return str(int(x))
+    s = f"{x:.15g}"
+    if "e" in s:
+        mant, exp = s.split("e")
+        sign = exp[0] if exp[0] in "+-" else "+"
+        digits = exp.lstrip("+-").lstrip("0") or "0"
+        s = f"{mant}e{sign}{int(digits):02d}"
+    return s
+
+
+def write_gwas_tsv(path, pvar_rows, colnames, res):
+    """ORIG-mode output (fit_model.nf:112-116,145-169): header + one line per SNP, gz."""
+    with gzip.open(path, "wt") as f:
+        f.write("chr\tpos\tid\tref\talt\tlrt_chisq\tlrt_df\tpval\tbeta\n")
+        for i, (chrom, pos, vid, ref, alt) in enumerate(pvar_rows):
+            beta = ",".join(f"{nm}~{_r_num(c)}" for nm, c in zip(colnames, res["coef"][i]))
+            f.write("\t".join([str(chrom), str(pos), str(vid), str(ref), str(alt), _r_num(res["lrt_chisq"][i]),
+                               str(int(res["lrt_df"][i])), _r_num(res["pval"][i]), beta]) + "\n")
+
+
+def write_perm_tsv(path, seeds, chrom, min_pval, nvars):
+    """PERM-mode output (fit_model.nf:176-181): one headerless line per seed; CAT_PERM concatenates gz members."""
+    with gzip.open(path, "wt") as f:
+        for sd, mp in zip(seeds, min_pval):
+            if not (0 <= mp <= 1):
+                raise ValueError("min_pval outside [0, 1] (fit_model.nf:177 stopifnot)")
+            f.write(f"{int(sd)}\t{chrom}\t{_r_num(mp)}\t{int(nvars)}\n")
+
+
+def fit_model_task(L, y_mm, X_null, ll_null, df_null, M0, M1, M2, var_idx, pgen=None, packed=None, raw_sample_ct=None,
+                   pgen_order=None, y_pred=None, U1=None, e_p=None, seeds=(), device=0, per_snp=True):
+    """One call = FIT_MODEL_ORIG plus every FIT_MODEL_PERM task of a (chromosome, phenotype) pair (lmm.nf:47-71)."""
+    with FitModel(device=device) as fm:
+        fm.set_whitening(L)
+        fm.set_null(X_null, y_mm, ll_null, df_null)
+        fm.set_design(M0, M1, M2)
+        if len(seeds):
+            fm.set_perm(y_pred, U1, e_p, seeds)
+        if pgen is not None:
+            fm.open_pgen(pgen, pgen_order)
+        else:
+            fm.set_packed(packed, raw_sample_ct, pgen_order)
+        return fm.run(var_idx, per_snp=per_snp)

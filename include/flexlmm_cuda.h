@@ -1,0 +1,149 @@
+/*
+ * flexlmm_cuda.h — C ABI of the B200-native per-SNP likelihood-ratio-test engine.
+ *
+ * This is the drop-in boundary for the hot loop of birneylab/flexlmm's FIT_MODEL process
+ * (/root/reference/modules/local/r/fit_model.nf:96-181).  The R script of that process keeps all
+ * file I/O (readRDS, pvar/psam parsing, TSV writing) and calls these entry points through a thin
+ * .Call shim (flexlmm_b200/r/r_shim.c); INTEGRATION.md shows the binding.  Everything here is
+ * plain C: host pointers, sizes, column-major FP64 matrices exactly as R stores them, 1-based
+ * indices where R uses them.  No torch types, no C++ in the signatures.
+ *
+ * Status codes: 0 = ok; negative = error, message available from flx_last_error().
+ * Error semantics follow the reference: a missing hard call in a tested variant is fatal
+ * (fit_model.nf:126-128 aborts in forwardsolve after model.frame drops the NA row).
+ *
+ * Thread model: one caller thread per handle; a handle owns one CUDA device, its streams and
+ * (optionally) one NCCL communicator.
+ */
+#ifndef FLEXLMM_CUDA_H
+#define FLEXLMM_CUDA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLX_OK                    0
+#define FLX_ERR_BAD_ARG          -1
+#define FLX_ERR_MISSING_GENOTYPE -2   /* NA hard call in a tested variant: the reference aborts */
+#define FLX_ERR_CUDA             -3
+#define FLX_ERR_NCCL             -4
+#define FLX_ERR_OOM              -5
+#define FLX_ERR_PGEN             -6   /* unreadable / unsupported .pgen */
+#define FLX_ERR_STATE            -7   /* call order violated (e.g. run before set_design) */
+#define FLX_ERR_NO_DEVICE        -8   /* no CUDA device: there is NO CPU fallback */
+
+#define FLX_MAX_K   24   /* design columns of the real model (k)            */
+#define FLX_MAX_S    8   /* SNP-dependent design columns (s)                */
+
+typedef struct flx_handle flx_handle;
+
+typedef struct {
+    int32_t device;            /* CUDA device ordinal                                                  */
+    int32_t batch_tiles;       /* column tiles (128 design columns each) per batch; 0 = auto (SM count)*/
+    int32_t verbose;           /* 1: timing lines on stderr                                            */
+    int32_t reserved;
+} flx_config;
+
+/* Per-SNP results in var_idx order, structure-of-arrays (what the R shim hands back as vectors / a k x M
+ * matrix).  Mirrors the ORIG-mode TSV columns lrt_chisq, lrt_df, pval, beta (fit_model.nf:112-116,145-169):
+ *   coef are the .lm.fit coefficients in PIVOTED order exactly as the reference pastes them against the
+ *   unpivoted column names (fit_model.nf:150-155); pivot is 1-based like R's fit$pivot.
+ * Any pointer may be NULL (that output is skipped).  pivot / coef: k values per SNP, SNP-major (R: k x M). */
+typedef struct {
+    double*  lrt_chisq;        /* [M]                                                                  */
+    double*  pval;             /* [M] NaN when lrt_df <= 0 (R NA, fit_model.nf:138)                    */
+    int32_t* lrt_df;           /* [M]                                                                  */
+    int32_t* rank;             /* [M]                                                                  */
+    int32_t* pivot;            /* [M*k]                                                                */
+    double*  coef;             /* [M*k]                                                                */
+} flx_snp_out;
+
+/* Timings and counters of the last flx_run*, for bench.py (device times from CUDA events, ms). */
+typedef struct {
+    double ms_total;           /* whole flx_run* call on the device stream                             */
+    double ms_decode;          /* K1  decode_2bit_tile                                                 */
+    double ms_whiten;          /* K2  whiten_tile (L^-1 . X)                                           */
+    double ms_fit;             /* K3  snp_gram + snp_solve                                             */
+    double ms_perm;            /* K4  perm_contract_minp                                               */
+    double ms_h2d;             /* host->device copies inside the call                                  */
+    double ms_d2h;             /* device->host copies inside the call                                  */
+    int64_t launches;          /* kernels launched by this library inside the call                     */
+    int64_t launches_whiten;
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t snps;
+    int64_t n_pad;
+    int64_t cols_per_tile;     /* design columns actually used per 128-wide tile                       */
+} flx_stats;
+
+const char* flx_last_error(void);
+const char* flx_version(void);
+int  flx_device_count(void);
+
+/* fit_model.nf:30-32,56-66 — create / destroy the per-task state. */
+int  flx_create(const flx_config* cfg, flx_handle** out);
+void flx_destroy(flx_handle* h);
+
+/* L of l.mm[["L"]] (fit_model.nf:61; decorrelate.nf:57,77): n x n column-major, lower triangle used,
+ * exactly what forwardsolve(L, X) reads (fit_model.nf:128).  is_inverse != 0: the matrix already is L^-1. */
+int  flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse);
+
+/* y.mm, X.mm (null design, whitened) and the null log-likelihood with its df attribute
+ * (fit_model.nf:59-60,63; fit_null_model.nf:33-34,72).  df_null = attr(ll, "df") = rank + 1. */
+int  flx_set_null(flx_handle* h, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null);
+
+/* The real model's design as a genotype lookup (fit_model.nf:124-127): M0/M1/M2 are
+ * model.matrix(model[-2], model.frame(...)) evaluated with x == 0, 1, 2 on every row, n x k column-major,
+ * columns in model.matrix order.  Columns identical in all three are SNP-independent. */
+int  flx_set_design(flx_handle* h, const double* M0, const double* M1, const double* M2, int32_t k);
+
+/* Permutation inputs (fit_model.nf:64-66,96-101): y.mm.pred (n), U1 (n x m col-major), e.p (m) and the
+ * permutation seeds (workflows/flexlmm.nf:67: 1..P).  Index order is R's set.seed(seed); sample(e.p). */
+int  flx_set_perm(flx_handle* h, const double* y_pred, const double* U1, const double* e_p, int64_t m,
+                  const int32_t* seeds, int32_t P);
+
+/* Genotype source A: a .pgen file (fit_model.nf:39-40,54,123).  pgen_order[i] = 1-based raw-sample index of
+ * model sample i (fit_model.nf:70,124: match(samples, psam$IID)). Modes 0x02 and 0x10 (hard calls). */
+int  flx_open_pgen(flx_handle* h, const char* path, const int32_t* pgen_order, int64_t n);
+
+/* Genotype source B: packed 2-bit hard-call records already in host memory (pgen mode-0x02 body:
+ * variant v at packed + v*bytes_per_variant, sample i at bits 2*(i&3) of byte i>>2; 3 = missing). */
+int  flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant,
+                    int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n);
+
+/* Copy the packed records of source B into HBM once (bench "value": inputs resident before timing). */
+int  flx_make_resident(flx_handle* h);
+
+/* The hot loop (fit_model.nf:120-171) for var_idx[0..M) (1-based variant numbers, get_var_idx.nf:34-35).
+ *   out  : per-SNP outputs (may be NULL to skip the per-SNP D2H copy, PERM-only use)
+ *   minp : P minima over the M variants, one per seed (fit_model.nf:141-143); NULL if no permutations set
+ *   nvars_tested: M on success (fit_model.nf:142,178)
+ * With an attached communicator minp is min-allreduced and nvars_tested sum-allreduced over the ranks. */
+int  flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const flx_snp_out* out, double* minp, int64_t* nvars_tested);
+
+int  flx_get_stats(flx_handle* h, flx_stats* out);
+
+/* R-exact permutation indices (set.seed(seed); sample.int(m)), 1-based. Host-only, bit-exact. */
+int  flx_perm_indices(int32_t seed, int64_t m, int32_t* out);
+
+/* Test hook for K1: decode var_idx[0..M) and return the design columns X (n x M*s, column-major; the
+ * s SNP-dependent columns of variant j at columns j*s .. j*s+s-1) and, if codes != NULL, the gathered
+ * 2-bit codes (M x n, row-major, value 3 = missing; no error is raised for them here). */
+int  flx_decode_tile(flx_handle* h, const int32_t* var_idx, int64_t M, double* X, uint8_t* codes);
+
+/* Test hook for K2: whiten arbitrary columns, W = L^-1 . X  (n x ncols, column-major both). */
+int  flx_whiten(flx_handle* h, const double* X, int64_t ncols, double* W);
+
+/* Multi-GPU (SNP-block sharding, one handle per GPU): NCCL communicator for the min-p allreduce.
+ * flx_comm_unique_id fills 128 bytes on rank 0; broadcast them by any means, then attach on every rank. */
+int  flx_comm_unique_id(uint8_t id[128]);
+int  flx_comm_attach(flx_handle* h, const uint8_t id[128], int32_t rank, int32_t nranks);
+
+/* Downstream definition of the minP threshold (get_null_p_dist.nf:77-79; make_plots.nf:31):
+ * quantile(min_pval, p_thr), R type 7. Host-only. */
+double flx_minp_threshold(const double* min_pval, int64_t P, double p_thr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
