@@ -1,0 +1,130 @@
+"""Host-side logic and the C-ABI boundary, without a GPU: the library loads, exports every symbol the header declares,
+its host-only entry points (R-exact permutation order, type-7 quantile) are bit-exact against the oracle, and the product
+path fails loudly when no B200 is present (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "flexlmm_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(flx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(fx):
+    L = ctypes.CDLL(fx.lib_path())
+    names = header_functions()
+    assert len(names) >= 18
+    for nm in names:
+        assert hasattr(L, nm), f"{nm} declared in include/flexlmm_cuda.h but not exported"
+    assert sorted(fx._capi.EXPORTS) == names
+
+
+def test_version_and_error_string(fx):
+    L = fx.load()
+    assert b"sm_100a" in L.flx_version()
+    assert isinstance(L.flx_last_error(), bytes)
+
+
+def test_no_gpu_means_loud_failure(fx):
+    if fx.load().flx_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fx.FlxError) as e:
+        fx.FitModel()
+    assert e.value.code == -8 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "flexlmm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f == "synth.py", f"{f} mentions the oracle"
+    assert "oracle" not in open(os.path.join(ROOT, "include", "flexlmm_cuda.h")).read().lower()
+
+
+@pytest.mark.parametrize("m", [1, 2, 9, 10, 298, 4998, 70001])
+def test_perm_indices_bit_exact_vs_oracle(fx, orc, m):
+    for seed in (1, 2, 42, 100, 2**31 - 1):
+        assert np.array_equal(fx.perm_indices(seed, m), orc.r_sample(seed, m))
+
+
+def test_perm_indices_known_answers(fx):
+    import json
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))
+    for seed, want in kat["sample10"].items():
+        assert fx.perm_indices(int(seed), 10).tolist() == want
+
+
+def test_minp_threshold_type7(fx, orc):
+    rng = np.random.default_rng(0)
+    for P in (1, 2, 10, 100, 1000):
+        x = rng.random(P)
+        for p in (0.05, 0.5, 0.0, 1.0, 0.013):
+            assert fx.minp_threshold(x, p) == pytest.approx(orc.quantile7(x, p), abs=1e-16)
+            assert fx.minp_threshold(x, p) == pytest.approx(np.quantile(x, p), abs=1e-15)
+
+
+def test_r_number_formatting(fx):
+    from flexlmm_b200.fit_model import _r_num
+    assert _r_num(9.98853558118183) == "9.98853558118183"
+    assert _r_num(0.006776681232578928) == "0.00677668123257893"
+    assert _r_num(2.0) == "2"
+    assert _r_num(float("nan")) == "NA"
+    assert _r_num(1e-20) == "1e-20"
+    assert _r_num(1.5e-7) == "1.5e-07"
+
+
+def test_tsv_writers(fx, tmp_path):
+    import gzip
+    res = dict(coef=np.array([[1.0, -0.5]]), lrt_chisq=np.array([3.25]), lrt_df=np.array([1]), pval=np.array([0.0714]))
+    p = tmp_path / "a.tsv.gwas.gz"
+    fx.write_gwas_tsv(p, [("14", 100, "rs1", "A", "G")], ["(Intercept)", "x"], res)
+    lines = gzip.open(p, "rt").read().splitlines()
+    assert lines[0].split("\t") == ["chr", "pos", "id", "ref", "alt", "lrt_chisq", "lrt_df", "pval", "beta"]
+    assert lines[1] == "14\t100\trs1\tA\tG\t3.25\t1\t0.0714\t(Intercept)~1,x~-0.5"
+    q = tmp_path / "a.perm.tsv.gz"
+    fx.write_perm_tsv(q, [1, 2], "14", [0.5, 0.25], 11)
+    assert gzip.open(q, "rt").read() == "1\t14\t0.5\t11\n2\t14\t0.25\t11\n"
+    with pytest.raises(ValueError):
+        fx.write_perm_tsv(q, [1], "14", [2.0], 11)       # fit_model.nf:177 stopifnot
+
+
+def test_synth_packing_roundtrip():
+    from flexlmm_b200 import synth
+    g = synth.genotypes(7, 13, seed=1, missing_rate=0.1)
+    p = synth.pack_2bit(g)
+    assert p.shape == (7, 4)
+    un = np.stack([(p[:, i >> 2] >> (2 * (i & 3))) & 3 for i in range(13)], axis=1)
+    assert np.array_equal(un, g)
+
+
+def test_shard_bounds():
+    from flexlmm_b200.sharding import shard_bounds, shard_var_idx
+    for M in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(M, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == M
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_var_idx(np.arange(1, 11), 1, 3).tolist() == [5, 6, 7]
+
+
+def test_golden_synth_matches_oracle_now(orc):
+    """The committed golden vectors are reproducible from the committed generator."""
+    from flexlmm_b200 import synth
+    G = np.load(os.path.join(ROOT, "tests", "golden", "synth_small.npz"))
+    n, M, P, n_raw, seed = G["additive.args"].tolist()
+    t = synth.task(n, M, model="additive", P=P, n_raw=None if n_raw == n else n_raw, seed=seed)
+    codes = t["codes_raw"][:, t["pgen_order"] - 1]
+    o = orc.fit_model(t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"], t["M0"], t["M1"], t["M2"], codes)
+    np.testing.assert_allclose(o["chisq"], G["additive.chisq"], rtol=1e-12)
+    assert np.array_equal(o["pivot"], G["additive.pivot"])

@@ -1,0 +1,192 @@
+"""The oracle against every known answer available for this path (the reference itself ships no
+golden outputs — parity unpinned) and against independent formulas (numpy lstsq, scipy chi2, mpmath)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
+C1 = json.load(open(os.path.join(HERE, "golden", "c1_test_asset.json")))
+
+
+def test_r_sample_known_answers(orc):
+    for seed, want in KAT["sample10"].items():
+        assert orc.r_sample(int(seed), 10).tolist() == want
+
+
+def test_r_runif_known_answers(orc):
+    np.testing.assert_allclose(orc.r_runif(1, 3), KAT["runif_seed1"], atol=5e-8)
+
+
+def test_r_sample_is_a_permutation(orc):
+    for m in (1, 2, 3, 17, 4998, 65537):
+        p = orc.r_sample(7, m)
+        assert sorted(p.tolist()) == list(range(1, m + 1))
+
+
+def test_pgen_fixture_bytes_decode(orc):
+    buf = bytes.fromhex(C1["pgen_hex"])
+    assert len(buf) == 77 and buf[:3] == b"\x6c\x1b\x10"
+    assert orc.pgen_info(buf) == (22, 12, 0x10)
+    for v in range(22):
+        assert orc.pgen_read_hardcalls(buf, v).tolist() == [2, 2, 2] + [0] * 9
+
+
+def test_pgen_writer_reproduces_reference_fixture():
+    from pgen_writer import write_pgen
+    codes = np.tile(np.array([2, 2, 2] + [0] * 9, dtype=np.uint8), (22, 1))
+    assert write_pgen(codes, [0] + [2] * 21).hex() == C1["pgen_hex"]
+
+
+@pytest.mark.parametrize("N", [1, 3, 4, 5, 12, 37, 255, 256, 257, 700])
+def test_pgen_all_vrtypes_roundtrip(orc, N):
+    from pgen_writer import write_pgen
+    rng = np.random.default_rng(N)
+    c = rng.integers(0, 3, size=(30, N)).astype(np.uint8)
+    c[rng.random(c.shape) < 0.03] = 3
+    vt = [0, 1, 2, 3, 4, 6, 7, 2, 3, 1] * 3
+    c[4] = 0; c[5] = 2; c[6] = 3
+    if N > 3:
+        c[5, 3] = 1
+    for mode, vts in ((0x10, vt), (0x02, None)):
+        b = write_pgen(c, vts, mode=mode)
+        for v in range(30):
+            assert np.array_equal(orc.pgen_read_hardcalls(b, v), c[v]), (mode, v)
+
+
+def test_codes_to_na(orc):
+    import ctypes
+    codes = np.array([0, 1, 2, 3], dtype=np.uint8); buf = np.zeros(4)
+    orc.lib().orc_codes_to_buf.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    orc.lib().orc_codes_to_buf(codes.ctypes.data, 4, buf.ctypes.data)
+    assert buf[:3].tolist() == [0.0, 1.0, 2.0] and np.isnan(buf[3])
+    assert buf.view(np.uint64)[3] & 0xFFFFFFFF == 1954      # R's NA_real_ payload
+
+
+def test_forwardsolve(orc):
+    rng = np.random.default_rng(0)
+    n = 60
+    L = np.tril(rng.standard_normal((n, n))) + 5 * np.eye(n)
+    X = rng.standard_normal((n, 4))
+    np.testing.assert_allclose(L @ orc.forwardsolve(L, X), X, atol=1e-12)
+
+
+def test_lm_fit_full_rank_vs_lstsq(orc):
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((50, 4)); y = rng.standard_normal(50)
+    f = orc.lm_fit(X, y)
+    b = np.linalg.lstsq(X, y, rcond=None)[0]
+    assert f["rank"] == 4 and f["pivot"].tolist() == [1, 2, 3, 4]
+    np.testing.assert_allclose(f["coefficients"], b, rtol=1e-10)
+    np.testing.assert_allclose(f["residuals"], y - X @ b, atol=1e-12)
+
+
+def test_lm_fit_rank_rule(orc):
+    rng = np.random.default_rng(2)
+    n = 40
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    X = np.column_stack([np.ones(n), a, np.zeros(n), 2 * a - 1, b])     # zero column and a collinear one
+    f = orc.lm_fit(X, rng.standard_normal(n))
+    assert f["rank"] == 3
+    assert f["pivot"].tolist() == [1, 2, 5, 3, 4]                        # rejected columns cycle to the end in order
+    assert f["coefficients"][3:].tolist() == [0.0, 0.0]
+
+
+def test_test_asset_known_answer(orc):
+    k = KAT["test_asset_identity"]
+    case = next(c for c in C1["cases"] if c["L"] == "identity" and c["formula"] == "test_config")
+    got = case["chr"]["14"]
+    assert got["rank"][0] == k["rank"] and got["pivot"][0] == k["pivot"] and got["df"][0] == k["lrt_df"]
+    assert abs(got["chisq"][0] - k["lrt_chisq"]) < 1e-12
+    assert abs(got["pval"][0] - k["pval"]) < 1e-15
+    np.testing.assert_allclose(got["coef"][0], k["coef"], atol=1e-6)
+    # and the oracle reproduces the committed golden values when re-run now
+    L = np.array(case["Lmat"]); g = np.array(C1["codes"], dtype=np.uint8)[[v - 1 for v in got["var_idx"]]]
+    o = orc.fit_model(L, case["y_mm"], np.array(case["X_null"]), case["ll_null"], case["df_null"], np.array(case["M0"]),
+                      np.array(case["M1"]), np.array(case["M2"]), g)
+    np.testing.assert_allclose(o["chisq"], got["chisq"], rtol=1e-13)
+    assert o["pivot"].tolist() == got["pivot"]
+
+
+def test_rss0_is_permutation_invariant(orc):
+    case = next(c for c in C1["cases"] if c["L"] == "identity" and c["formula"] == "test_config")
+    y_pred, U1, e_p, Xn = np.array(case["y_pred"]), np.array(case["U1"]), np.array(case["e_p"]), np.array(case["X_null"])
+    for seed in (1, 2, 3):
+        idx = orc.r_sample(seed, len(e_p))
+        y = y_pred + U1 @ e_p[idx - 1]
+        r = orc.lm_fit(Xn, y)["residuals"]
+        assert abs(r @ r - KAT["test_asset_identity"]["rss0"]) < 1e-13
+
+
+def test_pchisq_against_scipy_and_mpmath(orc):
+    from scipy import stats
+    import mpmath
+    for q, df, want in KAT["pchisq"]:
+        assert abs(orc.pchisq_upper(q, df) - want) < 1e-15
+    rng = np.random.default_rng(3)
+    for df in range(1, 9):
+        for q in list(rng.uniform(1e-6, 60, 25)) + [1e-12, 200.0, 900.0]:
+            got = orc.pchisq_upper(q, df)
+            want = float(mpmath.gammainc(mpmath.mpf(df) / 2, mpmath.mpf(q) / 2, mpmath.inf, regularized=True))
+            # conditioning of the tail in q is ~q/2 ulp: allow it (1.4e-14 absolute in -log10 p at q = 900)
+            assert abs(got - want) <= (2e-14 + 1e-16 * q) * want, (q, df, got, want)
+            assert abs(got - stats.chi2.sf(q, df)) <= 1e-12 * want
+    assert orc.pchisq_upper(0.0, 1) == 1.0 and orc.pchisq_upper(-1.0, 2) == 1.0
+    assert orc.pchisq_upper(1e5, 1) == 0.0                     # underflow -> exactly 0 like R
+    assert np.isnan(orc.pchisq_upper(3.0, 0))
+
+
+def test_loglik_and_lrt_identity(orc):
+    rng = np.random.default_rng(4)
+    n = 100
+    X0 = np.column_stack([np.ones(n), rng.standard_normal(n)]); x = rng.integers(0, 3, n).astype(float)
+    y = rng.standard_normal(n)
+    r0 = orc.lm_fit(X0, y)["residuals"]; r1 = orc.lm_fit(np.column_stack([X0, x]), y)["residuals"]
+    chisq = 2 * (orc.loglik_lm(r1) - orc.loglik_lm(r0))
+    assert abs(chisq - n * np.log((r0 @ r0) / (r1 @ r1))) < 1e-10
+
+
+def test_fit_model_against_numpy(orc):
+    from flexlmm_b200 import synth
+    t = synth.task(120, 30, model="domgxe", P=0, seed=5)
+    codes = t["codes_raw"]
+    o = orc.fit_model(t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"], t["M0"], t["M1"], t["M2"], codes)
+    from scipy import stats
+    Li = np.linalg.inv(t["L"])
+    for v in range(30):
+        x = codes[v].astype(float)
+        X = np.where(x[:, None] == 0, t["M0"], np.where(x[:, None] == 1, t["M1"], t["M2"]))
+        Xw = Li @ X
+        b, _, rk, _ = np.linalg.lstsq(Xw, t["y_mm"], rcond=None)
+        rss1 = np.sum((t["y_mm"] - Xw @ b) ** 2)
+        r0 = t["y_mm"] - t["y_pred"]
+        chisq = 120 * np.log((r0 @ r0) / rss1)
+        assert o["rank"][v] == rk
+        assert abs(o["chisq"][v] - chisq) < 1e-8 * max(1, chisq)
+        if rk == 5:
+            assert abs(o["pval"][v] - stats.chi2.sf(chisq, 3)) < 1e-9
+
+
+def test_missing_genotype_is_fatal(orc):
+    from flexlmm_b200 import synth
+    t = synth.task(40, 3, model="additive", seed=1)
+    codes = t["codes_raw"].copy(); codes[1, 7] = 3
+    with pytest.raises(ValueError):
+        orc.fit_model(t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"], t["M0"], t["M1"], t["M2"], codes)
+
+
+def test_quantile7_and_summarise(orc):
+    rng = np.random.default_rng(6)
+    x = rng.random(101)
+    for p in (0.05, 0.5, 0.013):
+        assert abs(orc.quantile7(x, p) - np.quantile(x, p)) < 1e-15
+    rows = [(1, "14", 0.2, 11), (1, "15", 0.1, 11), (2, "14", 0.5, 11), (2, "15", 0.7, 11)]
+    assert orc.summarise_minp(rows) == {1: (0.1, 22), 2: (0.5, 22)}
+
+
+def test_design_lowering_matches_terms_order(orc):
+    case = next(c for c in C1["cases"] if c["formula"] == "test_config")
+    assert case["colnames"] == ["(Intercept)", "x", "I(x == 1)TRUE", "covar1bbb", "qcovar1", "x:covar1bbb"]
+    assert case["null_colnames"] == ["(Intercept)", "covar1bbb", "qcovar1"]

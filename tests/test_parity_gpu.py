@@ -1,0 +1,361 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden fixtures.
+
+Bar: genotype decode and permutation index order bit-exact; lrt_df / rank / pivot exact;
+-log10 p and the minP threshold within |d| <= 1e-8 * |value| + 1e-10 in FP64; coefficients within 1e-8 relative.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL, ATOL = 1e-8, 1e-10        # the stated tolerance on -log10 p
+
+
+def assert_logp_close(p_gpu, p_ref):
+    p_gpu, p_ref = np.asarray(p_gpu, dtype=float), np.asarray(p_ref, dtype=float)
+    assert np.array_equal(np.isnan(p_gpu), np.isnan(p_ref))
+    ok = ~np.isnan(p_ref)
+    with np.errstate(divide="ignore"):
+        a, b = -np.log10(p_gpu[ok]), -np.log10(p_ref[ok])
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)                       # p -> 0 underflow must give exactly Inf like R
+    err = np.abs(a[fin] - b[fin]) - (RTOL * np.abs(b[fin]) + ATOL)
+    assert err.size == 0 or err.max() <= 0, f"-log10 p off by {err.max():.3e} beyond tolerance"
+
+
+def make(fx, t, perm=True, pgen_path=None, batch_tiles=0):
+    fm = fx.FitModel(batch_tiles=batch_tiles)
+    fm.set_whitening(t["L"])
+    fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"])
+    fm.set_design(t["M0"], t["M1"], t["M2"])
+    if perm and t.get("P", 0):
+        fm.set_perm(t["y_pred"], t["U1"], t["e_p"], t["seeds"])
+    if pgen_path is not None:
+        fm.open_pgen(pgen_path, t["pgen_order"])
+    else:
+        fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+    return fm
+
+
+def oracle_run(orc, t, codes, seed=0):
+    kw = dict(perm_seed=seed, y_pred=t["y_pred"], U1=t["U1"], e_p=t["e_p"]) if seed else {}
+    return orc.fit_model(t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"], t["M0"], t["M1"], t["M2"], codes, **kw)
+
+
+def compare(r, o):
+    assert np.array_equal(r["lrt_df"], o["df"])
+    assert np.array_equal(r["rank"], o["rank"])
+    assert np.array_equal(r["pivot"], o["pivot"])
+    assert_logp_close(r["pval"], o["pval"])
+    np.testing.assert_allclose(r["lrt_chisq"], o["chisq"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(r["coef"], o["coef"], rtol=1e-8, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------ K1 decode
+@pytest.mark.parametrize("n,n_raw,model", [(4, 4, "simple"), (5, 9, "additive"), (6, 6, "domgxe"), (127, 200, "additive"), (128, 128, "domgxe"),
+                                           (129, 400, "simple"), (300, 300, "domgxe"), (1000, 1777, "additive")])
+def test_decode_bit_exact(fx, orc, n, n_raw, model):
+    from flexlmm_b200 import synth
+    t = synth.task(n, 77, model=model, n_raw=n_raw, seed=n)
+    rng = np.random.default_rng(n)
+    t["pgen_order"] = (rng.permutation(t["n_raw"])[: t["n"]] + 1).astype(np.int32)       # non-monotone subset + reorder
+    codes = t["codes_raw"][:, t["pgen_order"] - 1]
+    with make(fx, t, perm=False) as fm:
+        vi = rng.permutation(77).astype(np.int32) + 1                                    # arbitrary variant order
+        X, cd = fm.decode_tile(vi)
+    assert np.array_equal(cd, codes[vi - 1])
+    s = X.shape[1] // 77
+    snp_cols = [j for j in range(t["M0"].shape[1]) if not (np.array_equal(t["M0"][:, j], t["M1"][:, j]) and np.array_equal(t["M0"][:, j], t["M2"][:, j]))]
+    assert len(snp_cols) == s
+    for q, v in enumerate(vi):
+        g = codes[v - 1]
+        for ti, j in enumerate(snp_cols):
+            want = np.where(g == 0, t["M0"][:, j], np.where(g == 1, t["M1"][:, j], t["M2"][:, j]))
+            assert np.array_equal(X[:, q * s + ti], want)                               # bit-exact design columns
+
+
+@pytest.mark.parametrize("mode", [0x02, 0x10])
+def test_decode_from_pgen_file_all_vrtypes(fx, orc, tmp_path, mode):
+    from flexlmm_b200 import synth
+    from pgen_writer import write_pgen
+    t = synth.task(211, 60, model="additive", n_raw=300, seed=2)
+    c = t["codes_raw"].copy()
+    c[4] = 0; c[5] = 2; c[5, 3] = 1
+    vt = ([0, 1, 2, 3, 4, 6, 7, 2, 3, 1] * 6) if mode == 0x10 else None
+    path = tmp_path / "t.pgen"
+    path.write_bytes(write_pgen(c, vt, mode=mode))
+    with make(fx, t, perm=False, pgen_path=path) as fm:
+        vi = np.arange(1, 61, dtype=np.int32)
+        _, cd = fm.decode_tile(vi, want_X=False)
+    assert np.array_equal(cd, c[:, t["pgen_order"] - 1])
+    buf = path.read_bytes()
+    for v in range(60):
+        assert np.array_equal(orc.pgen_read_hardcalls(buf, v)[t["pgen_order"] - 1], cd[v])
+
+
+def test_missing_genotype_is_fatal_like_the_reference(fx):
+    from flexlmm_b200 import synth
+    t = synth.task(100, 40, model="additive", seed=3)
+    c = t["codes_raw"].copy(); c[17, 5] = 3
+    t["packed"] = synth.pack_2bit(c)
+    with make(fx, t, perm=False) as fm:
+        _, cd = fm.decode_tile(np.arange(1, 41, dtype=np.int32), want_X=False)
+        assert cd[17, 5] == 3
+        with pytest.raises(fx.FlxError) as e:
+            fm.run(np.arange(1, 41, dtype=np.int32))
+        assert e.value.code == -2 and "var_idx[17]" in str(e.value)
+        fm.run(np.arange(1, 17, dtype=np.int32))            # variants without missing calls still run
+
+
+# ------------------------------------------------------------------------------------------------ K2 whiten
+@pytest.mark.parametrize("n", [12, 129, 500, 1000])
+def test_whiten_matches_forwardsolve(fx, orc, n):
+    from flexlmm_b200 import synth
+    L = synth.covariance_factor(n, seed=n)
+    rng = np.random.default_rng(n)
+    X = np.asfortranarray(rng.integers(0, 3, size=(n, 150)).astype(float) * rng.standard_normal((n, 1)))
+    with fx.FitModel() as fm:
+        fm.set_whitening(L)
+        W = fm.whiten(X)
+    Wo = orc.forwardsolve(L, X)
+    assert np.abs(W - Wo).max() <= 1e-12 * np.abs(Wo).max()
+
+
+def test_whitening_accepts_explicit_inverse(fx):
+    from flexlmm_b200 import synth
+    L = synth.covariance_factor(200, seed=1)
+    X = np.asfortranarray(np.random.default_rng(0).standard_normal((200, 5)))
+    with fx.FitModel() as a, fx.FitModel() as b:
+        a.set_whitening(L); b.set_whitening(np.linalg.inv(L), is_inverse=True)
+        np.testing.assert_allclose(a.whiten(X), b.whiten(X), rtol=1e-12, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------ K3 fit + LRT
+@pytest.mark.parametrize("n,M,model,n_raw", [(300, 200, "additive", None), (300, 130, "domgxe", 333), (1000, 300, "simple", None),
+                                             (64, 500, "domgxe", None), (2000, 64, "additive", 2100)])
+def test_fit_matches_oracle(fx, orc, n, M, model, n_raw):
+    from flexlmm_b200 import synth
+    t = synth.task(n, M, model=model, n_raw=n_raw, seed=n + M, effect=0.2)
+    codes = t["codes_raw"][:, t["pgen_order"] - 1]
+    with make(fx, t, perm=False) as fm:
+        r = fm.run(np.arange(1, M + 1, dtype=np.int32))
+    compare(r, oracle_run(orc, t, codes))
+    assert r["nvars_tested"] == M
+
+
+def test_rank_deficient_snps(fx, orc):
+    """Monomorphic SNPs, SNPs without heterozygotes (all-zero I(x==1) column), a SNP equal to a covariate: the dqrdc2 rank rule."""
+    from flexlmm_b200 import synth
+    n = 240
+    t = synth.task(n, 12, model="domgxe", seed=7)
+    c = t["codes_raw"].copy()
+    c[0] = 0; c[1] = 2; c[2] = 1                                  # monomorphic
+    c[3] = np.where(c[3] == 1, 0, c[3]); c[4] = np.where(c[4] == 1, 2, c[4])   # no hets
+    c[5] = c[6]                                                   # duplicated SNP
+    c[7] = 0; c[7, :3] = 2                                        # the test-asset pattern: few carriers, no hets
+    t["packed"] = synth.pack_2bit(c)
+    with make(fx, t, perm=False) as fm:
+        r = fm.run(np.arange(1, 13, dtype=np.int32))
+    o = oracle_run(orc, t, c)
+    compare(r, o)
+    assert r["lrt_df"][0] == 0 and np.isnan(r["pval"][0])           # lrt_df == 0 -> NA (fit_model.nf:138)
+    assert r["lrt_df"][3] == 2 and r["rank"][3] == 4
+    assert r["lrt_chisq"][5] == r["lrt_chisq"][6]
+
+
+def test_covariate_collinear_with_snp(fx, orc):
+    """A later NULL-model column collinear with (1, x): dqrdc2 rejects the covariate, not x; df drops to 0."""
+    from flexlmm_b200 import synth
+    n = 150
+    t = synth.task(n, 6, model="additive", seed=11)
+    g0 = t["codes_raw"][0].astype(float)
+    cov = 2.0 * g0 - 1.0
+    one = np.ones(n)
+    t["M0"], t["M1"], t["M2"] = (np.column_stack([one, np.full(n, v), cov]) for v in (0.0, 1.0, 2.0))
+    Xn = np.column_stack([one, cov])
+    y = np.random.default_rng(1).standard_normal(n)
+    t["y_mm"] = orc.forwardsolve(t["L"], y)[:, 0]; t["X_null"] = orc.forwardsolve(t["L"], Xn)
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    t["ll_null"], t["df_null"] = nm["ll"], nm["df"]
+    with make(fx, t, perm=False) as fm:
+        r = fm.run(np.arange(1, 7, dtype=np.int32))
+    o = oracle_run(orc, t, t["codes_raw"])
+    compare(r, o)
+    assert r["rank"][0] == 2 and r["pivot"][0].tolist() == [1, 2, 3] and r["lrt_df"][0] == 0
+
+
+def test_extra_covariate_in_real_model_only(fx, orc):
+    """Nested models where the real model adds an SNP-independent column too (y ~ x + cov1 vs y ~ 1): lrt_df = 2."""
+    from flexlmm_b200 import synth
+    n = 180
+    t = synth.task(n, 40, model="additive", seed=13)
+    Xn = np.ones((n, 1))
+    t["X_null"] = orc.forwardsolve(t["L"], Xn)
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    t["ll_null"], t["df_null"] = nm["ll"], nm["df"]
+    with make(fx, t, perm=False) as fm:
+        r = fm.run(np.arange(1, 41, dtype=np.int32))
+    o = oracle_run(orc, t, t["codes_raw"])
+    compare(r, o)
+    assert set(r["lrt_df"].tolist()) == {2}
+
+
+def test_huge_effect_underflows_to_zero_like_r(fx, orc):
+    from flexlmm_b200 import synth
+    n = 400
+    t = synth.task(n, 5, model="simple", seed=17)
+    g = t["codes_raw"][0].astype(float)
+    y = 50.0 * g + 1e-3 * np.random.default_rng(0).standard_normal(n)
+    t["y_mm"] = orc.forwardsolve(t["L"], y)[:, 0]
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    t["ll_null"], t["df_null"] = nm["ll"], nm["df"]
+    with make(fx, t, perm=False) as fm:
+        r = fm.run(np.arange(1, 6, dtype=np.int32))
+    o = oracle_run(orc, t, t["codes_raw"])
+    assert o["pval"][0] == 0.0 and r["pval"][0] == 0.0
+    np.testing.assert_allclose(r["lrt_chisq"], o["chisq"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ C1: the reference's own test assets
+def test_c1_test_assets_golden(fx, tmp_path):
+    C1 = json.load(open(os.path.join(ROOT, "tests", "golden", "c1_test_asset.json")))
+    path = tmp_path / "in.pgen"
+    path.write_bytes(bytes.fromhex(C1["pgen_hex"]))
+    for case in C1["cases"]:
+        n = len(case["y_mm"])
+        with fx.FitModel() as fm:
+            fm.set_whitening(np.array(case["Lmat"]))
+            fm.set_null(np.array(case["X_null"]).reshape(n, -1), case["y_mm"], case["ll_null"], case["df_null"])
+            fm.set_design(np.array(case["M0"]), np.array(case["M1"]), np.array(case["M2"]))
+            fm.set_perm(case["y_pred"], np.array(case["U1"]), case["e_p"], [1, 2])
+            fm.open_pgen(path, np.arange(1, n + 1))
+            for chrom, g in case["chr"].items():
+                r = fm.run(np.array(g["var_idx"], dtype=np.int32))
+                assert r["lrt_df"].tolist() == g["df"] and r["rank"].tolist() == g["rank"] and r["pivot"].tolist() == g["pivot"]
+                assert_logp_close(r["pval"], [np.nan if v is None else v for v in g["pval"]])
+                np.testing.assert_allclose(r["lrt_chisq"], g["chisq"], rtol=1e-8, atol=1e-9)
+                np.testing.assert_allclose(r["coef"], g["coef"], rtol=1e-8, atol=1e-10)
+                for si, sd in enumerate(("1", "2")):
+                    assert_logp_close([r["min_pval"][si]], [g["perm"][sd]["min_pval"]])
+                    assert fx.perm_indices(int(sd), len(case["e_p"])).tolist() == g["perm"][sd]["idx"]
+                assert r["nvars_tested"] == g["perm"]["1"]["nvars"]
+
+
+def test_golden_synth_small(fx):
+    from flexlmm_b200 import synth
+    G = np.load(os.path.join(ROOT, "tests", "golden", "synth_small.npz"))
+    for name in ("additive", "domgxe", "simple"):
+        n, M, P, n_raw, seed = G[f"{name}.args"].tolist()
+        t = synth.task(n, M, model=name, P=P, n_raw=None if n_raw == n else n_raw, seed=seed)
+        with make(fx, t) as fm:
+            r = fm.run(np.arange(1, M + 1, dtype=np.int32))
+        compare(r, {k2: G[f"{name}.{k2}"] for k2 in ("chisq", "df", "pval", "rank", "pivot", "coef")})
+        assert_logp_close(r["min_pval"], G[f"{name}.min_pval"])
+
+
+# ------------------------------------------------------------------------------------------------ K4 permutations
+@pytest.mark.parametrize("n,M,model,P", [(200, 150, "additive", 5), (160, 90, "domgxe", 4), (500, 40, "simple", 131)])
+def test_permutation_minp_matches_oracle(fx, orc, n, M, model, P):
+    from flexlmm_b200 import synth
+    t = synth.task(n, M, model=model, P=P, seed=n)
+    codes = t["codes_raw"]
+    with make(fx, t) as fm:
+        r = fm.run(np.arange(1, M + 1, dtype=np.int32))
+    nseed = min(P, 6)
+    want = np.array([oracle_run(orc, t, codes, seed=int(s))["min_pval"] for s in t["seeds"][:nseed]])
+    assert_logp_close(r["min_pval"][:nseed], want)
+    assert r["nvars_tested"] == M
+    thr_gpu = fx.minp_threshold(r["min_pval"][:nseed], 0.05)
+    assert abs(np.log10(thr_gpu) - np.log10(orc.quantile7(want, 0.05))) <= RTOL * abs(np.log10(thr_gpu)) + ATOL
+
+
+def test_permutation_with_rank_deficient_snps(fx, orc):
+    from flexlmm_b200 import synth
+    t = synth.task(120, 30, model="domgxe", P=3, seed=23)
+    c = t["codes_raw"].copy()
+    for v in range(0, 30, 3):
+        c[v] = np.where(c[v] == 1, 0, c[v])            # df = 2 SNPs mixed with df = 3 SNPs
+    c[1] = 0                                            # df = 0 (NA) is skipped by min(..., na.rm = TRUE)
+    t["packed"] = synth.pack_2bit(c)
+    with make(fx, t) as fm:
+        r = fm.run(np.arange(1, 31, dtype=np.int32))
+    want = np.array([oracle_run(orc, t, c, seed=int(s))["min_pval"] for s in t["seeds"]])
+    assert_logp_close(r["min_pval"], want)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE-size properties (n = 5,000)
+@pytest.fixture(scope="module")
+def big(fx):
+    from flexlmm_b200 import synth
+    t = synth.task(5000, 6000, model="additive", P=100, seed=1)
+    fm = make(fx, t)
+    r = fm.run(np.arange(1, 6001, dtype=np.int32))
+    yield t, fm, r
+    fm.close()
+
+
+def test_big_batching_and_order_invariance(fx, big):
+    """Per-SNP results do not depend on which other SNPs share the batch / tile, nor on their order (bit-exact)."""
+    t, fm, r = big
+    rng = np.random.default_rng(0)
+    sub = np.sort(rng.choice(6000, size=777, replace=False)).astype(np.int32) + 1
+    r2 = fm.run(sub, minp=False)
+    assert np.array_equal(r2["lrt_chisq"], r["lrt_chisq"][sub - 1])
+    assert np.array_equal(r2["coef"], r["coef"][sub - 1])
+    perm = rng.permutation(6000).astype(np.int32) + 1
+    r3 = fm.run(perm, minp=False)
+    assert np.array_equal(r3["pval"], r["pval"][perm - 1])
+
+
+def test_big_sample_against_oracle(fx, orc, big):
+    t, fm, r = big
+    pick = np.array([0, 1, 2, 3000, 5999])
+    o = oracle_run(orc, t, t["codes_raw"][pick])
+    compare({k2: r[k2][pick] for k2 in ("lrt_df", "rank", "pivot", "pval", "lrt_chisq", "coef")}, o)
+
+
+def test_big_perm_path_agrees_with_orig_path(fx, big):
+    """K4 (one contraction for all permutations) must equal running the ORIG path on the permuted phenotype itself:
+    min over SNPs of the per-SNP p-values == min_pval[seed].  Size-independent check of the permutation identity."""
+    t, fm, r = big
+    n = t["n"]
+    for si in (0, 57, 99):
+        seed = int(t["seeds"][si])
+        idx = fx.perm_indices(seed, len(t["e_p"]))
+        y_star = t["y_pred"] + t["U1"] @ t["e_p"][idx - 1]
+        Q, _ = np.linalg.qr(t["X_null"])
+        e = y_star - Q @ (Q.T @ y_star)
+        ll = 0.5 * (-n * (np.log(2 * np.pi) + 1 - np.log(n) + np.log(e @ e)))
+        with fx.FitModel() as f2:
+            f2.set_whitening(t["L"]); f2.set_null(t["X_null"], y_star, ll, t["df_null"]); f2.set_design(t["M0"], t["M1"], t["M2"])
+            f2.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+            r2 = f2.run(np.arange(1, 6001, dtype=np.int32))
+        assert_logp_close([r["min_pval"][si]], [np.nanmin(r2["pval"])])
+
+
+def test_big_scale_invariance(fx, big):
+    """lrt_chisq is invariant to rescaling the phenotype (linearity of the fit)."""
+    t, fm, r = big
+    n = t["n"]
+    with fx.FitModel() as f2:
+        f2.set_whitening(t["L"])
+        f2.set_null(t["X_null"], 3.0 * t["y_mm"], t["ll_null"] - n * np.log(3.0), t["df_null"])
+        f2.set_design(t["M0"], t["M1"], t["M2"]); f2.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r2 = f2.run(np.arange(1, 1001, dtype=np.int32))
+    np.testing.assert_allclose(r2["lrt_chisq"], r["lrt_chisq"][:1000], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r2["coef"], 3.0 * r["coef"][:1000], rtol=1e-9, atol=1e-12)
+
+
+def test_empty_and_single_variant(fx, big):
+    t, fm, r = big
+    r0 = fm.run(np.zeros(0, dtype=np.int32))
+    assert r0["nvars_tested"] == 0 and r0["lrt_chisq"].size == 0 and (r0["min_pval"] == 2.0).all()
+    r1 = fm.run(np.array([4321], dtype=np.int32))
+    assert r1["lrt_chisq"][0] == r["lrt_chisq"][4320]
+    with pytest.raises(fx.FlxError):
+        fm.run(np.array([0], dtype=np.int32))             # var_idx is 1-based
+    with pytest.raises(fx.FlxError):
+        fm.run(np.array([6001], dtype=np.int32))
