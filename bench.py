@@ -200,7 +200,7 @@ def main():
         if rank != 0:
             return 0
         # each "step" = a bounded sample of the workload on all host cores
-        auto = max(4, int(round(16 * (5000.0 / w["n"]) ** 2)))
+        auto = max(4, int(round(64 * (5000.0 / w["n"]) ** 2)))
         snps = a.cpu_snps or auto
         tasks = 3  # 1 ORIG + 2 PERM tasks per SNP sample
         vals = []
@@ -312,7 +312,7 @@ def main():
                 "wall_ms_per_step": wall_s / a.steps * 1e3, "setup_s_once": t_setup, "clocks": clocks,
                 "min_pval_head": [float(x) for x in res["min_pval"][:3]]}
         if not a.no_cpu_baseline and world == 1:
-            auto = max(4, int(round(16 * (5000.0 / n) ** 2)))
+            auto = max(4, int(round(64 * (5000.0 / n) ** 2)))
             snps = a.cpu_snps or auto
             rate, tmax, wall = cpu_reference_rate(w, snps, 3, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "SNP-tests/s", "cores": cores, "kind": "port",

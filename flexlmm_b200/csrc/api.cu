@@ -302,6 +302,14 @@ extern "C" int flx_open_pgen(flx_handle* h, const char* path, const int32_t* pge
     return set_order(h, pgen_order, n, h->raw_n);
 }
 
+extern "C" int flx_pgen_info(flx_handle* h, int64_t* variant_ct, int64_t* sample_ct, int32_t* has_dosage) {
+    if (!h || h->src != 1 || !h->pgen) { set_error("flx_pgen_info: no .pgen is open"); return FLX_ERR_STATE; }
+    if (variant_ct) *variant_ct = h->pgen->variant_ct();
+    if (sample_ct) *sample_ct = h->pgen->sample_ct();
+    if (has_dosage) *has_dosage = h->pgen->has_dosage() ? 1 : 0;
+    return FLX_OK;
+}
+
 extern "C" int flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n) {
     if (!h || !packed || n_variants < 0 || raw_sample_ct <= 0 || bytes_per_variant < (raw_sample_ct + 3) / 4 || n <= 0) { set_error("flx_set_packed: bad arguments"); return FLX_ERR_BAD_ARG; }
     h->src = 2;
@@ -332,6 +340,7 @@ static int whiten_dense(flx_handle* h, const double* Xd, int64_t ld, int64_t nco
     GemmArgs g{};
     g.A = h->linv.p; g.B = Xp.p; g.Out = Wp.p;
     g.T = h->T; g.NJ = NJ; g.KC = h->KC; g.n_items = (int64_t)h->T * NJ;
+    g.KC_live = (int)((h->n + KCH - 1) / KCH); g.last_row_blocks = (int)((h->n - (int64_t)(h->T - 1) * TJ + 7) / 8);
     FLX_TRY(launch_whiten(g, h->num_sms, h->stream));
     FLX_TRY(launch_unpack_cols(Wp.p, h->n, ldw, ncols, h->KC, Wd, h->stream));
     FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -636,6 +645,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         GemmArgs g{};
         g.A = h->linv.p; g.B = h->X.p; g.Out = h->W.p;
         g.T = h->T; g.NJ = NJ; g.KC = h->KC; g.n_items = (int64_t)h->T * NJ;
+        g.KC_live = (int)((h->n + KCH - 1) / KCH); g.last_row_blocks = (int)((h->n - (int64_t)(h->T - 1) * TJ + 7) / 8);
         FLX_TRY(launch_whiten(g, h->num_sms, h->stream));
         h->stats.launches++; h->stats.launches_whiten++;
         mark();  // [3] fit start

@@ -196,6 +196,7 @@ std::string PgenFile::parse() {
             r.off = off;
             off += r.len;
             if (static_cast<int64_t>(off) > len_) return "truncated .pgen record";
+            if (r.vrtype & 0x60) has_dosage_ = true;
             if ((r.vrtype & 6) != 2) { base = first + i; have_base = true; }
             else if (!have_base) return "LD-compressed record without a base variant";
             ldbase_[first + i] = base;

@@ -27,6 +27,7 @@ public:
     uint32_t sample_ct() const { return sample_ct_; }
     int64_t bytes_per_variant() const { return ((int64_t)sample_ct_ + 3) / 4; }
     int mode() const { return mode_; }
+    bool has_dosage() const { return has_dosage_; }
     // If the file is mode 0x02 the records are already packed 2-bit: pointer to record v (0-based).
     const uint8_t* fixed_record(uint32_t v) const { return data_ + 12 + (int64_t)v * bytes_per_variant(); }
     // Expand variant v (0-based) to packed 2-bit (bytes_per_variant() bytes, pad bits 0). Any mode.
@@ -42,6 +43,7 @@ private:
     int fd_ = -1;
     uint32_t variant_ct_ = 0, sample_ct_ = 0;
     int mode_ = 0;
+    bool has_dosage_ = false;
     std::vector<Rec> recs_;           // mode 0x10
     std::vector<uint32_t> ldbase_;    // mode 0x10: index of the LD base record for LD-compressed variants
     int64_t cached_base_ = -1;

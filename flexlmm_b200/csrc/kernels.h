@@ -15,6 +15,8 @@ struct GemmArgs {
     int NJ;                   // design-column tiles in the batch
     int NP;                   // K4: permutation tiles
     int KC;                   // k-chunks (n_pad / 16)
+    int KC_live;              // K2: k-chunks that hold real samples = ceil(n / 16)
+    int last_row_blocks;      // K2: 8-row blocks of the last row tile that hold real samples (1..16)
     // K4 epilogue
     const int32_t* snp_df;    // per SNP in batch: lrt_df (0 => skip)
     const double* snp_sm;     // per SNP: s(s+1)/2 packed symmetric matrix Sm, dSS = b' Sm b

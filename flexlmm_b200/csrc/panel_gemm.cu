@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
                     a_src = g.A + tri_chunks_before(I) * CHUNK;
                     b_src = g.B + (int64_t)J * g.KC * CHUNK;
                     nk = tri_chunks_of(I);
-                    if (nk > g.KC) nk = g.KC;
+                    if (nk > g.KC_live) nk = g.KC_live;
                 } else {
                     const int J = (int)(item / g.NP);
                     const int PJ = (int)(item % g.NP);
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
             I = g.T - 1 - (int)(item / g.NJ);
             J = (int)(item % g.NJ);
             nk = tri_chunks_of(I);
-            if (nk > g.KC) nk = g.KC;
+            if (nk > g.KC_live) nk = g.KC_live;
         } else {
             J = (int)(item / g.NP);
             PJ = (int)(item % g.NP);
@@ -141,11 +141,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
             for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         const int diag_start = (MODE == 0) ? 8 * I : (1 << 30);
+        // row blocks (8 rows each) of this tile that hold real samples: only the last row tile can be partial
+        const int i_hi = (MODE == 0 && I == g.T - 1) ? g.last_row_blocks : 16;
         for (int kc = 0; kc < nk; kc++) {
             mbar_wait(&full_bar[stage], phase);
             const double* sA = stage_base + (size_t)stage * (2 * CHUNK) + lane;
             const double* sB = sA + CHUNK;
-            if (kc < diag_start) {
+            if (kc < diag_start && i_hi == 16) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
                     double a[16], b[2];
@@ -159,20 +161,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
                         for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             } else {
-                // diagonal block of L^-1: k = 128 I + 16 d + 4 ks + (0..3); row block i (rows 8i..8i+7) is
-                // non-zero only when 8 i + 7 >= 16 d + 4 ks.
+                // (a) diagonal block of L^-1: k = 128 I + 16 d + 4 ks + (0..3); row block i (rows 8i..8i+7) is
+                //     non-zero only when 8 i + 7 >= 16 d + 4 ks;  (b) partial last row tile: row blocks >= i_hi are padding.
                 const int d = kc - diag_start;
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
-                    const int i_lo = (16 * d + 4 * ks) >> 3;
+                    const int i_lo = (d >= 0) ? ((16 * d + 4 * ks) >> 3) : 0;
                     double a[16], b[2];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) a[i] = (i >= i_lo) ? sA[(ks * 16 + i) * 32] : 0.0;
+                    for (int i = 0; i < 16; i++) a[i] = (i >= i_lo && i < i_hi) ? sA[(ks * 16 + i) * 32] : 0.0;
 #pragma unroll
                     for (int j = 0; j < 2; j++) b[j] = sB[(ks * 16 + warp * 2 + j) * 32];
 #pragma unroll
                     for (int i = 0; i < 16; i++)
-                        if (i >= i_lo) {
+                        if (i >= i_lo && i < i_hi) {
 #pragma unroll
                             for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                         }

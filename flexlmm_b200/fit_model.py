@@ -94,6 +94,11 @@ class FitModel:
         po = None if pgen_order is None else np.ascontiguousarray(pgen_order, dtype=np.int32)
         check(self._lib.flx_open_pgen(self._h, str(path).encode(), ptr(po), int(n)))
 
+    def pgen_info(self):
+        v, sc, d = C.c_int64(), C.c_int64(), C.c_int32()
+        check(self._lib.flx_pgen_info(self._h, C.byref(v), C.byref(sc), C.byref(d)))
+        return dict(variant_ct=v.value, sample_ct=sc.value, has_dosage=bool(d.value))
+
     def set_packed(self, packed, raw_sample_ct, pgen_order=None, n=None):
         """Packed 2-bit records (M_total x bytes_per_variant uint8) already in host memory."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8)

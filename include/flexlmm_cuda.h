@@ -106,6 +106,11 @@ int  flx_set_perm(flx_handle* h, const double* y_pred, const double* U1, const d
  * model sample i (fit_model.nf:70,124: match(samples, psam$IID)). Modes 0x02 and 0x10 (hard calls). */
 int  flx_open_pgen(flx_handle* h, const char* path, const int32_t* pgen_order, int64_t n);
 
+/* pgenlibr::NewPgen metadata of the open file: raw variant / sample counts and whether any record carries a dosage
+ * track (vrtype bits 5-6).  The engine reads hard calls (ReadHardcalls, fit_model.nf:26 with use_dosage = false); the R
+ * wrapper must refuse use_dosage = true on a file with dosages rather than silently drop them. */
+int  flx_pgen_info(flx_handle* h, int64_t* variant_ct, int64_t* sample_ct, int32_t* has_dosage);
+
 /* Genotype source B: packed 2-bit hard-call records already in host memory (pgen mode-0x02 body:
  * variant v at packed + v*bytes_per_variant, sample i at bits 2*(i&3) of byte i>>2; 3 = missing). */
 int  flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant,

@@ -128,3 +128,26 @@ def test_golden_synth_matches_oracle_now(orc):
     o = orc.fit_model(t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"], t["M0"], t["M1"], t["M2"], codes)
     np.testing.assert_allclose(o["chisq"], G["additive.chisq"], rtol=1e-12)
     assert np.array_equal(o["pivot"], G["additive.pivot"])
+
+
+def test_r_shim_compiles_against_stub():
+    """r_shim.c (the .Call binding R uses) must at least parse and type-check against the C ABI header; R itself is not
+    installed in this image, so R's API is declared by a stub header."""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wno-cast-function-type", "-Werror",
+                        "-I" + os.path.join(ROOT, "flexlmm_b200", "r", "stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "flexlmm_b200", "r", "r_shim.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_shim_and_module_cover_every_abi_step():
+    shim = open(os.path.join(ROOT, "flexlmm_b200", "r", "r_shim.c")).read()
+    for fn in ("flx_create", "flx_set_whitening", "flx_set_null", "flx_set_design", "flx_set_perm", "flx_open_pgen", "flx_pgen_info",
+               "flx_run", "flx_destroy", "flx_last_error", "flx_perm_indices"):
+        assert fn in shim
+    nf = open(os.path.join(ROOT, "flexlmm_b200", "r", "fit_model.nf")).read()
+    # same process interface as the reference (fit_model.nf:7-16)
+    for line in ("tuple val(meta), path(mm), path(var_idx), path(null_model_fit), val(perm_seed)",
+                 "tuple val(meta2), path(pgen), path(pvar), path(psam)", "path model", "tuple val(meta3), path(model_frame)", "val use_dosage",
+                 "path \"versions.yml\" , emit: versions", "chr\\\\tpos\\\\tid\\\\tref\\\\talt\\\\tlrt_chisq\\\\tlrt_df\\\\tpval\\\\tbeta"):
+        assert line in nf, line
