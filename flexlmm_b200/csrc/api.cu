@@ -137,7 +137,7 @@ struct flx_handle {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     cudaEvent_t ev_used[2] = {nullptr, nullptr};
     DevBuf<int32_t> vmap_d;
-    DevBuf<double> X, W, nrm2, u, Ag, b, snp_sm;
+    DevBuf<double> X, W, n_part, u_part, a_part, b_part, snp_sm;
     DevBuf<int32_t> snp_df;
     // run-wide results
     DevBuf<double> chisq, pval, coef;
@@ -361,8 +361,8 @@ extern "C" int flx_whiten(flx_handle* h, const double* X, int64_t ncols, double*
 }
 
 static void upload_rowmajor_padded(const std::vector<double>& Q, int64_t n, int r, int64_t n_pad, std::vector<double>& out) {
-    const int rp = (r + 3) & ~3;
-    out.assign((size_t)n_pad * (rp > 0 ? rp : 4) + 8, 0.0);
+    const int rp = gram_padded_width(r);
+    out.assign((size_t)n_pad * rp + 8, 0.0);
     for (int j = 0; j < r; j++)
         for (int64_t i = 0; i < n; i++) out[i * rp + j] = Q[i + (int64_t)j * n];
 }
@@ -495,7 +495,7 @@ static int finalize_setup(flx_handle* h) {
         // U1 %*% sample(e.p) for every seed: one plain library GEMM (setup, outside the hot loop)
         FLX_CUBLAS_TRY(cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, U1d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
         PermPrepArgs pa{};
-        pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.Qn = h->Qn.p; pa.cn = h->cn;
+        pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.crp = gram_padded_width(cr); pa.Qn = h->Qn.p; pa.cn = h->cn; pa.cnp = gram_padded_width(h->cn);
         pa.n = n; pa.n_pad = n_pad; pa.P = P; pa.rss_f = rssf_d.p; pa.rss0 = rss0_d.p;
         FLX_TRY(launch_perm_prep(pa, h->stream));
         FLX_TRY(h->Rpk.ensure((size_t)h->NP * h->KC * CHUNK));
@@ -533,6 +533,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const int64_t bpv = h->bpv;
     const int nsym = h->s * (h->s + 1) / 2;
     const int cr = h->cr;
+    const int crp = gram_padded_width(cr);
+    constexpr int KS_MAX = 32;
     const bool decode_only = (X_out_dense != nullptr) || (codes_out != nullptr);
 
     // validate indices; contiguity lets the resident path skip the index map
@@ -545,10 +547,10 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     FLX_TRY(h->X.ensure((size_t)tiles_per_batch * tile_elems));
     if (!decode_only) {
         FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
-        FLX_TRY(h->nrm2.ensure((size_t)snps_per_batch * h->s));
-        FLX_TRY(h->u.ensure((size_t)snps_per_batch * h->s * std::max(cr, 1)));
-        FLX_TRY(h->Ag.ensure((size_t)snps_per_batch * nsym));
-        FLX_TRY(h->b.ensure((size_t)snps_per_batch * h->s));
+        FLX_TRY(h->n_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
+        FLX_TRY(h->u_part.ensure((size_t)KS_MAX * snps_per_batch * h->s * crp));
+        FLX_TRY(h->a_part.ensure((size_t)KS_MAX * snps_per_batch * nsym));
+        FLX_TRY(h->b_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
         FLX_TRY(h->snp_sm.ensure((size_t)snps_per_batch * nsym));
         FLX_TRY(h->snp_df.ensure((size_t)snps_per_batch));
         FLX_TRY(h->chisq.ensure(M)); FLX_TRY(h->pval.ensure(M)); FLX_TRY(h->df.ensure(M)); FLX_TRY(h->rank.ensure(M));
@@ -650,20 +652,24 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         h->stats.launches++; h->stats.launches_whiten++;
         mark();  // [3] fit start
         GramArgs ga{};
-        ga.W = h->W.p; ga.Qc = h->Qc.p; ga.r = h->r.p; ga.KC = h->KC; ga.cr = cr; ga.s = h->s; ga.nsnp = nsnp;
-        ga.nrm2 = h->nrm2.p; ga.u = h->u.p; ga.Ag = h->Ag.p; ga.b = h->b.p;
+        ga.W = h->W.p; ga.Qc = h->Qc.p; ga.r = h->r.p; ga.KC = h->KC; ga.cr = cr; ga.crp = crp; ga.s = h->s; ga.nsnp = nsnp;
+        // sample splits: a function of n only, so a SNP's result never depends on which other SNPs share its batch
+        ga.cps = std::max(64, (h->KC + KS_MAX - 1) / KS_MAX);
+        ga.KS = (h->KC + ga.cps - 1) / ga.cps;
+        ga.n_part = h->n_part.p; ga.u_part = h->u_part.p; ga.a_part = h->a_part.p; ga.b_part = h->b_part.p;
         FLX_TRY(launch_snp_gram(ga, h->stream));
         if (do_perm) {
             FLX_CUDA_TRY(cudaMemsetAsync(h->snp_df.p, 0, (size_t)snps_per_batch * sizeof(int32_t), h->stream));
             FLX_CUDA_TRY(cudaMemsetAsync(h->snp_sm.p, 0, (size_t)snps_per_batch * nsym * sizeof(double), h->stream));
         }
         SolveArgs sa{};
-        sa.nrm2 = h->nrm2.p; sa.u = h->u.p; sa.Ag = h->Ag.p; sa.b = h->b.p; sa.nsnp = nsnp; sa.out_offset = s0;
+        sa.n_part = h->n_part.p; sa.u_part = h->u_part.p; sa.a_part = h->a_part.p; sa.b_part = h->b_part.p; sa.KS = ga.KS; sa.crp = crp;
+        sa.nsnp = nsnp; sa.out_offset = s0;
         sa.chisq = h->chisq.p; sa.pval = h->pval.p; sa.df = h->df.p; sa.rank = h->rank.p; sa.pivot = h->pivot.p; sa.coef = h->coef.p;
         sa.snp_df = do_perm ? h->snp_df.p : nullptr; sa.snp_sm = do_perm ? h->snp_sm.p : nullptr;
         sa.df_count = h->df_count.p;
         FLX_TRY(launch_snp_solve(sa, h->stream));
-        h->stats.launches += 2;
+        h->stats.launches += 3;
         mark();  // [4] perm start
         if (do_perm) {
             GemmArgs gp{};

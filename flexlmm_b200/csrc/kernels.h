@@ -63,20 +63,24 @@ struct FitConst {
 };
 struct GramArgs {
     const double* W;          // packed W tiles of the batch
-    const double* Qc;         // device [n_pad][crp] row-major, crp = cr rounded up to 4, zero padded rows/cols
+    const double* Qc;         // device [n_pad][crp] row-major, crp = padded basis width (gram_padded_width), zero padded
     const double* r;          // device [n_pad] residual of y on Qc (zero padded)
-    int KC; int cr; int s;
+    int KC; int cr; int crp; int s;
+    int KS;                   // sample splits
+    int cps;                  // k-chunks per split
     int64_t nsnp;
-    // per SNP outputs
-    double* nrm2;             // [nsnp][s]      ||w_t||^2
-    double* u;                // [nsnp][s][cr]  Qc' w_t
-    double* Ag;               // [nsnp][s(s+1)/2] residualised Gram
-    double* b;                // [nsnp][s]      w_r' r
+    // per split, per SNP partial sums (summed in fixed order by the consumers)
+    double* n_part;           // [KS][nsnp][s]        ||w_t||^2
+    double* u_part;           // [KS][nsnp][s][crp]   Qc' w_t
+    double* a_part;           // [KS][nsnp][s(s+1)/2] residualised Gram
+    double* b_part;           // [KS][nsnp][s]        w_r' r
 };
+int gram_padded_width(int cr);
 int launch_snp_gram(const GramArgs& a, cudaStream_t st);
 
 struct SolveArgs {
-    const double* nrm2; const double* u; const double* Ag; const double* b;
+    const double* n_part; const double* u_part; const double* a_part; const double* b_part;
+    int KS; int crp;
     int64_t nsnp;
     int64_t out_offset;       // first SNP of this batch in the run-wide outputs
     // outputs (run-wide arrays)
@@ -99,8 +103,8 @@ int launch_pack_tri(const double* Z, int64_t n, int64_t ld, int T, double* packe
 struct PermPrepArgs {
     double* UE;               // in: U1 * E (n x P col-major, ld = n_pad) ; out: residual Rf (in place)
     const double* y_pred;     // [n]
-    const double* Qc; int cr; // [n_pad][crp] row-major (crp = cr rounded up to 4)
-    const double* Qn; int cn; // [n_pad][cnp] row-major (null model basis)
+    const double* Qc; int cr; int crp; // [n_pad][crp] row-major
+    const double* Qn; int cn; int cnp; // [n_pad][cnp] row-major (null model basis)
     int64_t n, n_pad; int P;
     double* rss_f; double* rss0;  // [P]
 };

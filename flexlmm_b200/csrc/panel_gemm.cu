@@ -17,7 +17,7 @@ namespace flx {
 
 constexpr int STAGES = 5;
 constexpr int NCONS_WARPS = 8;
-constexpr int GEMM_THREADS = (NCONS_WARPS + 1) * 32;
+constexpr int GEMM_THREADS = (NCONS_WARPS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (1 active lane)
 constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
 
@@ -82,9 +82,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
 
     const int64_t n_items = g.n_items;
 
-    if (warp == NCONS_WARPS) {
-        // ===================== producer warp: one elected lane drives TMA =====================
-        if (lane == 0) {
+    if (warp >= NCONS_WARPS) {
+        // ===================== producer warpgroup: gives its registers away; one elected lane drives TMA =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == NCONS_WARPS && lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const double* a_src;
@@ -118,6 +119,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
     }
 
     // ===================== consumer warps: DMMA, warp tile = 128 (all 16 j-blocks of A) x 16 =====================
+    // The register file is split per SM sub-partition (16384 regs each): 2 consumer warps x 232 + 1 producer warp x 40.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int grp = lane >> 2;   // fragment row (A) / column (B) index
     const int qid = lane & 3;
     uint32_t stage = 0, phase = 0;
@@ -143,46 +146,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
         const int diag_start = (MODE == 0) ? 8 * I : (1 << 30);
         // row blocks (8 rows each) of this tile that hold real samples: only the last row tile can be partial
         const int i_hi = (MODE == 0 && I == g.T - 1) ? g.last_row_blocks : 16;
+
+        // Software-pipelined main loop: the fragments of k-step t+1 are fetched from shared memory while the DMMAs of
+        // k-step t issue (each A register is reloaded right after its last use), so the LDS latency and the mbarrier
+        // wait of the next stage hide behind tensor-pipe work.
+        mbar_wait(&full_bar[stage], phase);
+        const double* sA = stage_base + (size_t)stage * (2 * CHUNK) + lane;
+        double a[16], b[2];
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = sA[i * 32];
+#pragma unroll
+        for (int j = 0; j < 2; j++) b[j] = sA[CHUNK + (warp * 2 + j) * 32];
+
         for (int kc = 0; kc < nk; kc++) {
-            mbar_wait(&full_bar[stage], phase);
-            const double* sA = stage_base + (size_t)stage * (2 * CHUNK) + lane;
-            const double* sB = sA + CHUNK;
-            if (kc < diag_start && i_hi == 16) {
+            const int d = kc - diag_start;
+            const bool plain = (d < 0) && (i_hi == 16);
+            uint32_t nstage = stage + 1, nphase = phase;
+            if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    double a[16], b[2];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) a[i] = sA[(ks * 16 + i) * 32];
-#pragma unroll
-                    for (int j = 0; j < 2; j++) b[j] = sB[(ks * 16 + warp * 2 + j) * 32];
-#pragma unroll
-                    for (int i = 0; i < 16; i++)
-#pragma unroll
-                        for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int ks = 0; ks < 4; ks++) {
+                const double* nA;
+                if (ks < 3) {
+                    nA = sA + (ks + 1) * 16 * 32;
+                } else if (kc + 1 < nk) {
+                    mbar_wait(&full_bar[nstage], nphase);
+                    nA = stage_base + (size_t)nstage * (2 * CHUNK) + lane;
+                } else {
+                    nA = sA;  // nothing follows in this item: harmless re-read of the current stage
                 }
-            } else {
-                // (a) diagonal block of L^-1: k = 128 I + 16 d + 4 ks + (0..3); row block i (rows 8i..8i+7) is
-                //     non-zero only when 8 i + 7 >= 16 d + 4 ks;  (b) partial last row tile: row blocks >= i_hi are padding.
-                const int d = kc - diag_start;
+                double bn[2];
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
+                for (int j = 0; j < 2; j++) bn[j] = nA[CHUNK + (warp * 2 + j) * 32];
+                if (plain) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        dmma884(acc[i][0][0], acc[i][0][1], a[i], b[0]);
+                        dmma884(acc[i][1][0], acc[i][1][1], a[i], b[1]);
+                        a[i] = nA[i * 32];
+                    }
+                } else {
+                    // (a) diagonal block of L^-1: k = 128 I + 16 d + 4 ks + (0..3); row block i (rows 8i..8i+7) is non-zero
+                    //     only when 8 i + 7 >= 16 d + 4 ks;  (b) partial last row tile: row blocks >= i_hi are padding.
                     const int i_lo = (d >= 0) ? ((16 * d + 4 * ks) >> 3) : 0;
-                    double a[16], b[2];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) a[i] = (i >= i_lo && i < i_hi) ? sA[(ks * 16 + i) * 32] : 0.0;
-#pragma unroll
-                    for (int j = 0; j < 2; j++) b[j] = sB[(ks * 16 + warp * 2 + j) * 32];
-#pragma unroll
-                    for (int i = 0; i < 16; i++)
+                    for (int i = 0; i < 16; i++) {
                         if (i >= i_lo && i < i_hi) {
-#pragma unroll
-                            for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                            dmma884(acc[i][0][0], acc[i][0][1], a[i], b[0]);
+                            dmma884(acc[i][1][0], acc[i][1][1], a[i], b[1]);
                         }
+                        a[i] = nA[i * 32];
+                    }
                 }
+                b[0] = bn[0];
+                b[1] = bn[1];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            stage = nstage;
+            phase = nphase;
+            sA = stage_base + (size_t)stage * (2 * CHUNK) + lane;
         }
 
         if (MODE == 0) {

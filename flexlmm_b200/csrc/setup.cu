@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) perm_prep_kernel(const PermPrepArgs a) {
     __shared__ double coef[24];
     const int p = blockIdx.x;
     double* col = a.UE + (int64_t)p * a.n_pad;
-    const int crp = (a.cr + 3) & ~3, cnp = (a.cn + 3) & ~3;
+    const int crp = a.crp, cnp = a.cnp;
     // y*
     for (int64_t i = threadIdx.x; i < a.n_pad; i += 256) col[i] = (i < a.n) ? a.y_pred[i] + col[i] : 0.0;
     __syncthreads();

@@ -34,123 +34,154 @@ int upload_fit_const(const FitConst& c) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3a
+// K3a  — two sweeps over the whitened tile, split along the sample axis for parallelism.
+//   grid = (column tiles, KS sample splits); block = one warp per 8-SNP group of the tile.
+//   lane = (SNP within group = lane >> 2, sample phase = lane & 3): the packed panel stores, for one k-step, the 8 SNPs x 4
+//   samples of a group contiguously (256 B), so every warp load is two full 128-byte lines, and all warps of a CTA read
+//   the same Qc / r rows (L1 hits).  Partial sums are written per split and summed in fixed order by the consumer
+//   (deterministic, no atomics).
 // ------------------------------------------------------------------------------------------------
-constexpr int GRAM_WARPS = 4;
-constexpr int GRAM_THREADS = GRAM_WARPS * 32;
-constexpr int GRAM_JB = 8;
+template <int S, int CRP>
+struct GramCfg {
+    static constexpr bool UREG = (S * CRP <= 64);   // Qc' w coordinates live in registers
+    static constexpr int GROUPS = 16 / S;
+    static constexpr int THREADS = GROUPS * 32;
+    static constexpr int NSYM = S * (S + 1) / 2;
+};
 
-template <int S>
-__global__ void __launch_bounds__(GRAM_THREADS) snp_gram_kernel(const GramArgs a) {
-    constexpr int NSYM = S * (S + 1) / 2;
-    const TileShape ts = make_tile_shape(S);
-    const int J = blockIdx.x / ts.groups;
-    const int gi = blockIdx.x % ts.groups;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// sweep 1: u = Qc' w (per split), ||w||^2
+template <int S, int CRP>
+__global__ void __launch_bounds__(GramCfg<S, CRP>::THREADS) snp_gram1_kernel(const GramArgs a) {
+    using C = GramCfg<S, CRP>;
+    const int J = blockIdx.x, ks = blockIdx.y;
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 2, kp = lane & 3;
-    const int cr = a.cr;
-    const int crp = (cr + 3) & ~3;  // Qc row stride (padded to 4)
-    const double* wt = a.W + (int64_t)J * a.KC * CHUNK + ((S * gi) << 5) + lane;
+    const int kc0 = ks * a.cps, kc1 = min(kc0 + a.cps, a.KC);
+    const double* wt = a.W + (int64_t)J * a.KC * CHUNK + ((S * g) << 5) + lane;
+    const int64_t snp = (int64_t)J * (8 * C::GROUPS) + 8 * g + grp;
 
-    extern __shared__ __align__(16) double sm[];
-    double* u_s = sm;                         // [8][S][crp]
-    double* red = sm + 8 * S * crp;           // [GRAM_WARPS][8][max(S*GRAM_JB, NSYM + S) ]
-    constexpr int REDW = (S * GRAM_JB > NSYM + 2 * S) ? S * GRAM_JB : NSYM + 2 * S;
-
-    // ---------------- pass 1: u = Qc' w in blocks of GRAM_JB basis vectors; column norms on the first sweep
     double nrm[S];
 #pragma unroll
     for (int t = 0; t < S; t++) nrm[t] = 0.0;
-    for (int jb = 0; jb < crp || jb == 0; jb += GRAM_JB) {
-        double acc[S][GRAM_JB];
+    constexpr int JB = C::UREG ? CRP : 8;
+    for (int jb = 0; jb < CRP; jb += JB) {
+        double acc[S][JB];
 #pragma unroll
         for (int t = 0; t < S; t++)
 #pragma unroll
-            for (int j = 0; j < GRAM_JB; j++) acc[t][j] = 0.0;
-        const int jn = min(GRAM_JB, crp - jb);  // multiple of 4 (or <= 0 when cr == 0)
+            for (int j = 0; j < JB; j++) acc[t][j] = 0.0;
 #pragma unroll 2
-        for (int kc = warp; kc < a.KC; kc += GRAM_WARPS) {
+        for (int kc = kc0; kc < kc1; kc++) {
             const double* wc = wt + (int64_t)kc * CHUNK;
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-                const int64_t k = (int64_t)kc * KCH + 4 * ks + kp;
+            for (int k4 = 0; k4 < 4; k4++) {
+                const int64_t k = (int64_t)kc * KCH + 4 * k4 + kp;
                 double w[S];
 #pragma unroll
-                for (int t = 0; t < S; t++) w[t] = wc[(ks * 16 + t) << 5];
+                for (int t = 0; t < S; t++) w[t] = wc[(k4 * 16 + t) << 5];
                 if (jb == 0) {
 #pragma unroll
                     for (int t = 0; t < S; t++) nrm[t] = fma(w[t], w[t], nrm[t]);
                 }
-                const double* q = a.Qc + k * crp + jb;
-                if (jn > 0) {
-                    const double2 q01 = __ldg(reinterpret_cast<const double2*>(q));
-                    const double2 q23 = __ldg(reinterpret_cast<const double2*>(q + 2));
+                const double2* q = reinterpret_cast<const double2*>(a.Qc + k * CRP + jb);
 #pragma unroll
-                    for (int t = 0; t < S; t++) {
-                        acc[t][0] = fma(w[t], q01.x, acc[t][0]); acc[t][1] = fma(w[t], q01.y, acc[t][1]);
-                        acc[t][2] = fma(w[t], q23.x, acc[t][2]); acc[t][3] = fma(w[t], q23.y, acc[t][3]);
-                    }
-                }
-                if (jn > 4) {
-                    const double2 q45 = __ldg(reinterpret_cast<const double2*>(q + 4));
-                    const double2 q67 = __ldg(reinterpret_cast<const double2*>(q + 6));
+                for (int j = 0; j < JB; j += 2) {
+                    if (jb + j < CRP) {
+                        const double2 qq = __ldg(q + (j >> 1));
 #pragma unroll
-                    for (int t = 0; t < S; t++) {
-                        acc[t][4] = fma(w[t], q45.x, acc[t][4]); acc[t][5] = fma(w[t], q45.y, acc[t][5]);
-                        acc[t][6] = fma(w[t], q67.x, acc[t][6]); acc[t][7] = fma(w[t], q67.y, acc[t][7]);
+                        for (int t = 0; t < S; t++) {
+                            acc[t][j] = fma(w[t], qq.x, acc[t][j]);
+                            acc[t][j + 1] = fma(w[t], qq.y, acc[t][j + 1]);
+                        }
                     }
                 }
             }
         }
-        // reduce over the 4 sample phases of the quad, then across warps through shared memory
 #pragma unroll
         for (int t = 0; t < S; t++)
 #pragma unroll
-            for (int j = 0; j < GRAM_JB; j++) {
+            for (int j = 0; j < JB; j++) {
                 double v = acc[t][j];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (kp == 0) red[(warp * 8 + grp) * REDW + t * GRAM_JB + j] = v;
+                if (kp == 0 && jb + j < CRP && snp < a.nsnp) a.u_part[(((int64_t)ks * a.nsnp + snp) * S + t) * CRP + jb + j] = v;
             }
-        __syncthreads();
-        for (int e = threadIdx.x; e < 8 * S * GRAM_JB; e += GRAM_THREADS) {
-            const int g8 = e / (S * GRAM_JB), rem = e % (S * GRAM_JB);
-            const int t = rem / GRAM_JB, j = rem % GRAM_JB;
-            if (jb + j < crp) {
-                double v = 0.0;
-#pragma unroll
-                for (int w2 = 0; w2 < GRAM_WARPS; w2++) v += red[(w2 * 8 + g8) * REDW + rem];
-                u_s[(g8 * S + t) * crp + jb + j] = v;
-            }
-        }
-        __syncthreads();
-        if (crp == 0) break;
     }
+#pragma unroll
+    for (int t = 0; t < S; t++) {
+        double v = nrm[t];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (kp == 0 && snp < a.nsnp) a.n_part[((int64_t)ks * a.nsnp + snp) * S + t] = v;
+    }
+}
 
-    // ---------------- pass 2: explicit residualisation, Gram and right-hand side
+// sweep 2: w_r = w - Qc u (explicit residualisation), A = W_r' W_r, b = W_r' r  (per split)
+template <int S, int CRP>
+__global__ void __launch_bounds__(GramCfg<S, CRP>::THREADS) snp_gram2_kernel(const GramArgs a) {
+    using C = GramCfg<S, CRP>;
+    constexpr int NSYM = C::NSYM;
+    const int J = blockIdx.x, ks = blockIdx.y;
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 2, kp = lane & 3;
+    const int kc0 = ks * a.cps, kc1 = min(kc0 + a.cps, a.KC);
+    const double* wt = a.W + (int64_t)J * a.KC * CHUNK + ((S * g) << 5) + lane;
+    const int64_t snp = (int64_t)J * (8 * C::GROUPS) + 8 * g + grp;
+    const bool live = snp < a.nsnp;
+
+    extern __shared__ __align__(16) double u_sm[];   // only when !UREG: [GROUPS][8][S][CRP]
+    double u[C::UREG ? S : 1][C::UREG ? CRP : 1];
+    // total u over the splits, fixed order
+    if constexpr (C::UREG) {
+#pragma unroll
+        for (int t = 0; t < S; t++)
+#pragma unroll
+            for (int j = 0; j < CRP; j++) {
+                double v = 0.0;
+                if (live)
+                    for (int q = 0; q < a.KS; q++) v += a.u_part[(((int64_t)q * a.nsnp + snp) * S + t) * CRP + j];
+                u[t][j] = v;
+            }
+    } else {
+        if (kp == 0)
+            for (int e = 0; e < S * CRP; e++) {
+                double v = 0.0;
+                if (live)
+                    for (int q = 0; q < a.KS; q++) v += a.u_part[((int64_t)q * a.nsnp + snp) * S * CRP + e];
+                u_sm[((g * 8 + grp) * S) * CRP + e] = v;
+            }
+        __syncwarp();
+    }
+    const double* ug = u_sm + ((g * 8 + grp) * S) * CRP;
+
     double ag[NSYM], bb[S];
 #pragma unroll
     for (int q = 0; q < NSYM; q++) ag[q] = 0.0;
 #pragma unroll
     for (int t = 0; t < S; t++) bb[t] = 0.0;
-    const double* ug = u_s + (grp * S) * crp;
 #pragma unroll 2
-    for (int kc = warp; kc < a.KC; kc += GRAM_WARPS) {
+    for (int kc = kc0; kc < kc1; kc++) {
         const double* wc = wt + (int64_t)kc * CHUNK;
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-            const int64_t k = (int64_t)kc * KCH + 4 * ks + kp;
+        for (int k4 = 0; k4 < 4; k4++) {
+            const int64_t k = (int64_t)kc * KCH + 4 * k4 + kp;
             double w[S];
 #pragma unroll
-            for (int t = 0; t < S; t++) w[t] = wc[(ks * 16 + t) << 5];
-            const double* q = a.Qc + k * crp;
-            for (int j = 0; j < crp; j += 2) {
-                const double2 qq = __ldg(reinterpret_cast<const double2*>(q + j));
+            for (int t = 0; t < S; t++) w[t] = wc[(k4 * 16 + t) << 5];
+            const double2* q = reinterpret_cast<const double2*>(a.Qc + k * CRP);
+#pragma unroll
+            for (int j = 0; j < CRP; j += 2) {
+                const double2 qq = __ldg(q + (j >> 1));
 #pragma unroll
                 for (int t = 0; t < S; t++) {
-                    const double2 uu = *reinterpret_cast<const double2*>(ug + t * crp + j);
-                    w[t] = fma(-qq.x, uu.x, w[t]);
-                    w[t] = fma(-qq.y, uu.y, w[t]);
+                    if constexpr (C::UREG) {
+                        w[t] = fma(-qq.x, u[t][j], w[t]);
+                        w[t] = fma(-qq.y, u[t][j + 1], w[t]);
+                    } else {
+                        const double2 uu = *reinterpret_cast<const double2*>(ug + t * CRP + j);
+                        w[t] = fma(-qq.x, uu.x, w[t]);
+                        w[t] = fma(-qq.y, uu.y, w[t]);
+                    }
                 }
             }
             const double rk = __ldg(a.r + k);
@@ -163,48 +194,48 @@ __global__ void __launch_bounds__(GRAM_THREADS) snp_gram_kernel(const GramArgs a
             }
         }
     }
-    // reduce: quad lanes, then warps
 #pragma unroll
-    for (int q = 0; q < NSYM + 2 * S; q++) {
-        double v = (q < NSYM) ? ag[q < NSYM ? q : 0] : (q < NSYM + S ? bb[(q - NSYM) < S ? (q - NSYM) : 0] : nrm[(q - NSYM - S) < S ? (q - NSYM - S) : 0]);
+    for (int q = 0; q < NSYM; q++) {
+        double v = ag[q];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (kp == 0) red[(warp * 8 + grp) * REDW + q] = v;
+        if (kp == 0 && live) a.a_part[((int64_t)ks * a.nsnp + snp) * NSYM + q] = v;
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 8 * (NSYM + 2 * S); e += GRAM_THREADS) {
-        const int g8 = e / (NSYM + 2 * S), q = e % (NSYM + 2 * S);
-        const int64_t snp = (int64_t)J * ts.snps + 8 * gi + g8;
-        if (snp < a.nsnp) {
-            double v = 0.0;
 #pragma unroll
-            for (int w2 = 0; w2 < GRAM_WARPS; w2++) v += red[(w2 * 8 + g8) * REDW + q];
-            if (q < NSYM) a.Ag[snp * NSYM + q] = v;
-            else if (q < NSYM + S) a.b[snp * S + (q - NSYM)] = v;
-            else a.nrm2[snp * S + (q - NSYM - S)] = v;
-        }
-    }
-    for (int e = threadIdx.x; e < 8 * S * cr; e += GRAM_THREADS) {
-        const int g8 = e / (S * cr), rem = e % (S * cr);
-        const int t = rem / cr, j = rem % cr;
-        const int64_t snp = (int64_t)J * ts.snps + 8 * gi + g8;
-        if (snp < a.nsnp) a.u[(snp * S + t) * cr + j] = u_s[(g8 * S + t) * crp + j];
+    for (int t = 0; t < S; t++) {
+        double v = bb[t];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (kp == 0 && live) a.b_part[((int64_t)ks * a.nsnp + snp) * S + t] = v;
     }
 }
 
-template <int S>
-static int launch_gram_s(const GramArgs& a, cudaStream_t st) {
-    constexpr int NSYM = S * (S + 1) / 2;
-    constexpr int REDW = (S * GRAM_JB > NSYM + 2 * S) ? S * GRAM_JB : NSYM + 2 * S;
-    const TileShape ts = make_tile_shape(S);
-    const int crp = (a.cr + 3) & ~3;
-    const int64_t NJ = (a.nsnp + ts.snps - 1) / ts.snps;
-    const size_t smem = sizeof(double) * (8 * S * crp + GRAM_WARPS * 8 * REDW);
-    snp_gram_kernel<S><<<(unsigned)(NJ * ts.groups), GRAM_THREADS, smem, st>>>(a);
+template <int S, int CRP>
+static int launch_gram_sc(const GramArgs& a, cudaStream_t st) {
+    using C = GramCfg<S, CRP>;
+    const int64_t NJ = (a.nsnp + 8 * C::GROUPS - 1) / (8 * C::GROUPS);
+    dim3 grid((unsigned)NJ, (unsigned)a.KS);
+    snp_gram1_kernel<S, CRP><<<grid, C::THREADS, 0, st>>>(a);
+    const size_t smem = C::UREG ? 0 : sizeof(double) * C::GROUPS * 8 * S * CRP;
+    snp_gram2_kernel<S, CRP><<<grid, C::THREADS, smem, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("snp_gram launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
 }
+
+template <int S>
+static int launch_gram_s(const GramArgs& a, cudaStream_t st) {
+    switch (a.crp) {
+        case 4: return launch_gram_sc<S, 4>(a, st);
+        case 8: return launch_gram_sc<S, 8>(a, st);
+        case 16: return launch_gram_sc<S, 16>(a, st);
+        case 24: return launch_gram_sc<S, 24>(a, st);
+    }
+    set_error("snp_gram: unsupported padded basis width %d", a.crp);
+    return -1;
+}
+
+int gram_padded_width(int cr) { return cr <= 4 ? 4 : cr <= 8 ? 8 : cr <= 16 ? 16 : 24; }
 
 int launch_snp_gram(const GramArgs& a, cudaStream_t st) {
     if (a.nsnp <= 0) return 0;
@@ -273,10 +304,20 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     double bq[MAXS], qsr[MAXS], nrm2[MAXS];
     bool alive[MAXS];
     {
+        // partial sums of the sample splits, fixed order
         int q = 0;
         for (int t = 0; t < s; t++)
-            for (int v = t; v < s; v++) { A[t][v] = A[v][t] = a.Ag[snp * nsym + q]; q++; }
-        for (int t = 0; t < s; t++) { bq[t] = a.b[snp * s + t]; nrm2[t] = a.nrm2[snp * s + t]; }
+            for (int v = t; v < s; v++) {
+                double acc = 0.0;
+                for (int p = 0; p < a.KS; p++) acc += a.a_part[((int64_t)p * a.nsnp + snp) * nsym + q];
+                A[t][v] = A[v][t] = acc;
+                q++;
+            }
+        for (int t = 0; t < s; t++) {
+            double ab = 0.0, an = 0.0;
+            for (int p = 0; p < a.KS; p++) { ab += a.b_part[((int64_t)p * a.nsnp + snp) * s + t]; an += a.n_part[((int64_t)p * a.nsnp + snp) * s + t]; }
+            bq[t] = ab; nrm2[t] = an;
+        }
     }
     // guarded Cholesky A = Rs' Rs in term order; a vanished pivot leaves a zero row (direction dropped)
     for (int l = 0; l < s; l++) {
@@ -324,7 +365,11 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             for (int i = 0; i < cr; i++) col[i] = c.Rc[i + kind * MAXK];
         } else {
             const int t = -kind - 1;
-            for (int i = 0; i < cr; i++) col[i] = a.u[(snp * s + t) * cr + i];
+            for (int i = 0; i < cr; i++) {
+                double acc = 0.0;
+                for (int p = 0; p < a.KS; p++) acc += a.u_part[(((int64_t)p * a.nsnp + snp) * s + t) * a.crp + i];
+                col[i] = acc;
+            }
             for (int i = 0; i <= t; i++) col[cr + i] = Rs[i][t];
         }
     }
