@@ -90,6 +90,8 @@ struct flx_handle {
     int64_t n = 0, n_pad = 0;
     int KC = 0, T = 0;
     DevBuf<double> linv;     // triangular packed panels
+    DevBuf<double> Zdense;   // dense L^-1 (kept until finalize when the int8 path may be used)
+    bool have_Z = false;
     // null model
     bool have_null = false;
     std::vector<double> X_null, y_mm;
@@ -118,6 +120,12 @@ struct flx_handle {
     int64_t P_pad = 0;
     int NP = 0;
     DevBuf<double> Rpk, inv_rss, lrs0p, maxratio, minp_d;
+    // int8 quadratic-form path (K2q)
+    bool fast = false;
+    int Q = 6, T256 = 0, NKB = 0, crpH = 4;
+    DevBuf<int8_t> T8, X8;
+    DevBuf<double> rowscale, Hrow, qf_part;
+    DevBuf<int32_t> refit_flag, out_map_d;
     DevBuf<int> df_count, missing;
 
     // genotype source
@@ -220,20 +228,23 @@ extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int6
     h->KC = (int)(h->n_pad / KCH);
     h->T = (int)(h->n_pad / TJ);
     h->dirty = true;
-    DevBuf<double> Ld, Z;
+    // dense L and L^-1 live on the device during setup (n <= ~45000 in this round)
+    DevBuf<double> Ld;
     FLX_TRY(Ld.ensure((size_t)n * n));
     FLX_CUDA_TRY(cudaMemcpy2DAsync(Ld.p, n * sizeof(double), L, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
-    const double* inv = Ld.p;
+    FLX_TRY(h->Zdense.ensure((size_t)n * n));
     if (!is_inverse) {
         // Z = L^-1 by a triangular solve against the identity (setup only; library call outside the hot loop)
-        FLX_TRY(Z.ensure((size_t)n * n));
-        FLX_TRY(launch_set_identity(Z.p, n, n, h->stream));
+        FLX_TRY(launch_set_identity(h->Zdense.p, n, n, h->stream));
         const double one = 1.0;
-        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)n, &one, Ld.p, (int)n, Z.p, (int)n));
-        inv = Z.p;
+        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)n, &one, Ld.p, (int)n, h->Zdense.p, (int)n));
+    } else {
+        FLX_CUDA_TRY(cudaMemcpyAsync(h->Zdense.p, Ld.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        FLX_TRY(launch_zero_upper(h->Zdense.p, n, n, h->stream));
     }
+    h->have_Z = true;
     FLX_TRY(h->linv.ensure((size_t)tri_chunks_before(h->T) * CHUNK));
-    FLX_TRY(launch_pack_tri(inv, n, n, h->T, h->linv.p, h->stream));
+    FLX_TRY(launch_pack_tri(h->Zdense.p, n, n, h->T, h->linv.p, h->stream));
     FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return FLX_OK;
 }
@@ -459,6 +470,42 @@ static int finalize_setup(flx_handle* h) {
     FLX_TRY(h->Qn.ensure(tmp.size()));
     FLX_CUDA_TRY(cudaMemcpy(h->Qn.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
 
+    // ---- int8 quadratic-form path (K2q): one SNP term whose values are small integers for every sample (x itself, I(x==1), ...)
+    h->fast = false;
+    if (!(h->cfg.flags & FLX_FLAG_NO_INT8) && h->have_Z && h->s == 1 && (h->uniform_mask & 1u) && cr + 1 <= 24) {
+        bool ints = true;
+        for (int g = 0; g < 3; g++) ints = ints && (h->uni[0][g] == std::floor(h->uni[0][g])) && std::fabs(h->uni[0][g]) <= 2.0;
+        h->fast = ints;
+    }
+    if (h->fast) {
+        const double one = 1.0, zero = 0.0;
+        h->T256 = (int)((n + 255) / 256);
+        h->NKB = h->T256 * 4;
+        h->crpH = gram_padded_width(cr + 1);
+        // V^-1 = L^-T L^-1 (lower), digit planes of its lower triangle
+        DevBuf<double> V;
+        FLX_TRY(V.ensure((size_t)n * n));
+        FLX_CUBLAS_TRY(cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, (int)n, (int)n, &one, h->Zdense.p, (int)n, &zero, V.p, (int)n));
+        FLX_TRY(h->rowscale.ensure((size_t)h->T256 * 256));
+        FLX_TRY(h->T8.ensure((size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384));
+        FLX_TRY(launch_qf_slice(V.p, n, n, h->T256, h->Q, h->rowscale.p, h->T8.p, h->stream));
+        // H = L^-T [Qc | r]  (n x (cr+1)), stored row-major padded like Qc
+        std::vector<double> Hc((size_t)n * (cr + 1));
+        memcpy(Hc.data(), Qc.data(), (size_t)n * cr * sizeof(double));
+        memcpy(Hc.data() + (size_t)n * cr, r.data(), (size_t)n * sizeof(double));
+        DevBuf<double> Hd;
+        FLX_TRY(Hd.ensure(Hc.size()));
+        FLX_CUDA_TRY(cudaMemcpyAsync(Hd.p, Hc.data(), Hc.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, cr + 1, &one, h->Zdense.p, (int)n, Hd.p, (int)n, Hd.p, (int)n));
+        FLX_CUDA_TRY(cudaMemcpyAsync(Hc.data(), Hd.p, Hc.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        std::vector<double> Hrow((size_t)n_pad * h->crpH + 8, 0.0);
+        for (int j = 0; j <= cr; j++)
+            for (int64_t i = 0; i < n; i++) Hrow[i * h->crpH + j] = Hc[i + (size_t)j * n];
+        FLX_TRY(h->Hrow.ensure(Hrow.size()));
+        FLX_CUDA_TRY(cudaMemcpy(h->Hrow.p, Hrow.data(), Hrow.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+
     // ---- permutation prologue (fit_model.nf:96-101) for all seeds at once
     h->P_pad = 0; h->NP = 0;
     if (h->have_perm && h->P > 0) {
@@ -498,6 +545,10 @@ static int finalize_setup(flx_handle* h) {
         pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.crp = gram_padded_width(cr); pa.Qn = h->Qn.p; pa.cn = h->cn; pa.cnp = gram_padded_width(h->cn);
         pa.n = n; pa.n_pad = n_pad; pa.P = P; pa.rss_f = rssf_d.p; pa.rss0 = rss0_d.p;
         FLX_TRY(launch_perm_prep(pa, h->stream));
+        if (h->fast) {
+            // the contraction runs against the raw genotypes: R_f -> L^-T R_f  (b* = x' L^-T r*)
+            FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, P, &one, h->Zdense.p, (int)n, UE.p, (int)n_pad, UE.p, (int)n_pad));
+        }
         FLX_TRY(h->Rpk.ensure((size_t)h->NP * h->KC * CHUNK));
         FLX_TRY(launch_pack_cols(UE.p, n, n_pad, h->P_pad, h->KC, h->Rpk.p, h->stream));
         std::vector<double> rssf(P), rss0(P);
@@ -519,13 +570,19 @@ static int finalize_setup(flx_handle* h) {
     }
     FLX_TRY(h->df_count.ensure(16));
     FLX_TRY(h->missing.ensure(1));
+    h->Zdense.release();
+    h->have_Z = false;
     h->dirty = false;
     return FLX_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
+// use_fast: K2q (int8 quadratic form) instead of K2 + K3a sweep 2.  accumulate: second pass over a subset (refit of flagged
+// SNPs on the FP64 path) — run-wide accumulators are kept and results go to the slots out_map_host[q].
 static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool want_results, bool do_perm,
-                       double* X_out_dense, uint8_t* codes_out) {
+                       double* X_out_dense, uint8_t* codes_out, bool use_fast = false, bool accumulate = false,
+                       const int32_t* out_map_host = nullptr, int64_t M_total = 0) {
+    if (M_total < M) M_total = M;
     const TileShape ts = make_tile_shape(h->s);
     const int tiles_per_batch = h->cfg.batch_tiles > 0 ? h->cfg.batch_tiles : h->num_sms;
     const int64_t snps_per_batch = (int64_t)tiles_per_batch * ts.snps;
@@ -533,8 +590,9 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const int64_t bpv = h->bpv;
     const int nsym = h->s * (h->s + 1) / 2;
     const int cr = h->cr;
-    const int crp = gram_padded_width(cr);
+    const int crp = use_fast ? h->crpH : gram_padded_width(cr);
     constexpr int KS_MAX = 32;
+    const int QG = h->Q / 2;
     const bool decode_only = (X_out_dense != nullptr) || (codes_out != nullptr);
 
     // validate indices; contiguity lets the resident path skip the index map
@@ -546,15 +604,25 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const size_t tile_elems = (size_t)h->KC * CHUNK;
     FLX_TRY(h->X.ensure((size_t)tiles_per_batch * tile_elems));
     if (!decode_only) {
-        FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
+        if (!use_fast) FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
+        if (use_fast) {
+            FLX_TRY(h->X8.ensure((size_t)tiles_per_batch * h->NKB * 8192));
+            FLX_TRY(h->qf_part.ensure((size_t)h->T256 * QG * snps_per_batch));
+            FLX_TRY(h->refit_flag.ensure(M_total));
+        }
         FLX_TRY(h->n_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
         FLX_TRY(h->u_part.ensure((size_t)KS_MAX * snps_per_batch * h->s * crp));
         FLX_TRY(h->a_part.ensure((size_t)KS_MAX * snps_per_batch * nsym));
         FLX_TRY(h->b_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
         FLX_TRY(h->snp_sm.ensure((size_t)snps_per_batch * nsym));
         FLX_TRY(h->snp_df.ensure((size_t)snps_per_batch));
-        FLX_TRY(h->chisq.ensure(M)); FLX_TRY(h->pval.ensure(M)); FLX_TRY(h->df.ensure(M)); FLX_TRY(h->rank.ensure(M));
-        FLX_TRY(h->pivot.ensure((size_t)M * h->k)); FLX_TRY(h->coef.ensure((size_t)M * h->k));
+        FLX_TRY(h->chisq.ensure(M_total)); FLX_TRY(h->pval.ensure(M_total)); FLX_TRY(h->df.ensure(M_total)); FLX_TRY(h->rank.ensure(M_total));
+        FLX_TRY(h->pivot.ensure((size_t)M_total * h->k)); FLX_TRY(h->coef.ensure((size_t)M_total * h->k));
+        if (out_map_host) {
+            FLX_TRY(h->out_map_d.ensure(M));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->out_map_d.p, out_map_host, M * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
     }
     DevBuf<uint8_t> codes_d;
     if (codes_out) FLX_TRY(codes_d.ensure((size_t)snps_per_batch * h->n));
@@ -572,9 +640,11 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             FLX_TRY(h->staging[i].ensure((size_t)snps_per_batch * bpv));
         }
     const int int_max = INT_MAX;
-    FLX_CUDA_TRY(cudaMemcpyAsync(h->missing.p, &int_max, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    FLX_CUDA_TRY(cudaMemsetAsync(h->df_count.p, 0, 16 * sizeof(int), h->stream));
-    if (do_perm) FLX_CUDA_TRY(cudaMemsetAsync(h->maxratio.p, 0, (size_t)h->s * h->P_pad * sizeof(double), h->stream));
+    if (!accumulate) {
+        FLX_CUDA_TRY(cudaMemcpyAsync(h->missing.p, &int_max, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUDA_TRY(cudaMemsetAsync(h->df_count.p, 0, 16 * sizeof(int), h->stream));
+        if (do_perm) FLX_CUDA_TRY(cudaMemsetAsync(h->maxratio.p, 0, (size_t)h->s * h->P_pad * sizeof(double), h->stream));
+    }
     if (!decode_only) FLX_TRY(upload_fit_const(h->fc));
 
     std::vector<cudaEvent_t> evs;
@@ -644,20 +714,40 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             mark(); mark(); mark();
             continue;
         }
-        GemmArgs g{};
-        g.A = h->linv.p; g.B = h->X.p; g.Out = h->W.p;
-        g.T = h->T; g.NJ = NJ; g.KC = h->KC; g.n_items = (int64_t)h->T * NJ;
-        g.KC_live = (int)((h->n + KCH - 1) / KCH); g.last_row_blocks = (int)((h->n - (int64_t)(h->T - 1) * TJ + 7) / 8);
-        FLX_TRY(launch_whiten(g, h->num_sms, h->stream));
-        h->stats.launches++; h->stats.launches_whiten++;
-        mark();  // [3] fit start
         GramArgs ga{};
-        ga.W = h->W.p; ga.Qc = h->Qc.p; ga.r = h->r.p; ga.KC = h->KC; ga.cr = cr; ga.crp = crp; ga.s = h->s; ga.nsnp = nsnp;
+        ga.KC = h->KC; ga.cr = cr; ga.crp = crp; ga.s = h->s; ga.nsnp = nsnp;
         // sample splits: a function of n only, so a SNP's result never depends on which other SNPs share its batch
         ga.cps = std::max(64, (h->KC + KS_MAX - 1) / KS_MAX);
         ga.KS = (h->KC + ga.cps - 1) / ga.cps;
         ga.n_part = h->n_part.p; ga.u_part = h->u_part.p; ga.a_part = h->a_part.p; ga.b_part = h->b_part.p;
-        FLX_TRY(launch_snp_gram(ga, h->stream));
+        if (use_fast) {
+            // K1q + K2q: int8 tile and the exact quadratic form x' V^-1 x on the i8 tensor pipe
+            FLX_TRY(launch_decode_i8(da, h->X8.p, NJ, h->NKB, h->stream));
+            QfArgs q{};
+            q.X8 = h->X8.p; q.T8 = h->T8.p; q.rowscale = h->rowscale.p; q.part = h->qf_part.p;
+            for (int i = 0; i < 4; i++) q.group_scale[i] = std::ldexp(1.0, -16 * (i + 1));
+            q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.QG = QG; q.Q = h->Q; q.NKB = h->NKB;
+            q.NKB_live = (int)((h->n + 63) / 64);
+            q.n_items = (int64_t)h->T256 * NJ * QG;
+            FLX_TRY(launch_qf(q, h->num_sms, h->stream));
+            h->stats.launches += 2; h->stats.launches_whiten++;
+            mark();  // [3] fit start
+            // u = (L^-T Qc)' x, b = (L^-T r)' x : one sweep of the FP64 design tile against H
+            ga.W = h->X.p; ga.Qc = h->Hrow.p; ga.r = h->r.p;
+            FLX_TRY(launch_snp_gram_sweep1(ga, h->stream));
+            h->stats.launches += 1;
+        } else {
+            GemmArgs g{};
+            g.A = h->linv.p; g.B = h->X.p; g.Out = h->W.p;
+            g.T = h->T; g.NJ = NJ; g.KC = h->KC; g.n_items = (int64_t)h->T * NJ;
+            g.KC_live = (int)((h->n + KCH - 1) / KCH); g.last_row_blocks = (int)((h->n - (int64_t)(h->T - 1) * TJ + 7) / 8);
+            FLX_TRY(launch_whiten(g, h->num_sms, h->stream));
+            h->stats.launches++; h->stats.launches_whiten++;
+            mark();  // [3] fit start
+            ga.W = h->W.p; ga.Qc = h->Qc.p; ga.r = h->r.p;
+            FLX_TRY(launch_snp_gram(ga, h->stream));
+            h->stats.launches += 2;
+        }
         if (do_perm) {
             FLX_CUDA_TRY(cudaMemsetAsync(h->snp_df.p, 0, (size_t)snps_per_batch * sizeof(int32_t), h->stream));
             FLX_CUDA_TRY(cudaMemsetAsync(h->snp_sm.p, 0, (size_t)snps_per_batch * nsym * sizeof(double), h->stream));
@@ -665,24 +755,24 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         SolveArgs sa{};
         sa.n_part = h->n_part.p; sa.u_part = h->u_part.p; sa.a_part = h->a_part.p; sa.b_part = h->b_part.p; sa.KS = ga.KS; sa.crp = crp;
         sa.nsnp = nsnp; sa.out_offset = s0;
+        sa.out_map = out_map_host ? h->out_map_d.p + s0 : nullptr;
         sa.chisq = h->chisq.p; sa.pval = h->pval.p; sa.df = h->df.p; sa.rank = h->rank.p; sa.pivot = h->pivot.p; sa.coef = h->coef.p;
         sa.snp_df = do_perm ? h->snp_df.p : nullptr; sa.snp_sm = do_perm ? h->snp_sm.p : nullptr;
         sa.df_count = h->df_count.p;
+        sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * QG;
+        sa.refit_flag = use_fast ? h->refit_flag.p + s0 : nullptr;
         FLX_TRY(launch_snp_solve(sa, h->stream));
-        h->stats.launches += 3;
+        h->stats.launches += 1;
         mark();  // [4] perm start
         if (do_perm) {
             GemmArgs gp{};
-            gp.A = h->W.p; gp.B = h->Rpk.p; gp.NJ = NJ; gp.NP = h->NP; gp.KC = h->KC; gp.n_items = (int64_t)NJ * h->NP;
+            gp.A = use_fast ? h->X.p : h->W.p;   // int8 path: b* = x' (L^-T r*), the contraction runs on the raw design tile
+            gp.B = h->Rpk.p; gp.NJ = NJ; gp.NP = h->NP; gp.KC = h->KC; gp.n_items = (int64_t)NJ * h->NP;
             gp.snp_df = h->snp_df.p; gp.snp_sm = h->snp_sm.p; gp.perm_inv_rss = h->inv_rss.p; gp.perm_maxratio = h->maxratio.p; gp.P_pad = h->P_pad;
             FLX_TRY(launch_perm_contract(gp, h->s, h->num_sms, h->stream));
             h->stats.launches++;
         }
         mark();  // [5] batch end
-    }
-    if (do_perm && !decode_only) {
-        FLX_TRY(launch_minp_finalize(h->maxratio.p, h->P_pad, h->P, h->s, h->lrs0p.p, (double)h->n, h->df_count.p, h->minp_d.p, h->stream));
-        h->stats.launches++;
     }
     mark();
     FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -696,7 +786,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         cudaEventElapsedTime(&ms, e[3], e[4]); h->stats.ms_fit += ms;
         cudaEventElapsedTime(&ms, e[4], e[5]); h->stats.ms_perm += ms;
     }
-    if (!evs.empty()) { float ms; cudaEventElapsedTime(&ms, evs.front(), evs.back()); h->stats.ms_total = ms; }
+    if (!evs.empty()) { float ms; cudaEventElapsedTime(&ms, evs.front(), evs.back()); h->stats.ms_total += ms; }
     for (auto e : evs) cudaEventDestroy(e);
     int miss = INT_MAX;
     FLX_CUDA_TRY(cudaMemcpy(&miss, h->missing.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -718,7 +808,25 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
     const bool do_perm = h->have_perm && h->P > 0;
     if (minp && !do_perm) { set_error("flx_run: minp requested but no permutations were set (flx_set_perm)"); return FLX_ERR_STATE; }
     h->stats.snps = M; h->stats.n_pad = h->n_pad; h->stats.cols_per_tile = make_tile_shape(h->s).blocks * 8;
-    if (M > 0) FLX_TRY(run_batches(h, var_idx, M, out != nullptr, do_perm, nullptr, nullptr));
+    if (M > 0) {
+        const bool fast = h->fast;
+        h->stats.int8_path = fast ? 1 : 0;
+        FLX_TRY(run_batches(h, var_idx, M, out != nullptr, do_perm, nullptr, nullptr, fast, false, nullptr, M));
+        if (fast) {
+            // SNPs whose x is (nearly) in the span of the constant columns lose digits in A = x'V^-1x - |u|^2: re-fit them in FP64
+            std::vector<int32_t> flags(M);
+            FLX_CUDA_TRY(cudaMemcpy(flags.data(), h->refit_flag.p, M * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            std::vector<int32_t> sub, slot;
+            for (int64_t i = 0; i < M; i++)
+                if (flags[i]) { sub.push_back(var_idx[i]); slot.push_back((int32_t)i); }
+            h->stats.refit_snps = (int64_t)sub.size();
+            if (!sub.empty()) FLX_TRY(run_batches(h, sub.data(), (int64_t)sub.size(), out != nullptr, do_perm, nullptr, nullptr, false, true, slot.data(), M));
+        }
+        if (do_perm) {
+            FLX_TRY(launch_minp_finalize(h->maxratio.p, h->P_pad, h->P, h->s, h->lrs0p.p, (double)h->n, h->df_count.p, h->minp_d.p, h->stream));
+            h->stats.launches++;
+        }
+    }
     // ---- results D2H
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);

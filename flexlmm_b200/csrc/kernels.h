@@ -27,6 +27,23 @@ struct GemmArgs {
 int launch_whiten(const GemmArgs& g, int num_sms, cudaStream_t st);
 int launch_perm_contract(const GemmArgs& g, int s, int num_sms, cudaStream_t st);
 
+// ---------------------------------------------------------------- K2q (qf.cu): x' V^-1 x on the int8 tensor cores
+struct QfArgs {
+    const int8_t* X8;         // [NJ][NKB][8 KB]  int8 genotype tiles (128 SNPs x 64 samples per block, UMMA canonical K-major)
+    const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(V^-1) (half diagonal)
+    const double* rowscale;   // [n_pad256] power-of-two scale of each row of T
+    double group_scale[4];    // 2^-16(qg+1)
+    double* part;             // [T256][QG][nsnp] partial quadratic forms
+    int64_t n_items;
+    int64_t nsnp;
+    int T256, NJ, QG, Q;
+    int NKB;                  // k-blocks per X8 tile (n_pad256 / 64)
+    int NKB_live;             // k-blocks that hold real samples
+};
+int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
+int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, double* rowscale, int8_t* T8, cudaStream_t st);
+int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st);
+
 // ---------------------------------------------------------------- K1 (decode.cu)
 struct DecodeArgs {
     const uint8_t* packed;    // device: 2-bit records of the batch's variants, record v at packed + v*bpv
@@ -48,6 +65,7 @@ struct DecodeArgs {
     uint8_t* codes_out;       // optional (tests): nsnp x n gathered codes
 };
 int launch_decode(const DecodeArgs& a, cudaStream_t st);
+int launch_decode_i8(const DecodeArgs& a, int8_t* X8, int NJ, int NKB, cudaStream_t st);
 
 // ---------------------------------------------------------------- K3 (snp_fit.cu)
 struct FitConst {
@@ -77,6 +95,7 @@ struct GramArgs {
 };
 int gram_padded_width(int cr);
 int launch_snp_gram(const GramArgs& a, cudaStream_t st);
+int launch_snp_gram_sweep1(const GramArgs& a, cudaStream_t st);   // only u = Qc' w and ||w||^2 (fast mode: against H = L^-T [Qc | r])
 
 struct SolveArgs {
     const double* n_part; const double* u_part; const double* a_part; const double* b_part;
@@ -88,6 +107,11 @@ struct SolveArgs {
     // batch-local outputs for K4
     int32_t* snp_df; double* snp_sm;
     int* df_count;            // [9] run-wide count of SNPs per lrt_df (1..8)
+    const int32_t* out_map;   // optional: run-wide output slot of batch SNP q (refit pass), else out_offset + q
+    // fast (int8 quadratic form) mode, s == 1: A_raw = 2 * sum of qf_nparts partials; u, b from the H sweep (u_part)
+    int fast;
+    const double* qf_part; int qf_nparts;
+    int32_t* refit_flag;      // [nsnp] set to 1 when the SNP must be re-fitted on the FP64 path (near-collinear with the constant columns)
 };
 int upload_fit_const(const FitConst& c);
 int launch_snp_solve(const SolveArgs& a, cudaStream_t st);

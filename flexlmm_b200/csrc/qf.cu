@@ -1,0 +1,314 @@
+// qf.cu — K2q: the whitened quadratic form x' V^-1 x on the int8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators).
+//
+// For a design whose SNP-dependent column is the hard call itself (x in {0,1,2}; additive models, BASELINE configs C2/C4/C5)
+// the only O(n^2)-per-SNP quantity of the fit is  ||L^-1 x||^2 = x' V^-1 x = 2 x' T x,  T = strict lower triangle of V^-1
+// plus half its diagonal (everything else — Qc' L^-1 x, r' L^-1 x, R_f' L^-1 x — is x against n x (c+1+P) matrices that
+// are whitened once).  x is an exact small integer, so T is split ONCE into Q = 6 balanced base-256 digit planes
+// ("Ozaki slices", 48 bits below each row's power-of-two scale): every int8 x int8 product and every s32 accumulation is
+// exact, and the result differs from the FP64 value only by the 2^-48 truncation of T — measured 4e-15 relative in
+// x' V^-1 x at n = 2000, better than the rounding a length-n FP64 dot product accumulates.  Throughput of the i8 pipe
+// (4.5 POP/s nominal, 4.17 POP/s measured by tools/qf_probe.cu) over 6 slices is ~19x the FP64 DMMA pipe.
+//
+// Kernel: persistent, warp-specialised, one CTA per SM.
+//   warp 0  : TMA producer — 1-D bulk copies of pre-packed operand blocks (UMMA canonical K-major, no swizzle: 8 x 16 B
+//             core matrices) into a 5-stage x 40 KB ring.
+//   warp 1  : allocates 512 TMEM columns; one lane issues tcgen05.mma.cta_group::1.kind::i8, M = 128 SNPs (A = X8 tile),
+//             N = 256 rows of T (B = two digit planes per work item), K = 32 per instruction; tcgen05.commit frees stages.
+//   warps 2-5: epilogue — tcgen05.ld the two 128 x 256 s32 accumulators, combine the planes exactly in int64, multiply by
+//             the SNP's own genotype at that row, scale by the row's power of two and sum over the 256 rows IN THE THREAD
+//             (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane pair, SNP).
+// Work item = (row tile I of 256 rows, SNP tile J of 128, plane pair qg); k runs over the lower-triangular range.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace flx {
+
+constexpr int QF_KB = 64;                     // k bytes per stage
+constexpr int QF_A_BYTES = 128 * QF_KB;       // 8 KB  (X8 tile block)
+constexpr int QF_B_BYTES = 256 * QF_KB;       // 16 KB (one digit plane block)
+constexpr int QF_QC = 2;                      // planes per work item (2 x 256 TMEM columns)
+constexpr int QF_STAGE_BYTES = QF_A_BYTES + QF_QC * QF_B_BYTES;
+constexpr int QF_STAGES = 5;
+constexpr int QF_SMEM = QF_STAGES * QF_STAGE_BYTES + 256;
+constexpr int QF_THREADS = 192;
+
+__device__ __forceinline__ uint32_t qsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void qbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qsmem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void qbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qsmem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void qbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qsmem_u32(bar)) : "memory"); }
+__device__ __forceinline__ bool qbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(qsmem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void qbar_wait(uint64_t* bar, uint32_t parity) { while (!qbar_try_wait(bar, parity)) {} }
+__device__ __forceinline__ void qtma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(qsmem_u32(dst)), "l"(src), "r"(bytes), "r"(qsmem_u32(bar)) : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 descriptor version 1):
+// canonical layout ((8, n), 2) : ((16 B, SBO), LBO) — 8-row x 16-byte core matrices.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(qsmem_u32(bar)) : "memory");
+}
+// instruction descriptor: D = S32 (2 @bit4), A = INT8 (1 @7), B = INT8 (1 @10), both K-major, N>>3 @17, M>>4 @24
+constexpr uint32_t QF_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+#define QF_TMEM_LD32(v, taddr)                                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), \
+                   "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])         \
+                 : "r"(taddr))
+
+__global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + QF_STAGES;
+    uint64_t* acc_full = empty_bar + QF_STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < QF_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 1); }
+        qbar_init(acc_full, 1);
+        qbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qsmem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int per_I = g.NJ * g.QG;
+    if (warp == 0) {
+        // ---------------- TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                const int I = g.T256 - 1 - (int)(item / per_I);
+                const int rem = (int)(item % per_I);
+                const int qg = rem / g.NJ, J = rem % g.NJ;
+                int nkb = 4 * (I + 1);
+                if (nkb > g.NKB_live) nkb = g.NKB_live;
+                const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
+                const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + QF_QC * qg) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
+                for (int kb = 0; kb < nkb; kb++) {
+                    qbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
+                    qbar_expect_tx(&full_bar[stage], QF_STAGE_BYTES);
+                    qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
+                    qtma_bulk_g2s(dst + QF_A_BYTES, b_src + (int64_t)kb * g.Q * QF_B_BYTES, QF_QC * QF_B_BYTES, &full_bar[stage]);
+                    if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, aphase = 0;
+            for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                const int I = g.T256 - 1 - (int)(item / per_I);
+                int nkb = 4 * (I + 1);
+                if (nkb > g.NKB_live) nkb = g.NKB_live;
+                qbar_wait(acc_empty, aphase ^ 1);           // epilogue has drained the accumulators of the previous item
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                for (int kb = 0; kb < nkb; kb++) {
+                    qbar_wait(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t sa = qsmem_u32(smem + (size_t)stage * QF_STAGE_BYTES);
+#pragma unroll
+                    for (int q = 0; q < QF_QC; q++) {
+                        const uint32_t sb = sa + QF_A_BYTES + q * QF_B_BYTES;
+#pragma unroll
+                        for (int j = 0; j < QF_KB / 32; j++) {
+                            // A block: [k16 chunk 4][row group 16][8 rows][16 B]  -> LBO 2048 B, SBO 128 B
+                            // B block: [k16 chunk 4][row group 32][8 rows][16 B]  -> LBO 4096 B, SBO 128 B
+                            const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
+                            const uint64_t bd = umma_desc(sb + j * 8192, 4096, 128);
+                            umma_i8(tmem_base + q * 256, ad, bd, QF_IDESC, (kb > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(acc_full);
+                aphase ^= 1;
+            }
+        }
+    } else {
+        // ---------------- epilogue: thread = TMEM lane = SNP of the tile
+        const int quad = warp & 3;
+        const int snp_l = quad * 32 + lane;
+        uint32_t aphase = 0;
+        for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+            const int I = g.T256 - 1 - (int)(item / per_I);
+            const int rem = (int)(item % per_I);
+            const int qg = rem / g.NJ, J = rem % g.NJ;
+            qbar_wait(acc_full, aphase);
+            aphase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            // this SNP's own genotypes at the 256 rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
+            const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
+            const double* rs = g.rowscale + 256 * (int64_t)I;
+            double sum = 0.0;
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t hi[32], lo[32];
+                QF_TMEM_LD32(hi, trow + c0);
+                QF_TMEM_LD32(lo, trow + 256 + c0);
+                // 32 rows = two 16-byte k chunks of the X8 block
+                const int kbl = c0 >> 6, ch = (c0 & 63) >> 4;
+                const uint4 xv0 = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)kbl * QF_A_BYTES + (ch * 16) * 128));
+                const uint4 xv1 = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)kbl * QF_A_BYTES + ((ch + 1) * 16) * 128));
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                const uint32_t xw[8] = {xv0.x, xv0.y, xv0.z, xv0.w, xv1.x, xv1.y, xv1.z, xv1.w};
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int x = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xff);
+                    const long long comb = (long long)(int)hi[j] * 256 + (long long)(int)lo[j];
+                    sum = fma((double)(comb * x), rs[c0 + j], sum);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) qbar_arrive(acc_empty);
+            const int64_t snp = (int64_t)J * 128 + snp_l;
+            if (snp < g.nsnp) g.part[((int64_t)I * g.QG + qg) * g.nsnp + snp] = sum * g.group_scale[qg];
+        }
+    }
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(qf): %s", cudaGetErrorString(e)); return -3; }
+        configured = true;
+    }
+    const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
+    if (grid <= 0) return 0;
+    qf_i8_kernel<<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("qf launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1q: packed 2-bit hard calls -> int8 tile in the UMMA canonical K-major layout (A operand of K2q)
+//   X8[J][kb][k16 chunk 4][SNP group 16][8 SNPs][16 samples]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) decode_i8_tile_kernel(const DecodeArgs a, int8_t* __restrict__ X8, int NKB) {
+    const int J = blockIdx.x, kb = blockIdx.y;
+    const int r = threadIdx.x & 127, ch = threadIdx.x >> 7;
+    const int64_t snp = (int64_t)J * 128 + r;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (snp < a.nsnp) {
+        const uint8_t* rec = a.packed + (a.vmap ? (int64_t)a.vmap[snp] : snp) * a.bpv;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const int64_t k = (int64_t)kb * QF_KB + ch * 16 + b;
+            if (k < a.n) {
+                const int64_t ro = a.order ? (int64_t)a.order[k] : k;
+                const int code = (__ldg(rec + (ro >> 2)) >> (2 * (int)(ro & 3))) & 3;
+                if (code == 3) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
+                else w[b >> 2] |= (uint32_t)((int)a.uni[0][code] & 0xff) << (8 * (b & 3));
+            }
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(X8 + ((int64_t)J * NKB + kb) * QF_A_BYTES + ((ch * 16 + (r >> 3)) * 8 + (r & 7)) * 16);
+    *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int launch_decode_i8(const DecodeArgs& a, int8_t* X8, int NJ, int NKB, cudaStream_t st) {
+    if (NJ <= 0) return 0;
+    decode_i8_tile_kernel<<<dim3((unsigned)NJ, (unsigned)NKB), 512, 0, st>>>(a, X8, NKB);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("decode_i8 launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup: T = tril(V^-1) with half diagonal  ->  per-row power-of-two scale + Q balanced base-256 digit planes,
+//        packed as the B operand:  T8[row tile I][kb < 4(I+1)][plane q][k16 chunk 4][row group 32][8 rows][16 B]
+// ------------------------------------------------------------------------------------------------
+__global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int64_t ld, int64_t n_pad, double* __restrict__ rowscale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    double m = 0.0;
+    if (i < n) {
+        for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(V[i + j * ld]));
+        m = fmax(m, 0.5 * fabs(V[i + i * ld]));
+    }
+    // scale = 2^(e+1) with max < 2^e  =>  |T / scale| < 0.5
+    int e = 0;
+    if (m > 0.0) { frexp(m, &e); }            // m = f * 2^e, f in [0.5, 1)  =>  m < 2^e
+    rowscale[i] = (m > 0.0) ? ldexp(1.0, e + 1) : 1.0;
+}
+
+__global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __restrict__ V, int64_t n, int64_t ld, const double* __restrict__ rowscale, int Q,
+                                                           int8_t* __restrict__ T8) {
+    const int I = blockIdx.y, kb = blockIdx.x;
+    if (kb >= 4 * (I + 1)) return;
+    const int rl = threadIdx.x;                         // row within the 256-row tile
+    const int64_t i = (int64_t)I * 256 + rl;
+    const double inv = (i < n) ? 1.0 / rowscale[i] : 0.0;
+    const double up = ldexp(1.0, 8 * Q);
+    int8_t* blk = T8 + ((int64_t)2 * I * (I + 1) + kb) * Q * QF_B_BYTES;
+    for (int ch = 0; ch < 4; ch++) {
+        uint32_t w[7][4];
+        for (int q = 0; q < Q; q++) w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
+        for (int b = 0; b < 16; b++) {
+            const int64_t j = (int64_t)kb * QF_KB + ch * 16 + b;
+            double t = 0.0;
+            if (i < n && j <= i) t = (j == i) ? 0.5 * V[i + j * ld] : V[i + j * ld];
+            long long ri = __double2ll_rn(t * inv * up);
+            for (int q = Q - 1; q >= 0; q--) {
+                const long long d = ((ri + 128) & 255) - 128;
+                ri = (ri - d) >> 8;
+                w[q][b >> 2] |= (uint32_t)((int)d & 0xff) << (8 * (b & 3));
+            }
+        }
+        for (int q = 0; q < Q; q++) {
+            uint4* dst = reinterpret_cast<uint4*>(blk + (int64_t)q * QF_B_BYTES + ((ch * 32 + (rl >> 3)) * 8 + (rl & 7)) * 16);
+            *dst = make_uint4(w[q][0], w[q][1], w[q][2], w[q][3]);
+        }
+    }
+}
+
+int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, double* rowscale, int8_t* T8, cudaStream_t st) {
+    const int64_t n_pad = (int64_t)T256 * 256;
+    qf_rowscale_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(V, n, ld, n_pad, rowscale);
+    qf_slice_pack_kernel<<<dim3((unsigned)(4 * T256), (unsigned)T256), 256, 0, st>>>(V, n, ld, rowscale, Q, T8);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("qf_slice launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+// zero the strict upper triangle of a dense column-major matrix (caller-supplied L^-1 may carry anything there)
+__global__ void zero_upper_kernel(double* Z, int64_t n, int64_t ld) {
+    const int64_t j = blockIdx.x;
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < j; i += (int64_t)gridDim.y * blockDim.x) Z[i + j * ld] = 0.0;
+}
+int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st) {
+    if (n <= 1) return 0;
+    zero_upper_kernel<<<dim3((unsigned)n, 32), 256, 0, st>>>(Z, n, ld);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("zero_upper launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+}  // namespace flx

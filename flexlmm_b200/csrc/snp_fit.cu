@@ -235,6 +235,28 @@ static int launch_gram_s(const GramArgs& a, cudaStream_t st) {
     return -1;
 }
 
+template <int CRP>
+static int launch_sweep1_c(const GramArgs& a, cudaStream_t st) {
+    using C = GramCfg<1, CRP>;
+    const int64_t NJ = (a.nsnp + 8 * C::GROUPS - 1) / (8 * C::GROUPS);
+    snp_gram1_kernel<1, CRP><<<dim3((unsigned)NJ, (unsigned)a.KS), C::THREADS, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("snp_gram sweep1 launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+int launch_snp_gram_sweep1(const GramArgs& a, cudaStream_t st) {
+    if (a.nsnp <= 0) return 0;
+    if (a.s != 1) { set_error("snp_gram sweep1: s must be 1"); return -1; }
+    switch (a.crp) {
+        case 4: return launch_sweep1_c<4>(a, st);
+        case 8: return launch_sweep1_c<8>(a, st);
+        case 16: return launch_sweep1_c<16>(a, st);
+        case 24: return launch_sweep1_c<24>(a, st);
+    }
+    set_error("snp_gram sweep1: unsupported padded width %d", a.crp);
+    return -1;
+}
+
 int gram_padded_width(int cr) { return cr <= 4 ? 4 : cr <= 8 ? 8 : cr <= 16 ? 16 : 24; }
 
 int launch_snp_gram(const GramArgs& a, cudaStream_t st) {
@@ -303,7 +325,24 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     double A[MAXS][MAXS], Rs[MAXS][MAXS], Mq[MAXS][MAXS];
     double bq[MAXS], qsr[MAXS], nrm2[MAXS];
     bool alive[MAXS];
-    {
+    bool refit = false;
+    if (a.fast) {
+        // s == 1: A_raw = x' V^-1 x = 2 * sum of the int8 partials; u_j = h_j' x (columns 0..cr-1 of H), b = h_r' x (column cr)
+        double araw = 0.0;
+        for (int p = 0; p < a.qf_nparts; p++) araw += a.qf_part[(int64_t)p * a.nsnp + snp];
+        araw *= 2.0;
+        double uu = 0.0, bsum = 0.0;
+        for (int j = 0; j <= cr; j++) {
+            double acc = 0.0;
+            for (int p = 0; p < a.KS; p++) acc += a.u_part[((int64_t)p * a.nsnp + snp) * a.crp + j];
+            if (j < cr) uu += acc * acc; else bsum = acc;
+        }
+        nrm2[0] = araw;
+        A[0][0] = araw - uu;
+        bq[0] = bsum;
+        // the subtraction loses log2(A_raw / A) bits: hand near-collinear SNPs (monomorphic, ...) to the FP64 path
+        refit = !(A[0][0] > 1e-5 * araw);
+    } else {
         // partial sums of the sample splits, fixed order
         int q = 0;
         for (int t = 0; t < s; t++)
@@ -319,6 +358,7 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             bq[t] = ab; nrm2[t] = an;
         }
     }
+    if (a.refit_flag) a.refit_flag[snp] = refit ? 1 : 0;
     // guarded Cholesky A = Rs' Rs in term order; a vanished pivot leaves a zero row (direction dropped)
     for (int l = 0; l < s; l++) {
         double d = A[l][l];
@@ -465,7 +505,7 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     const int df = rank + 1 - c.df_null;
     const double p = (df > 0) ? chisq_upper_tail(chisq, df) : nan("");
 
-    const int64_t o = a.out_offset + snp;
+    const int64_t o = a.out_map ? (int64_t)a.out_map[snp] : a.out_offset + snp;
     a.chisq[o] = chisq;
     a.pval[o] = p;
     a.df[o] = df;
@@ -510,12 +550,12 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             for (int v2 = t; v2 < s; v2++) {
                 double v = 0.0;
                 for (int l = 0; l < s; l++) v += Mq[l][t] * GM[l][v2];
-                a.snp_sm[snp * nsym + q] = (df > 0) ? v : 0.0;
+                a.snp_sm[snp * nsym + q] = (df > 0 && !refit) ? v : 0.0;
                 q++;
             }
-        a.snp_df[snp] = df > 0 ? df : 0;
+        a.snp_df[snp] = (df > 0 && !refit) ? df : 0;
     }
-    if (a.df_count && df > 0 && df <= MAXS) atomicAdd(&a.df_count[df], 1);
+    if (a.df_count && df > 0 && df <= MAXS && !refit) atomicAdd(&a.df_count[df], 1);
 }
 
 int launch_snp_solve(const SolveArgs& a, cudaStream_t st) {

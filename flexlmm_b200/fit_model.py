@@ -30,10 +30,10 @@ def minp_threshold(min_pval, p_thr=0.05):
 class FitModel:
     """One FIT_MODEL task bound to one B200.  Method order mirrors the R script: inputs (:30-66), then run (:120-171)."""
 
-    def __init__(self, device=0, batch_tiles=0, verbose=0):
+    def __init__(self, device=0, batch_tiles=0, verbose=0, int8=True):
         self._lib = _capi.load()
         self._h = C.c_void_p()
-        cfg = FlxConfig(int(device), int(batch_tiles), int(verbose), 0)
+        cfg = FlxConfig(int(device), int(batch_tiles), int(verbose), 0 if int8 else 1)
         check(self._lib.flx_create(C.byref(cfg), C.byref(self._h)))
         self._keep = {}
         self.n = None

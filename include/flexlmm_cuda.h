@@ -32,6 +32,9 @@ extern "C" {
 #define FLX_ERR_STATE            -7   /* call order violated (e.g. run before set_design) */
 #define FLX_ERR_NO_DEVICE        -8   /* no CUDA device: there is NO CPU fallback */
 
+/* flx_config.flags */
+#define FLX_FLAG_NO_INT8   1  /* never use the exact int8 tensor-core path for x' V^-1 x (K2q); always whiten in FP64 (K2) */
+
 #define FLX_MAX_K   24   /* design columns of the real model (k)            */
 #define FLX_MAX_S    8   /* SNP-dependent design columns (s)                */
 
@@ -41,7 +44,7 @@ typedef struct {
     int32_t device;            /* CUDA device ordinal                                                  */
     int32_t batch_tiles;       /* column tiles (128 design columns each) per batch; 0 = auto (SM count)*/
     int32_t verbose;           /* 1: timing lines on stderr                                            */
-    int32_t reserved;
+    int32_t flags;             /* FLX_FLAG_* bits                                                      */
 } flx_config;
 
 /* Per-SNP results in var_idx order, structure-of-arrays (what the R shim hands back as vectors / a k x M
@@ -62,7 +65,7 @@ typedef struct {
 typedef struct {
     double ms_total;           /* whole flx_run* call on the device stream                             */
     double ms_decode;          /* K1  decode_2bit_tile                                                 */
-    double ms_whiten;          /* K2  whiten_tile (L^-1 . X)                                           */
+    double ms_whiten;          /* K2  whiten_tile (L^-1 . X)  or  K2q int8 quadratic form                      */
     double ms_fit;             /* K3  snp_gram + snp_solve                                             */
     double ms_perm;            /* K4  perm_contract_minp                                               */
     double ms_h2d;             /* host->device copies inside the call                                  */
@@ -74,6 +77,8 @@ typedef struct {
     int64_t snps;
     int64_t n_pad;
     int64_t cols_per_tile;     /* design columns actually used per 128-wide tile                       */
+    int64_t int8_path;         /* 1: the batches ran K2q (int8 tensor cores), 0: K2 (FP64 DMMA)        */
+    int64_t refit_snps;        /* SNPs re-fitted on the FP64 path (near-collinear with constant columns)*/
 } flx_stats;
 
 const char* flx_last_error(void);
