@@ -41,6 +41,15 @@ WORKLOADS = {
 }
 
 
+def i8_peak():
+    try:
+        with open(os.path.join(HERE, "profiles", "i8_peak.json")) as f:
+            d = json.load(f)
+        return d["umma_i8_tops"], "measured tcgen05.mma kind::i8 M128 N256 on this pool (tools/qf_probe.cu, profiles/i8_peak.json)"
+    except Exception:
+        return 2 * 1657.4, "2 x MEASURED_PEAKS.json bf16_tflops (int8 tensor rate is twice bf16 on B200)"
+
+
 def fp64_peak():
     try:
         with open(os.path.join(HERE, "profiles", "fp64_peak.json")) as f:
@@ -287,14 +296,25 @@ def main():
     e2e_value = total_tests / e2e_wall
 
     if rank == 0:
-        peak, peak_src = fp64_peak()
         n = w["n"]
-        flops_whiten = float(w["s"]) * n * n * w["M"] * a.steps          # algorithmic: s*n^2 per SNP (triangular solve)
         ms_whiten = acc["ms_whiten"]
-        achieved = flops_whiten / (ms_whiten * 1e-3) / 1e12
+        int8_path = bool(acc.get("int8_path", 0))
+        if int8_path:
+            # K2q: Q = 6 digit planes x n(n+1)/2 int8 MACs per SNP (2 ops per MAC), on the i8 tensor pipe
+            peak, peak_src = i8_peak()
+            work = 6.0 * n * n * w["M"] * a.steps
+            kname = "qf_i8_kernel (K2q: x'V^-1x, tcgen05.mma kind::i8, 6 exact digit planes)"
+            tfile = "qf_traffic.json"
+        else:
+            peak, peak_src = fp64_peak()
+            work = float(w["s"]) * n * n * w["M"] * a.steps          # algorithmic: s*n^2 per SNP (triangular solve)
+            kname = "panel_gemm_kernel<0,1> (K2 whiten_tile, FP64 DMMA)"
+            tfile = "whiten_traffic.json"
+        achieved = work / (ms_whiten * 1e-3) / 1e12
+        fp64_equiv = float(w["s"]) * n * n * w["M"] * a.steps / (ms_whiten * 1e-3) / 1e12
         traffic = None
         try:
-            with open(os.path.join(HERE, "profiles", "whiten_traffic.json")) as f:
+            with open(os.path.join(HERE, "profiles", tfile)) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -304,10 +324,12 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "SNP-tests/s", "h2d_bytes_per_step": e2e_acc["h2d_bytes"] / a.steps,
                         "d2h_bytes_per_step": e2e_acc["d2h_bytes"] / a.steps, "ms_per_step_wall": e2e_wall / a.steps * 1e3},
                 "gpu_launches": int(acc["launches"]),
-                "roofline": {"kernel": "panel_gemm_kernel<0,1> (K2 whiten_tile)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "roofline": {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "launches": int(acc["launches_whiten"]), "avg_launch_ms": ms_whiten / max(1, acc["launches_whiten"]),
-                             "algorithmic_flops_per_launch": flops_whiten / max(1, acc["launches_whiten"])},
+                             "algorithmic_ops_per_launch": work / max(1, acc["launches_whiten"]),
+                             "fp64_equivalent_tflops": fp64_equiv, "fp64_dgemm_peak_tflops": fp64_peak()[0]},
+                "int8_path": int8_path, "refit_snps_per_step": acc.get("refit_snps", 0) / a.steps,
                 "stage_ms_per_step": {kk: acc[kk] / a.steps for kk in ("ms_decode", "ms_whiten", "ms_fit", "ms_perm", "ms_h2d", "ms_d2h")},
                 "wall_ms_per_step": wall_s / a.steps * 1e3, "setup_s_once": t_setup, "clocks": clocks,
                 "min_pval_head": [float(x) for x in res["min_pval"][:3]]}

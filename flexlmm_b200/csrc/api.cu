@@ -132,6 +132,7 @@ struct flx_handle {
     int src = 0;  // 0 none, 1 pgen file, 2 host packed
     PgenFile* pgen = nullptr;
     const uint8_t* packed_host = nullptr;
+    bool host_registered = false;
     int64_t src_variants = 0, bpv = 0, raw_n = 0;
     std::vector<int32_t> order0;
     bool identity_order = true;
@@ -154,6 +155,7 @@ struct flx_handle {
     flx_stats stats{};
 
     ~flx_handle() {
+        if (host_registered && packed_host) cudaHostUnregister(const_cast<uint8_t*>(packed_host));
         if (pgen) delete pgen;
         for (int i = 0; i < 2; i++) {
             if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
@@ -323,8 +325,17 @@ extern "C" int flx_pgen_info(flx_handle* h, int64_t* variant_ct, int64_t* sample
 
 extern "C" int flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n) {
     if (!h || !packed || n_variants < 0 || raw_sample_ct <= 0 || bytes_per_variant < (raw_sample_ct + 3) / 4 || n <= 0) { set_error("flx_set_packed: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (h->host_registered && h->packed_host) { cudaHostUnregister(const_cast<uint8_t*>(h->packed_host)); h->host_registered = false; }
     h->src = 2;
     h->packed_host = packed;
+    // pin the caller's buffer in place so batches go H2D by DMA straight from it (no staging copy); harmless if it fails
+    if (cudaSetDevice(h->cfg.device) == cudaSuccess && n_variants * bytes_per_variant >= (1 << 20)) {
+        if (cudaHostRegister(const_cast<uint8_t*>(packed), (size_t)n_variants * bytes_per_variant, cudaHostRegisterReadOnly) == cudaSuccess ||
+            (cudaGetLastError(), cudaHostRegister(const_cast<uint8_t*>(packed), (size_t)n_variants * bytes_per_variant, cudaHostRegisterDefault) == cudaSuccess))
+            h->host_registered = true;
+        else
+            cudaGetLastError();
+    }
     h->src_variants = n_variants;
     h->raw_n = raw_sample_ct;
     h->bpv = bytes_per_variant;
@@ -663,19 +674,28 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             if (contiguous) packed_dev = h->resident.p + (size_t)(var_idx[s0] - 1) * bpv;
             else { packed_dev = h->resident.p; vmap = h->vmap_d.p + s0; }
         } else {
-            // stage the batch's records in pinned memory (host work overlaps the previous batch's kernels)
-            if (bi >= 2) FLX_CUDA_TRY(cudaEventSynchronize(h->ev_used[buf]));
-            uint8_t* st = h->staging[buf].p;
-            if (h->src == 2) {
-                if (contiguous) memcpy(st, h->packed_host + (size_t)(var_idx[s0] - 1) * bpv, (size_t)nsnp * bpv);
-                else for (int64_t i = 0; i < nsnp; i++) memcpy(st + i * bpv, h->packed_host + (size_t)(var_idx[s0 + i] - 1) * bpv, bpv);
-            } else if (h->src == 1) {
-                for (int64_t i = 0; i < nsnp; i++) {
-                    std::string e = h->pgen->read_packed((uint32_t)(var_idx[s0 + i] - 1), st + i * bpv);
-                    if (!e.empty()) { set_error("pgen variant %d: %s", var_idx[s0 + i], e.c_str()); return FLX_ERR_PGEN; }
-                }
-            } else { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
-            FLX_CUDA_TRY(cudaMemcpyAsync(h->packed_d[buf].p, st, (size_t)nsnp * bpv, cudaMemcpyHostToDevice, h->stream));
+            // H2D on the copy stream so that the transfer of batch b+1 overlaps the kernels of batch b
+            FLX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[buf], 0));   // the decode of batch b-2 has read this buffer
+            const uint8_t* src_ptr;
+            if (h->src == 2 && contiguous && h->host_registered) {
+                src_ptr = h->packed_host + (size_t)(var_idx[s0] - 1) * bpv;          // pinned in place: no staging copy
+            } else {
+                if (bi >= 2) FLX_CUDA_TRY(cudaEventSynchronize(h->ev_h2d[buf]));      // the staging buffer's previous H2D is done
+                uint8_t* st = h->staging[buf].p;
+                if (h->src == 2) {
+                    if (contiguous) memcpy(st, h->packed_host + (size_t)(var_idx[s0] - 1) * bpv, (size_t)nsnp * bpv);
+                    else for (int64_t i = 0; i < nsnp; i++) memcpy(st + i * bpv, h->packed_host + (size_t)(var_idx[s0 + i] - 1) * bpv, bpv);
+                } else if (h->src == 1) {
+                    for (int64_t i = 0; i < nsnp; i++) {
+                        std::string e = h->pgen->read_packed((uint32_t)(var_idx[s0 + i] - 1), st + i * bpv);
+                        if (!e.empty()) { set_error("pgen variant %d: %s", var_idx[s0 + i], e.c_str()); return FLX_ERR_PGEN; }
+                    }
+                } else { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
+                src_ptr = st;
+            }
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->packed_d[buf].p, src_ptr, (size_t)nsnp * bpv, cudaMemcpyHostToDevice, h->copy_stream));
+            FLX_CUDA_TRY(cudaEventRecord(h->ev_h2d[buf], h->copy_stream));
+            FLX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[buf], 0));
             h->stats.h2d_bytes += nsnp * bpv;
             packed_dev = h->packed_d[buf].p;
         }
@@ -689,6 +709,10 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         da.codes_out = codes_out ? codes_d.p : nullptr;
         FLX_TRY(launch_decode(da, h->stream));
         h->stats.launches++;
+        if (use_fast && !decode_only) {
+            FLX_TRY(launch_decode_i8(da, h->X8.p, NJ, h->NKB, h->stream));   // K1q: int8 tile for the i8 tensor pipe
+            h->stats.launches++;
+        }
         if (!use_resident) FLX_CUDA_TRY(cudaEventRecord(h->ev_used[buf], h->stream));
         mark();  // [2] whiten start
         if (decode_only) {
@@ -721,8 +745,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         ga.KS = (h->KC + ga.cps - 1) / ga.cps;
         ga.n_part = h->n_part.p; ga.u_part = h->u_part.p; ga.a_part = h->a_part.p; ga.b_part = h->b_part.p;
         if (use_fast) {
-            // K1q + K2q: int8 tile and the exact quadratic form x' V^-1 x on the i8 tensor pipe
-            FLX_TRY(launch_decode_i8(da, h->X8.p, NJ, h->NKB, h->stream));
+            // K2q: the exact quadratic form x' V^-1 x on the i8 tensor pipe
             QfArgs q{};
             q.X8 = h->X8.p; q.T8 = h->T8.p; q.rowscale = h->rowscale.p; q.part = h->qf_part.p;
             for (int i = 0; i < 4; i++) q.group_scale[i] = std::ldexp(1.0, -16 * (i + 1));
@@ -730,7 +753,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             q.NKB_live = (int)((h->n + 63) / 64);
             q.n_items = (int64_t)h->T256 * NJ * QG;
             FLX_TRY(launch_qf(q, h->num_sms, h->stream));
-            h->stats.launches += 2; h->stats.launches_whiten++;
+            h->stats.launches += 1; h->stats.launches_whiten++;
             mark();  // [3] fit start
             // u = (L^-T Qc)' x, b = (L^-T r)' x : one sweep of the FP64 design tile against H
             ga.W = h->X.p; ga.Qc = h->Hrow.p; ga.r = h->r.p;

@@ -359,3 +359,69 @@ def test_empty_and_single_variant(fx, big):
         fm.run(np.array([0], dtype=np.int32))             # var_idx is 1-based
     with pytest.raises(fx.FlxError):
         fm.run(np.array([6001], dtype=np.int32))
+
+
+# ------------------------------------------------------------------------------------------------ K2q: exact int8 tensor-core path
+def _run(fx, t, int8, M, perm=True):
+    fm = fx.FitModel(int8=int8)
+    fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+    if perm and t["P"]:
+        fm.set_perm(t["y_pred"], t["U1"], t["e_p"], t["seeds"])
+    fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+    r = fm.run(np.arange(1, M + 1, dtype=np.int32))
+    st = fm.stats()
+    fm.close()
+    return r, st
+
+
+@pytest.mark.parametrize("n,M,model", [(700, 300, "additive"), (5000, 2000, "additive"), (1300, 500, "simple")])
+def test_int8_path_equals_fp64_path(fx, n, M, model):
+    """The int8 digit-plane path (K2q) and the FP64 DMMA path (K2) are two arithmetics for the same numbers."""
+    from flexlmm_b200 import synth
+    t = synth.task(n, M, model=model, P=7, seed=n, effect=0.1)
+    r8, st8 = _run(fx, t, True, M)
+    r64, st64 = _run(fx, t, False, M)
+    assert st8["int8_path"] == 1 and st64["int8_path"] == 0
+    assert np.array_equal(r8["lrt_df"], r64["lrt_df"]) and np.array_equal(r8["pivot"], r64["pivot"])
+    np.testing.assert_allclose(r8["lrt_chisq"], r64["lrt_chisq"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r8["coef"], r64["coef"], rtol=1e-9, atol=1e-12)
+    assert_logp_close(r8["pval"], r64["pval"])
+    assert_logp_close(r8["min_pval"], r64["min_pval"])
+
+
+def test_int8_path_refits_collinear_snps_in_fp64(fx, orc):
+    """Monomorphic / nearly-constant SNPs lose digits in x'V^-1x - |u|^2: they must be flagged and re-fitted on the FP64 path."""
+    from flexlmm_b200 import synth
+    n, M = 400, 60
+    t = synth.task(n, M, model="additive", P=3, seed=5)
+    c = t["codes_raw"].copy()
+    c[0] = 0; c[1] = 2; c[2] = 1          # monomorphic: x collinear with the intercept
+    c[3] = 0; c[3, 0] = 1                 # a single carrier: legitimate, tiny variance
+    t["packed"] = synth.pack_2bit(c)
+    r8, st8 = _run(fx, t, True, M)
+    assert st8["int8_path"] == 1 and st8["refit_snps"] >= 3
+    o = oracle_run(orc, t, c)
+    compare(r8, o)
+    want = np.array([oracle_run(orc, t, c, seed=int(s))["min_pval"] for s in t["seeds"]])
+    assert_logp_close(r8["min_pval"], want)
+    assert r8["lrt_df"][0] == 0 and np.isnan(r8["pval"][0])
+
+
+def test_int8_path_for_an_indicator_term(fx, orc):
+    """A single SNP term with integer values other than x itself: y ~ I(x == 1) + cov1."""
+    from flexlmm_b200 import synth
+    n, M = 350, 90
+    t = synth.task(n, M, model="additive", P=2, seed=8)
+    cov = t["M0"][:, 2]
+    one = np.ones(n)
+    t["M0"], t["M1"], t["M2"] = (np.column_stack([one, np.full(n, v), cov]) for v in (0.0, 1.0, 0.0))
+    r8, st8 = _run(fx, t, True, M)
+    assert st8["int8_path"] == 1
+    compare(r8, oracle_run(orc, t, t["codes_raw"]))
+
+
+def test_int8_path_not_used_for_real_valued_terms(fx):
+    from flexlmm_b200 import synth
+    t = synth.task(300, 50, model="domgxe", P=0, seed=1)
+    _, st = _run(fx, t, True, 50, perm=False)
+    assert st["int8_path"] == 0
