@@ -123,8 +123,9 @@ struct flx_handle {
     // int8 quadratic-form path (K2q)
     bool fast = false;
     int Q = 6, T256 = 0, NKB = 0, crpH = 4;
-    DevBuf<int8_t> T8, X8;
-    DevBuf<double> rowscale, Hrow, qf_part;
+    DevBuf<int8_t> T8, X8, GA8, GB8;
+    DevBuf<double> rowscale, qf_part, GA_scale, GB_scale;
+    int NB_A = 16, NB_B = 16, ntilesB = 0;
     DevBuf<int32_t> refit_flag, out_map_d;
     DevBuf<int> df_count, missing;
 
@@ -508,13 +509,12 @@ static int finalize_setup(flx_handle* h) {
         FLX_TRY(Hd.ensure(Hc.size()));
         FLX_CUDA_TRY(cudaMemcpyAsync(Hd.p, Hc.data(), Hc.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, cr + 1, &one, h->Zdense.p, (int)n, Hd.p, (int)n, Hd.p, (int)n));
-        FLX_CUDA_TRY(cudaMemcpyAsync(Hc.data(), Hd.p, Hc.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        // digit planes of H for K4q pass A (u = Qc' w, b = r' w)
+        h->NB_A = ((cr + 1 + 15) / 16) * 16;
+        FLX_TRY(h->GA_scale.ensure(h->NB_A));
+        FLX_TRY(h->GA8.ensure((size_t)h->NKB * h->Q * h->NB_A * 64));
+        FLX_TRY(launch_xg_slice(Hd.p, n, n, cr + 1, h->NB_A, 1, h->Q, h->NKB, h->GA_scale.p, h->GA8.p, h->stream));
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
-        std::vector<double> Hrow((size_t)n_pad * h->crpH + 8, 0.0);
-        for (int j = 0; j <= cr; j++)
-            for (int64_t i = 0; i < n; i++) Hrow[i * h->crpH + j] = Hc[i + (size_t)j * n];
-        FLX_TRY(h->Hrow.ensure(Hrow.size()));
-        FLX_CUDA_TRY(cudaMemcpy(h->Hrow.p, Hrow.data(), Hrow.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
 
     // ---- permutation prologue (fit_model.nf:96-101) for all seeds at once
@@ -556,26 +556,33 @@ static int finalize_setup(flx_handle* h) {
         pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.crp = gram_padded_width(cr); pa.Qn = h->Qn.p; pa.cn = h->cn; pa.cnp = gram_padded_width(h->cn);
         pa.n = n; pa.n_pad = n_pad; pa.P = P; pa.rss_f = rssf_d.p; pa.rss0 = rss0_d.p;
         FLX_TRY(launch_perm_prep(pa, h->stream));
-        if (h->fast) {
-            // the contraction runs against the raw genotypes: R_f -> L^-T R_f  (b* = x' L^-T r*)
-            FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, P, &one, h->Zdense.p, (int)n, UE.p, (int)n_pad, UE.p, (int)n_pad));
-        }
         FLX_TRY(h->Rpk.ensure((size_t)h->NP * h->KC * CHUNK));
         FLX_TRY(launch_pack_cols(UE.p, n, n_pad, h->P_pad, h->KC, h->Rpk.p, h->stream));
+        int64_t inv_len = h->P_pad;
+        if (h->fast) {
+            // int8 path: the contraction runs against the raw genotypes, b* = x' (L^-T r*): digit planes of L^-T R_f
+            FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, P, &one, h->Zdense.p, (int)n, UE.p, (int)n_pad, UE.p, (int)n_pad));
+            h->ntilesB = (P + 79) / 80;
+            h->NB_B = (((P + h->ntilesB - 1) / h->ntilesB + 15) / 16) * 16;
+            inv_len = std::max<int64_t>(inv_len, (int64_t)h->ntilesB * h->NB_B);
+            FLX_TRY(h->GB_scale.ensure((size_t)h->ntilesB * h->NB_B));
+            FLX_TRY(h->GB8.ensure((size_t)h->ntilesB * h->NKB * h->Q * h->NB_B * 64));
+            FLX_TRY(launch_xg_slice(UE.p, n, n_pad, P, h->NB_B, h->ntilesB, h->Q, h->NKB, h->GB_scale.p, h->GB8.p, h->stream));
+        }
         std::vector<double> rssf(P), rss0(P);
         FLX_CUDA_TRY(cudaMemcpyAsync(rssf.data(), rssf_d.p, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         FLX_CUDA_TRY(cudaMemcpyAsync(rss0.data(), rss0_d.p, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
-        std::vector<double> inv(h->P_pad, 0.0), lr(P);
+        std::vector<double> inv(inv_len, 0.0), lr(P);
         for (int p = 0; p < P; p++) {
             inv[p] = 1.0 / rssf[p];
             lr[p] = (double)(logl((long double)rss0[p]) - logl((long double)rssf[p]));
         }
-        FLX_TRY(h->inv_rss.ensure(h->P_pad));
+        FLX_TRY(h->inv_rss.ensure(inv_len));
         FLX_TRY(h->lrs0p.ensure(P));
-        FLX_TRY(h->maxratio.ensure((size_t)h->s * h->P_pad));
+        FLX_TRY(h->maxratio.ensure((size_t)h->s * std::max<int64_t>(h->P_pad, inv_len)));
         FLX_TRY(h->minp_d.ensure(P));
-        FLX_CUDA_TRY(cudaMemcpy(h->inv_rss.p, inv.data(), h->P_pad * sizeof(double), cudaMemcpyHostToDevice));
+        FLX_CUDA_TRY(cudaMemcpy(h->inv_rss.p, inv.data(), inv_len * sizeof(double), cudaMemcpyHostToDevice));
         FLX_CUDA_TRY(cudaMemcpy(h->lrs0p.p, lr.data(), P * sizeof(double), cudaMemcpyHostToDevice));
         std::vector<double>().swap(h->U1_copy);
     }
@@ -601,7 +608,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const int64_t bpv = h->bpv;
     const int nsym = h->s * (h->s + 1) / 2;
     const int cr = h->cr;
-    const int crp = use_fast ? h->crpH : gram_padded_width(cr);
+    const int crp = use_fast ? h->NB_A : gram_padded_width(cr);
     constexpr int KS_MAX = 32;
     const int QG = h->Q / 2;
     const bool decode_only = (X_out_dense != nullptr) || (codes_out != nullptr);
@@ -622,7 +629,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             FLX_TRY(h->refit_flag.ensure(M_total));
         }
         FLX_TRY(h->n_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
-        FLX_TRY(h->u_part.ensure((size_t)KS_MAX * snps_per_batch * h->s * crp));
+        FLX_TRY(h->u_part.ensure((size_t)KS_MAX * snps_per_batch * h->s * std::max(crp, 32)));
         FLX_TRY(h->a_part.ensure((size_t)KS_MAX * snps_per_batch * nsym));
         FLX_TRY(h->b_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
         FLX_TRY(h->snp_sm.ensure((size_t)snps_per_batch * nsym));
@@ -707,12 +714,12 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         da.lut = h->lut.p; memcpy(da.uni, h->uni, sizeof(da.uni)); da.uniform_mask = h->uniform_mask;
         da.n_pad = h->n_pad; da.X = h->X.p; da.NJ = NJ; da.missing_flag = h->missing.p;
         da.codes_out = codes_out ? codes_d.p : nullptr;
-        FLX_TRY(launch_decode(da, h->stream));
-        h->stats.launches++;
         if (use_fast && !decode_only) {
             FLX_TRY(launch_decode_i8(da, h->X8.p, NJ, h->NKB, h->stream));   // K1q: int8 tile for the i8 tensor pipe
-            h->stats.launches++;
+        } else {
+            FLX_TRY(launch_decode(da, h->stream));
         }
+        h->stats.launches++;
         if (!use_resident) FLX_CUDA_TRY(cudaEventRecord(h->ev_used[buf], h->stream));
         mark();  // [2] whiten start
         if (decode_only) {
@@ -755,10 +762,15 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             FLX_TRY(launch_qf(q, h->num_sms, h->stream));
             h->stats.launches += 1; h->stats.launches_whiten++;
             mark();  // [3] fit start
-            // u = (L^-T Qc)' x, b = (L^-T r)' x : one sweep of the FP64 design tile against H
-            ga.W = h->X.p; ga.Qc = h->Hrow.p; ga.r = h->r.p;
-            FLX_TRY(launch_snp_gram_sweep1(ga, h->stream));
+            // K4q pass A: u = (L^-T Qc)' x, b = (L^-T r)' x against the digit planes of H
+            XgArgs xa{};
+            xa.X8 = h->X8.p; xa.G8 = h->GA8.p; xa.colscale = h->GA_scale.p;
+            for (int i = 0; i < 3; i++) xa.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
+            xa.n_items = NJ; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_A; xa.NC = cr + 1; xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = q.NKB_live;
+            xa.out = h->u_part.p; xa.ld_out = h->NB_A;
+            FLX_TRY(launch_xg(xa, 0, h->num_sms, h->stream));
             h->stats.launches += 1;
+            ga.KS = 1;
         } else {
             GemmArgs g{};
             g.A = h->linv.p; g.B = h->X.p; g.Out = h->W.p;
@@ -787,10 +799,19 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         FLX_TRY(launch_snp_solve(sa, h->stream));
         h->stats.launches += 1;
         mark();  // [4] perm start
-        if (do_perm) {
+        if (do_perm && use_fast) {
+            // K4q pass B: b* = x' (L^-T r*) for every seed on the i8 pipe, fused max-ratio epilogue
+            XgArgs xb{};
+            xb.X8 = h->X8.p; xb.G8 = h->GB8.p; xb.colscale = h->GB_scale.p;
+            for (int i = 0; i < 3; i++) xb.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
+            xb.n_items = (int64_t)h->ntilesB * NJ; xb.nsnp = nsnp; xb.NJ = NJ; xb.NB = h->NB_B; xb.NC = h->P; xb.Q = h->Q; xb.NKB = h->NKB;
+            xb.NKB_live = (int)((h->n + 63) / 64);
+            xb.snp_df = h->snp_df.p; xb.snp_sm = h->snp_sm.p; xb.perm_inv_rss = h->inv_rss.p; xb.perm_maxratio = h->maxratio.p;
+            FLX_TRY(launch_xg(xb, 1, h->num_sms, h->stream));
+            h->stats.launches++;
+        } else if (do_perm) {
             GemmArgs gp{};
-            gp.A = use_fast ? h->X.p : h->W.p;   // int8 path: b* = x' (L^-T r*), the contraction runs on the raw design tile
-            gp.B = h->Rpk.p; gp.NJ = NJ; gp.NP = h->NP; gp.KC = h->KC; gp.n_items = (int64_t)NJ * h->NP;
+            gp.A = h->W.p; gp.B = h->Rpk.p; gp.NJ = NJ; gp.NP = h->NP; gp.KC = h->KC; gp.n_items = (int64_t)NJ * h->NP;
             gp.snp_df = h->snp_df.p; gp.snp_sm = h->snp_sm.p; gp.perm_inv_rss = h->inv_rss.p; gp.perm_maxratio = h->maxratio.p; gp.P_pad = h->P_pad;
             FLX_TRY(launch_perm_contract(gp, h->s, h->num_sms, h->stream));
             h->stats.launches++;

@@ -41,6 +41,23 @@ struct QfArgs {
     int NKB_live;             // k-blocks that hold real samples
 };
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
+
+// K4q (qf.cu): X8 against digit planes of a column block of G = L^-T [Qc | r | R_f]
+struct XgArgs {
+    const int8_t* X8;         // [NJ][NKB][8 KB]
+    const int8_t* G8;         // [col block][NKB][Q][NB*64 B]
+    const double* colscale;   // [ntiles*NB] power-of-two column scales
+    double pair_scale[3];     // 2^-16, 2^-32, 2^-48
+    int64_t n_items;          // ntiles * NJ
+    int64_t nsnp;
+    int NJ, NB, NC, Q, NKB, NKB_live;
+    // MODE 0
+    double* out; int64_t ld_out;
+    // MODE 1
+    const int32_t* snp_df; const double* snp_sm; const double* perm_inv_rss; double* perm_maxratio;
+};
+int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st);
+int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, double* colscale, int8_t* G8, cudaStream_t st);
 int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, double* rowscale, int8_t* T8, cudaStream_t st);
 int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 

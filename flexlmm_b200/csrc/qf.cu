@@ -311,4 +311,228 @@ int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st) {
     return 0;
 }
 
+// ================================================================================================
+// K4q: X8 (128 SNPs x n, int8) against a column block of G = L^-T [Qc | r | R_f] split into Q digit planes:
+//      out[snp][col] = x_snp' g_col  exactly (up to the 2^-48 truncation of G below each column's power-of-two scale).
+//   MODE 0: store the values (u = Qc' w and b = r' w for K3b).
+//   MODE 1: permutation epilogue — ratio = val^2 * Sm[snp] / RSS_f[col], running max over SNPs per permutation.
+// Same pipeline as K2q; the Q planes of a column block are accumulated side by side in TMEM (Q * NB <= 512 columns).
+// ================================================================================================
+constexpr int XG_MAX_NB = 80;
+constexpr int XG_STAGES = 5;
+constexpr int XG_STAGE_MAX = QF_A_BYTES + 6 * XG_MAX_NB * QF_KB;     // 8 KB + 30 KB
+constexpr int XG_SMEM = XG_STAGES * XG_STAGE_MAX + 256;
+
+#define XG_TMEM_LD16(v, taddr)                                                                                                  \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
+                 : "r"(taddr))
+
+template <int MODE>
+__global__ void __launch_bounds__(QF_THREADS, 1) xg_i8_kernel(const XgArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XG_STAGES * XG_STAGE_MAX);
+    uint64_t* empty_bar = full_bar + XG_STAGES;
+    uint64_t* acc_full = empty_bar + XG_STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < XG_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 1); }
+        qbar_init(acc_full, 1);
+        qbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qsmem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = *tmem_slot;
+    const int NB = g.NB, Q = g.Q;
+    const uint32_t b_bytes = (uint32_t)Q * NB * QF_KB;          // all planes of one k-block
+    const uint32_t stage_bytes = QF_A_BYTES + b_bytes;
+    const int nkb = g.NKB_live;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                const int ct = (int)(item / g.NJ), J = (int)(item % g.NJ);
+                const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
+                const int8_t* b_src = g.G8 + (int64_t)ct * g.NKB * b_bytes;
+                for (int kb = 0; kb < nkb; kb++) {
+                    qbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* dst = smem + (size_t)stage * XG_STAGE_MAX;
+                    qbar_expect_tx(&full_bar[stage], stage_bytes);
+                    qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
+                    qtma_bulk_g2s(dst + QF_A_BYTES, b_src + (int64_t)kb * b_bytes, b_bytes, &full_bar[stage]);
+                    if (++stage == XG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)NB >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t plane_bytes = (uint32_t)NB * QF_KB;       // [k16 chunk 4][col group NB/8][8][16 B]
+            const uint32_t lbo_b = (uint32_t)(NB / 8) * 128;
+            uint32_t stage = 0, phase = 0, aphase = 0;
+            for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                qbar_wait(acc_empty, aphase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                for (int kb = 0; kb < nkb; kb++) {
+                    qbar_wait(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t sa = qsmem_u32(smem + (size_t)stage * XG_STAGE_MAX);
+                    for (int q = 0; q < Q; q++) {
+                        const uint32_t sb = sa + QF_A_BYTES + q * plane_bytes;
+#pragma unroll
+                        for (int j = 0; j < QF_KB / 32; j++) {
+                            const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
+                            const uint64_t bd = umma_desc(sb + j * 2 * lbo_b, lbo_b, 128);
+                            umma_i8(tmem_base + q * NB, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == XG_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(acc_full);
+                aphase ^= 1;
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int snp_l = quad * 32 + lane;
+        uint32_t aphase = 0;
+        for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+            const int ct = (int)(item / g.NJ), J = (int)(item % g.NJ);
+            const int64_t snp = (int64_t)J * 128 + snp_l;
+            double sm = 0.0;
+            if (MODE == 1 && snp < g.nsnp && g.snp_df[snp] > 0) sm = g.snp_sm[snp];
+            qbar_wait(acc_full, aphase);
+            aphase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 0; c0 < NB; c0 += 16) {
+                uint32_t v[6][16];
+#pragma unroll
+                for (int q = 0; q < 6; q++)
+                    if (q < Q) XG_TMEM_LD16(v[q], trow + q * NB + c0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int col = ct * NB + c0 + j;                 // column of G
+                    // planes pairwise exact in int64, then FP64: sum_q d_q 256^-(q+1)
+                    double val = 0.0;
+#pragma unroll
+                    for (int qq = 2; qq >= 0; qq--) {
+                        if (2 * qq < Q) {
+                            const long long comb = (long long)(int)v[2 * qq][j] * 256 + ((2 * qq + 1 < Q) ? (long long)(int)v[2 * qq + 1][j] : 0);
+                            val += (double)comb * g.pair_scale[qq];
+                        }
+                    }
+                    val *= g.colscale[col];
+                    if (MODE == 0) {
+                        if (snp < g.nsnp && col < g.NC) g.out[snp * g.ld_out + col] = val;
+                    } else {
+                        // ratio of this (SNP, permutation); max over the 32 SNPs of the warp, one atomic per column
+                        double ratio = fmax(val * val * sm * g.perm_inv_rss[col], 0.0);
+                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 16));
+                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 8));
+                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 4));
+                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 2));
+                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 1));
+                        if (lane == 0 && ratio > 0.0)
+                            atomicMax(reinterpret_cast<unsigned long long*>(&g.perm_maxratio[col]), (unsigned long long)__double_as_longlong(ratio));
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) qbar_arrive(acc_empty);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(xg_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, XG_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(xg_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, XG_SMEM);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(xg): %s", cudaGetErrorString(e)); return -3; }
+        configured = true;
+    }
+    if (g.NB % 16 != 0 || g.NB < 16 || g.NB > XG_MAX_NB || g.Q < 1 || g.Q > 6) { set_error("xg: bad column block %d / planes %d", g.NB, g.Q); return -1; }
+    const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
+    if (grid <= 0) return 0;
+    if (mode == 0) xg_i8_kernel<0><<<(unsigned)grid, QF_THREADS, XG_SMEM, st>>>(g);
+    else xg_i8_kernel<1><<<(unsigned)grid, QF_THREADS, XG_SMEM, st>>>(g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("xg launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
+// ---- setup: G (n x NC dense, column-major) -> per-column power-of-two scale + Q digit planes, packed per column block:
+//      G8[col block ct][kb][plane q][k16 chunk 4][col group NB/8][8 cols][16 B]
+__global__ void xg_colscale_kernel(const double* __restrict__ G, int64_t n, int64_t ld, int NC, int NC_pad, double* __restrict__ colscale) {
+    const int col = blockIdx.x;
+    __shared__ double sh[8];
+    double m = 0.0;
+    if (col < NC)
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(G[i + (int64_t)col * ld]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmax(m, sh[w]);
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);
+        colscale[col] = (m > 0.0) ? ldexp(1.0, e + 1) : 1.0;
+    }
+    (void)NC_pad;
+}
+
+__global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __restrict__ G, int64_t n, int64_t ld, int NC, int NB, int Q, int NKB,
+                                                           const double* __restrict__ colscale, int8_t* __restrict__ G8) {
+    const int ct = blockIdx.y, kb = blockIdx.x;
+    const int plane_bytes = NB * QF_KB;
+    int8_t* blk = G8 + ((int64_t)ct * NKB + kb) * Q * plane_bytes;
+    const double up = ldexp(1.0, 8 * Q);
+    // one thread per (column of the block, k16 chunk)
+    for (int e = threadIdx.x; e < NB * 4; e += blockDim.x) {
+        const int cl = e % NB, ch = e / NB;
+        const int col = ct * NB + cl;
+        const double inv = (col < NC) ? 1.0 / colscale[col] : 0.0;
+        uint32_t w[6][4];
+        for (int q = 0; q < 6; q++) w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
+        for (int b = 0; b < 16; b++) {
+            const int64_t k = (int64_t)kb * QF_KB + ch * 16 + b;
+            const double t = (col < NC && k < n) ? G[k + (int64_t)col * ld] : 0.0;
+            long long ri = __double2ll_rn(t * inv * up);
+            for (int q = Q - 1; q >= 0; q--) {
+                const long long d = ((ri + 128) & 255) - 128;
+                ri = (ri - d) >> 8;
+                w[q][b >> 2] |= (uint32_t)((int)d & 0xff) << (8 * (b & 3));
+            }
+        }
+        for (int q = 0; q < Q; q++) {
+            uint4* dst = reinterpret_cast<uint4*>(blk + (int64_t)q * plane_bytes + ((ch * (NB / 8) + (cl >> 3)) * 8 + (cl & 7)) * 16);
+            *dst = make_uint4(w[q][0], w[q][1], w[q][2], w[q][3]);
+        }
+    }
+}
+
+int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, double* colscale, int8_t* G8, cudaStream_t st) {
+    xg_colscale_kernel<<<(unsigned)(NB * ntiles), 256, 0, st>>>(G, n, ld, NC, NB * ntiles, colscale);
+    xg_slice_pack_kernel<<<dim3((unsigned)NKB, (unsigned)ntiles), 256, 0, st>>>(G, n, ld, NC, NB, Q, NKB, colscale, G8);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("xg_slice launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
 }  // namespace flx
