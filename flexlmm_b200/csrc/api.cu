@@ -625,7 +625,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         if (!use_fast) FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
         if (use_fast) {
             FLX_TRY(h->X8.ensure((size_t)tiles_per_batch * h->NKB * 8192));
-            FLX_TRY(h->qf_part.ensure((size_t)h->T256 * QG * snps_per_batch));
+            FLX_TRY(h->qf_part.ensure((size_t)h->T256 * QG * 2 * snps_per_batch));
             FLX_TRY(h->refit_flag.ensure(M_total));
         }
         FLX_TRY(h->n_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
@@ -794,7 +794,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         sa.chisq = h->chisq.p; sa.pval = h->pval.p; sa.df = h->df.p; sa.rank = h->rank.p; sa.pivot = h->pivot.p; sa.coef = h->coef.p;
         sa.snp_df = do_perm ? h->snp_df.p : nullptr; sa.snp_sm = do_perm ? h->snp_sm.p : nullptr;
         sa.df_count = h->df_count.p;
-        sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * QG;
+        sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * QG * 2;
         sa.refit_flag = use_fast ? h->refit_flag.p + s0 : nullptr;
         FLX_TRY(launch_snp_solve(sa, h->stream));
         h->stats.launches += 1;

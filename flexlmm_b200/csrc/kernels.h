@@ -33,7 +33,7 @@ struct QfArgs {
     const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(V^-1) (half diagonal)
     const double* rowscale;   // [n_pad256] power-of-two scale of each row of T
     double group_scale[4];    // 2^-16(qg+1)
-    double* part;             // [T256][QG][nsnp] partial quadratic forms
+    double* part;             // [T256][QG][2 row halves][nsnp] partial quadratic forms
     int64_t n_items;
     int64_t nsnp;
     int T256, NJ, QG, Q;

@@ -30,7 +30,8 @@ constexpr int QF_QC = 2;                      // planes per work item (2 x 256 T
 constexpr int QF_STAGE_BYTES = QF_A_BYTES + QF_QC * QF_B_BYTES;
 constexpr int QF_STAGES = 5;
 constexpr int QF_SMEM = QF_STAGES * QF_STAGE_BYTES + 256;
-constexpr int QF_THREADS = 192;
+constexpr int QF_THREADS = 320;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int XG_THREADS = 192;
 
 __device__ __forceinline__ uint32_t qsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void qbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qsmem_u32(bar)), "r"(count)); }
@@ -66,6 +67,12 @@ constexpr uint32_t QF_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) 
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])         \
                  : "r"(taddr))
 
+#define XG_TMEM_LD16(v, taddr)                                                                                                  \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
+                 : "r"(taddr))
+
 __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < QF_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 1); }
         qbar_init(acc_full, 1);
-        qbar_init(acc_empty, 4);
+        qbar_init(acc_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -147,45 +154,54 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             }
         }
     } else {
-        // ---------------- epilogue: thread = TMEM lane = SNP of the tile
+        // ---------------- epilogue: thread = TMEM lane = SNP of the tile; the two warps of a lane quadrant split the 256 rows
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int snp_l = quad * 32 + lane;
+        const int cbase = half * 128;
         uint32_t aphase = 0;
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             const int I = g.T256 - 1 - (int)(item / per_I);
             const int rem = (int)(item % per_I);
             const int qg = rem / g.NJ, J = rem % g.NJ;
+            // this SNP's own genotypes at the rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
+            const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
+            const double* rs = g.rowscale + 256 * (int64_t)I + cbase;
+            uint4 xq[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int r = cbase + 16 * c;
+                xq[c] = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)(r >> 6) * QF_A_BYTES + (((r & 63) >> 4) * 16) * 128));
+            }
             qbar_wait(acc_full, aphase);
             aphase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            // this SNP's own genotypes at the 256 rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
-            const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
-            const double* rs = g.rowscale + 256 * (int64_t)I;
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + cbase;
             double sum = 0.0;
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t hi[32], lo[32];
-                QF_TMEM_LD32(hi, trow + c0);
-                QF_TMEM_LD32(lo, trow + 256 + c0);
-                // 32 rows = two 16-byte k chunks of the X8 block
-                const int kbl = c0 >> 6, ch = (c0 & 63) >> 4;
-                const uint4 xv0 = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)kbl * QF_A_BYTES + (ch * 16) * 128));
-                const uint4 xv1 = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)kbl * QF_A_BYTES + ((ch + 1) * 16) * 128));
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
-                const uint32_t xw[8] = {xv0.x, xv0.y, xv0.z, xv0.w, xv1.x, xv1.y, xv1.z, xv1.w};
+            uint32_t hi[2][16], lo[2][16];
+            XG_TMEM_LD16(hi[0], trow);
+            XG_TMEM_LD16(lo[0], trow + 256);
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
+            for (int c = 0; c < 8; c++) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                if (c + 1 < 8) {      // next 16 rows in flight while these are reduced
+                    XG_TMEM_LD16(hi[(c + 1) & 1], trow + 16 * (c + 1));
+                    XG_TMEM_LD16(lo[(c + 1) & 1], trow + 256 + 16 * (c + 1));
+                }
+                const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
                     const int x = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xff);
-                    const long long comb = (long long)(int)hi[j] * 256 + (long long)(int)lo[j];
-                    sum = fma((double)(comb * x), rs[c0 + j], sum);
+                    // planes combined exactly: |hi*256 + lo| < 2^40, times x and a power of two: all exact in FP64
+                    const double comb = fma((double)(int)hi[c & 1][j], 256.0, (double)(int)lo[c & 1][j]);
+                    sum = fma(comb * (double)x, rs[16 * c + j], sum);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) qbar_arrive(acc_empty);
             const int64_t snp = (int64_t)J * 128 + snp_l;
-            if (snp < g.nsnp) g.part[((int64_t)I * g.QG + qg) * g.nsnp + snp] = sum * g.group_scale[qg];
+            if (snp < g.nsnp) g.part[(((int64_t)I * g.QG + qg) * 2 + half) * g.nsnp + snp] = sum * g.group_scale[qg];
         }
     }
     __syncthreads();
@@ -211,31 +227,58 @@ int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
 // K1q: packed 2-bit hard calls -> int8 tile in the UMMA canonical K-major layout (A operand of K2q)
 //   X8[J][kb][k16 chunk 4][SNP group 16][8 SNPs][16 samples]
 // ------------------------------------------------------------------------------------------------
+constexpr int DEC8_KBS = 8;   // k-blocks per CTA: 512 samples = 128 packed bytes per record, one cache line
 __global__ void __launch_bounds__(512) decode_i8_tile_kernel(const DecodeArgs a, int8_t* __restrict__ X8, int NKB) {
-    const int J = blockIdx.x, kb = blockIdx.y;
+    __shared__ uint32_t lut[256];      // packed byte (4 codes) -> 4 int8 design values
+    const int J = blockIdx.x, kb0 = blockIdx.y * DEC8_KBS;
     const int r = threadIdx.x & 127, ch = threadIdx.x >> 7;
+    if (threadIdx.x < 256) {
+        uint32_t w = 0;
+        for (int q = 0; q < 4; q++) {
+            const int code = (threadIdx.x >> (2 * q)) & 3;
+            const int v = (code == 3) ? 0 : (int)a.uni[0][code];
+            w |= (uint32_t)(v & 0xff) << (8 * q);
+        }
+        lut[threadIdx.x] = w;
+    }
+    __syncthreads();
     const int64_t snp = (int64_t)J * 128 + r;
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (snp < a.nsnp) {
-        const uint8_t* rec = a.packed + (a.vmap ? (int64_t)a.vmap[snp] : snp) * a.bpv;
+    const bool live = snp < a.nsnp;
+    const uint8_t* rec = a.packed + (live ? (a.vmap ? (int64_t)a.vmap[snp] : snp) : 0) * a.bpv;
+    const int kend = min(kb0 + DEC8_KBS, NKB);
+    for (int kb = kb0; kb < kend; kb++) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        const int64_t k0 = (int64_t)kb * QF_KB + ch * 16;
+        if (live && k0 < a.n) {
+            if (!a.order && k0 + 16 <= a.n) {
+                // identity sample order: 16 samples = 4 packed bytes
 #pragma unroll
-        for (int b = 0; b < 16; b++) {
-            const int64_t k = (int64_t)kb * QF_KB + ch * 16 + b;
-            if (k < a.n) {
-                const int64_t ro = a.order ? (int64_t)a.order[k] : k;
-                const int code = (__ldg(rec + (ro >> 2)) >> (2 * (int)(ro & 3))) & 3;
-                if (code == 3) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
-                else w[b >> 2] |= (uint32_t)((int)a.uni[0][code] & 0xff) << (8 * (b & 3));
+                for (int b4 = 0; b4 < 4; b4++) {
+                    const uint32_t byte = __ldg(rec + (k0 >> 2) + b4);
+                    if (byte & (byte >> 1) & 0x55u) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
+                    w[b4] = lut[byte];
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    const int64_t k = k0 + b;
+                    if (k < a.n) {
+                        const int64_t ro = a.order ? (int64_t)a.order[k] : k;
+                        const int code = (__ldg(rec + (ro >> 2)) >> (2 * (int)(ro & 3))) & 3;
+                        if (code == 3) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
+                        else w[b >> 2] |= (uint32_t)((int)a.uni[0][code] & 0xff) << (8 * (b & 3));
+                    }
+                }
             }
         }
+        uint4* dst = reinterpret_cast<uint4*>(X8 + ((int64_t)J * NKB + kb) * QF_A_BYTES + ((ch * 16 + (r >> 3)) * 8 + (r & 7)) * 16);
+        *dst = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    uint4* dst = reinterpret_cast<uint4*>(X8 + ((int64_t)J * NKB + kb) * QF_A_BYTES + ((ch * 16 + (r >> 3)) * 8 + (r & 7)) * 16);
-    *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 int launch_decode_i8(const DecodeArgs& a, int8_t* X8, int NJ, int NKB, cudaStream_t st) {
     if (NJ <= 0) return 0;
-    decode_i8_tile_kernel<<<dim3((unsigned)NJ, (unsigned)NKB), 512, 0, st>>>(a, X8, NKB);
+    decode_i8_tile_kernel<<<dim3((unsigned)NJ, (unsigned)((NKB + DEC8_KBS - 1) / DEC8_KBS)), 512, 0, st>>>(a, X8, NKB);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decode_i8 launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
@@ -323,14 +366,8 @@ constexpr int XG_STAGES = 5;
 constexpr int XG_STAGE_MAX = QF_A_BYTES + 6 * XG_MAX_NB * QF_KB;     // 8 KB + 30 KB
 constexpr int XG_SMEM = XG_STAGES * XG_STAGE_MAX + 256;
 
-#define XG_TMEM_LD16(v, taddr)                                                                                                  \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
-                 : "r"(taddr))
-
 template <int MODE>
-__global__ void __launch_bounds__(QF_THREADS, 1) xg_i8_kernel(const XgArgs g) {
+__global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XG_STAGES * XG_STAGE_MAX);
     uint64_t* empty_bar = full_bar + XG_STAGES;
@@ -470,8 +507,8 @@ int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st) {
     if (g.NB % 16 != 0 || g.NB < 16 || g.NB > XG_MAX_NB || g.Q < 1 || g.Q > 6) { set_error("xg: bad column block %d / planes %d", g.NB, g.Q); return -1; }
     const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
     if (grid <= 0) return 0;
-    if (mode == 0) xg_i8_kernel<0><<<(unsigned)grid, QF_THREADS, XG_SMEM, st>>>(g);
-    else xg_i8_kernel<1><<<(unsigned)grid, QF_THREADS, XG_SMEM, st>>>(g);
+    if (mode == 0) xg_i8_kernel<0><<<(unsigned)grid, XG_THREADS, XG_SMEM, st>>>(g);
+    else xg_i8_kernel<1><<<(unsigned)grid, XG_THREADS, XG_SMEM, st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("xg launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
