@@ -124,14 +124,20 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         // ---------------- MMA issuer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, aphase = 0;
+            long long t_acc = 0, t_full = 0, t0 = 0;
+            const long long t_begin = g.prof ? clock64() : 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
+                if (g.prof) t0 = clock64();
                 qbar_wait(acc_empty, aphase ^ 1);           // epilogue has drained the accumulators of the previous item
+                if (g.prof) t_acc += clock64() - t0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < nkb; kb++) {
+                    if (g.prof) t0 = clock64();
                     qbar_wait(&full_bar[stage], phase);
+                    if (g.prof) t_full += clock64() - t0;
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t sa = qsmem_u32(smem + (size_t)stage * QF_STAGE_BYTES);
 #pragma unroll
@@ -152,6 +158,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                 umma_commit(acc_full);
                 aphase ^= 1;
             }
+            if (g.prof) { g.prof[3 * blockIdx.x] = clock64() - t_begin; g.prof[3 * blockIdx.x + 1] = t_acc; g.prof[3 * blockIdx.x + 2] = t_full; }
         }
     } else {
         // ---------------- epilogue: thread = TMEM lane = SNP of the tile; the two warps of a lane quadrant split the 256 rows
@@ -192,9 +199,12 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const int x = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xff);
-                    // planes combined exactly: |hi*256 + lo| < 2^40, times x and a power of two: all exact in FP64
-                    const double comb = fma((double)(int)hi[c & 1][j], 256.0, (double)(int)lo[c & 1][j]);
-                    sum = fma(comb * (double)x, rs[16 * c + j], sum);
+                    // planes combined exactly in int64 (|hi*256 + lo| < 2^40, times |x| <= 127), then to FP64 without I2F
+                    // (int->double conversions run at 16/clk/SM and were the epilogue's bottleneck): 2^52 + 2^51 + v has v in
+                    // its mantissa, one DADD removes the bias.
+                    const long long cx = ((long long)(int)hi[c & 1][j] * 256 + (long long)(int)lo[c & 1][j]) * x;
+                    const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
+                    sum = fma(d, rs[16 * c + j], sum);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
