@@ -73,16 +73,20 @@ def solve_lower(L, B):
         return np.linalg.solve(L, B)
 
 
-def null_fit(y_mm, X_mm):
+def null_fit(y_mm, X_mm, with_U1=True):
     """FIT_NULL_MODEL restated with an implicit-complement U1 (last n-c columns of the Householder Q)."""
     n, c = X_mm.shape
-    Q, _ = np.linalg.qr(X_mm, mode="complete")
-    Qc, U1 = Q[:, :c], np.asfortranarray(Q[:, c:])
+    if with_U1:
+        Q, _ = np.linalg.qr(X_mm, mode="complete")
+        Qc, U1 = Q[:, :c], np.asfortranarray(Q[:, c:])
+    else:
+        Qc, _ = np.linalg.qr(X_mm)
+        U1 = None
     fitted = Qc @ (Qc.T @ y_mm)
     e = y_mm - fitted
     rss = float(e @ e)
     ll = 0.5 * (-n * (np.log(2 * np.pi) + 1 - np.log(n) + np.log(rss)))
-    return dict(e_p=U1.T @ e, y_pred=fitted, U1=U1, ll=ll, df=c + 1)
+    return dict(e_p=None if U1 is None else U1.T @ e, y_pred=fitted, U1=U1, ll=ll, df=c + 1)
 
 
 def task(n, M, model="additive", P=0, seed=0, n_raw=None, subset=False, effect=0.0):
@@ -102,7 +106,7 @@ def task(n, M, model="additive", P=0, seed=0, n_raw=None, subset=False, effect=0
         y = y + effect * codes_raw[0, order - 1]
     y_mm = solve_lower(L, y)
     X_mm = solve_lower(L, Xn)
-    nf = null_fit(y_mm, X_mm)
+    nf = null_fit(y_mm, X_mm, with_U1=P > 0)
     return dict(n=n, M=M, model=model, P=P, L=L, y_mm=y_mm, X_null=np.asfortranarray(X_mm), ll_null=nf["ll"], df_null=nf["df"],
                 M0=M0, M1=M1, M2=M2, names=names, codes_raw=codes_raw, packed=pack_2bit(codes_raw), n_raw=n_raw,
                 pgen_order=order, y_pred=nf["y_pred"], U1=nf["U1"], e_p=nf["e_p"], seeds=np.arange(1, P + 1, dtype=np.int32))

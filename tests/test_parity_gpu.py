@@ -425,3 +425,18 @@ def test_int8_path_not_used_for_real_valued_terms(fx):
     t = synth.task(300, 50, model="domgxe", P=0, seed=1)
     _, st = _run(fx, t, True, 50, perm=False)
     assert st["int8_path"] == 0
+
+
+def test_int8_path_at_larger_n(fx, orc):
+    """n = 12,000 (47 row tiles of 256, 188 k-blocks): int8 route vs FP64 route vs the oracle on a handful of SNPs."""
+    from flexlmm_b200 import synth
+    n, M = 12000, 300
+    t = synth.task(n, M, model="additive", P=0, seed=4, effect=0.05)
+    r8, st8 = _run(fx, t, True, M, perm=False)
+    r64, st64 = _run(fx, t, False, M, perm=False)
+    assert st8["int8_path"] == 1 and st64["int8_path"] == 0
+    np.testing.assert_allclose(r8["lrt_chisq"], r64["lrt_chisq"], rtol=1e-9, atol=1e-10)
+    assert_logp_close(r8["pval"], r64["pval"])
+    pick = np.array([0, 150, 299])
+    o = oracle_run(orc, t, t["codes_raw"][pick])
+    compare({k2: r8[k2][pick] for k2 in ("lrt_df", "rank", "pivot", "pval", "lrt_chisq", "coef")}, o)
