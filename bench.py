@@ -184,6 +184,39 @@ def cpu_reference_rate(w, snps_per_core, tasks, cores):
     return tests / max(times), max(times), wall
 
 
+def stage_roofline(w, acc, steps, int8_path):
+    """Every stage against the roofline that bounds it: algorithmic bytes or ops per step / CUDA-event time."""
+    n, M, P, s, c = w["n"], w["M"], w["P"], w["s"], w["c"]
+    n128 = (n + 127) // 128 * 128
+    n256 = (n + 255) // 256 * 256
+    hbm = 6546.2
+    try:
+        with open(os.path.join(HERE, "MEASURED_PEAKS.json")) as f:
+            hbm = json.load(f)["hbm_gbs"]
+    except Exception:
+        pass
+    out = {}
+
+    def put(name, work, unit, ms, peak, bound):
+        if ms <= 0:
+            return
+        ach = work / (ms * 1e-3 / steps) / (1e9 if unit == "GB/s" else 1e12)
+        out[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "ms_per_step": ms / steps}
+
+    raw = (n + 3) // 4
+    if int8_path:
+        put("K1q decode_i8", M * (raw + n256), "GB/s", acc["ms_decode"], hbm, "hbm")
+        put("K2q qf_i8 (x'V^-1x, 6 planes)", 6.0 * n * n * M, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
+        put("K4q-A + K3b (u, b, fit, LRT)", M * (n256 * 2.0), "GB/s", acc["ms_fit"], hbm, "hbm")
+        put("K4q-B perm contraction (6 planes)", 6.0 * 2 * n * P * M, "TFLOP/s", acc["ms_perm"], i8_peak()[0], "tensor(i8)")
+    else:
+        put("K1 decode_2bit_tile", M * (raw + 8.0 * n128 * s), "GB/s", acc["ms_decode"], hbm, "hbm")
+        put("K2 whiten_tile (DMMA)", float(s) * n * n * M, "TFLOP/s", acc["ms_whiten"], fp64_peak()[0], "tensor(f64)")
+        put("K3a snp_gram (2 sweeps) + K3b", M * (2 * 8.0 * n128 * s), "GB/s", acc["ms_fit"], hbm, "hbm")
+        put("K4 perm_contract (DMMA)", 2.0 * n * s * P * M, "TFLOP/s", acc["ms_perm"], fp64_peak()[0], "tensor(f64)")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -193,6 +226,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--route", default="auto", choices=["auto", "fp64"], help="fp64: force the FP64 DMMA route (FLX_FLAG_NO_INT8)")
     ap.add_argument("--cpu-snps", type=int, default=0, help="SNPs per core for the CPU baseline sample (0 = auto)")
     a = ap.parse_args()
     w = WORKLOADS[a.workload]
@@ -203,7 +237,7 @@ def main():
     tests_per_step_rank = w["M"] * (1 + w["P"])
     config = {"workload": f"{a.workload}: {w['desc']}", "n": w["n"], "snps_per_gpu": w["M"], "permutations": w["P"],
               "design": {"k": w["k"], "c": w["c"], "s": w["s"]}, "sharding": "SNP blocks per GPU, NCCL min-allreduce of min-p" if world > 1 else "single GPU",
-              "l2_policy": "inputs (1.25 GB packed genotypes, 107 MB L^-1 panels) and per-batch tiles (2 x 775 MB) exceed the 126 MB L2; no flush needed"}
+              "l2_policy": "no flush needed: each step streams 1.25 GB of packed genotypes and, per batch, 97 MB of int8 tiles + 79 MB of digit planes (FP64 route: 2 x 775 MB tiles + 107 MB L^-1), all above the 126 MB L2"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -237,7 +271,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     inp = make_inputs(w, rank, local_rank)
-    fm = fx.FitModel(device=local_rank)
+    fm = fx.FitModel(device=local_rank, int8=(a.route == "auto"))
     t_setup0 = time.perf_counter()
     fm.set_whitening(inp["L"])
     fm.set_null(inp["X_null"], inp["y_mm"], inp["ll_null"], inp["df_null"])
@@ -331,6 +365,7 @@ def main():
                              "fp64_equivalent_tflops": fp64_equiv, "fp64_dgemm_peak_tflops": fp64_peak()[0]},
                 "int8_path": int8_path, "refit_snps_per_step": acc.get("refit_snps", 0) / a.steps,
                 "stage_ms_per_step": {kk: acc[kk] / a.steps for kk in ("ms_decode", "ms_whiten", "ms_fit", "ms_perm", "ms_h2d", "ms_d2h")},
+                "stage_roofline": stage_roofline(w, acc, a.steps, int8_path),
                 "wall_ms_per_step": wall_s / a.steps * 1e3, "setup_s_once": t_setup, "clocks": clocks,
                 "min_pval_head": [float(x) for x in res["min_pval"][:3]]}
         if not a.no_cpu_baseline and world == 1:
