@@ -588,8 +588,8 @@ static int finalize_setup(flx_handle* h) {
     }
     FLX_TRY(h->df_count.ensure(16));
     FLX_TRY(h->missing.ensure(1));
-    h->Zdense.release();
-    h->have_Z = false;
+    // the dense inverse is only needed again if the null model / design / permutations are re-set: keep it while it is small
+    if ((size_t)n * n * sizeof(double) > ((size_t)4 << 30)) { h->Zdense.release(); h->have_Z = false; }
     h->dirty = false;
     return FLX_OK;
 }
@@ -777,7 +777,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             XgArgs xa{};
             xa.X8 = h->X8.p; xa.G8 = h->GA8.p; xa.colscale = h->GA_scale.p;
             for (int i = 0; i < 3; i++) xa.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-            xa.n_items = NJ; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_A; xa.NC = cr + 1; xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = q.NKB_live;
+            xa.n_items = NJ; xa.NCT = 1; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_A; xa.NC = cr + 1; xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = q.NKB_live;
             xa.out = h->u_part.p; xa.ld_out = h->NB_A;
             FLX_TRY(launch_xg(xa, 0, h->num_sms, h->stream));
             h->stats.launches += 1;
@@ -815,7 +815,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             XgArgs xb{};
             xb.X8 = h->X8.p; xb.G8 = h->GB8.p; xb.colscale = h->GB_scale.p;
             for (int i = 0; i < 3; i++) xb.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-            xb.n_items = (int64_t)h->ntilesB * NJ; xb.nsnp = nsnp; xb.NJ = NJ; xb.NB = h->NB_B; xb.NC = h->P; xb.Q = h->Q; xb.NKB = h->NKB;
+            xb.n_items = (int64_t)h->ntilesB * NJ; xb.NCT = h->ntilesB; xb.nsnp = nsnp; xb.NJ = NJ; xb.NB = h->NB_B; xb.NC = h->P; xb.Q = h->Q; xb.NKB = h->NKB;
             xb.NKB_live = (int)((h->n + 63) / 64);
             xb.snp_df = h->snp_df.p; xb.snp_sm = h->snp_sm.p; xb.perm_inv_rss = h->inv_rss.p; xb.perm_maxratio = h->maxratio.p;
             FLX_TRY(launch_xg(xb, 1, h->num_sms, h->stream));

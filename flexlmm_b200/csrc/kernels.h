@@ -52,6 +52,7 @@ struct XgArgs {
     int64_t n_items;          // ntiles * NJ
     int64_t nsnp;
     int NJ, NB, NC, Q, NKB, NKB_live;
+    int NCT;                  // column blocks (n_items = NJ * NCT)
     // MODE 0
     double* out; int64_t ld_out;
     // MODE 1

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-                const int ct = (int)(item / g.NJ), J = (int)(item % g.NJ);
+                const int J = (int)(item / g.NCT), ct = (int)(item % g.NCT);   // column blocks of one SNP tile back to back: X8 stays L2-hot
                 const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
                 const int8_t* b_src = g.G8 + (int64_t)ct * g.NKB * b_bytes;
                 for (int kb = 0; kb < nkb; kb++) {
@@ -423,9 +423,11 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)NB >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t plane_bytes = (uint32_t)NB * QF_KB;       // [k16 chunk 4][col group NB/8][8][16 B]
-            const uint32_t lbo_b = (uint32_t)(NB / 8) * 128;
+            // The Q planes of the column block sit side by side along N in the B block ([k16 chunk][(Q*NB)/8 groups][8][16 B]) and in
+            // TMEM (plane q at column q*NB), so one instruction covers up to 256 of the Q*NB columns: the A tile is read from
+            // shared memory once per 256 columns instead of once per plane (N = NB <= 80 alone would be smem-read bound).
+            const int n_total = Q * NB;
+            const uint32_t lbo_b = (uint32_t)(n_total / 8) * 128;
             uint32_t stage = 0, phase = 0, aphase = 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 qbar_wait(acc_empty, aphase ^ 1);
@@ -434,13 +436,15 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
                     qbar_wait(&full_bar[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t sa = qsmem_u32(smem + (size_t)stage * XG_STAGE_MAX);
-                    for (int q = 0; q < Q; q++) {
-                        const uint32_t sb = sa + QF_A_BYTES + q * plane_bytes;
+                    const uint32_t sb = sa + QF_A_BYTES;
+                    for (int n0 = 0; n0 < n_total; n0 += 256) {
+                        const uint32_t n_this = (uint32_t)min(256, n_total - n0);
+                        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((n_this >> 3) << 17) | ((128u >> 4) << 24);
 #pragma unroll
                         for (int j = 0; j < QF_KB / 32; j++) {
                             const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
-                            const uint64_t bd = umma_desc(sb + j * 2 * lbo_b, lbo_b, 128);
-                            umma_i8(tmem_base + q * NB, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            const uint64_t bd = umma_desc(sb + j * 2 * lbo_b + (n0 / 8) * 128, lbo_b, 128);
+                            umma_i8(tmem_base + n0, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
         const int snp_l = quad * 32 + lane;
         uint32_t aphase = 0;
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-            const int ct = (int)(item / g.NJ), J = (int)(item % g.NJ);
+            const int J = (int)(item / g.NCT), ct = (int)(item % g.NCT);
             const int64_t snp = (int64_t)J * 128 + snp_l;
             double sm = 0.0;
             if (MODE == 1 && snp < g.nsnp && g.snp_df[snp] > 0) sm = g.snp_sm[snp];
@@ -568,7 +572,8 @@ __global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __rest
             }
         }
         for (int q = 0; q < Q; q++) {
-            uint4* dst = reinterpret_cast<uint4*>(blk + (int64_t)q * plane_bytes + ((ch * (NB / 8) + (cl >> 3)) * 8 + (cl & 7)) * 16);
+            const int nidx = q * NB + cl;       // planes side by side along N
+            uint4* dst = reinterpret_cast<uint4*>(blk + ((ch * (Q * NB / 8) + (nidx >> 3)) * 8 + (nidx & 7)) * 16);
             *dst = make_uint4(w[q][0], w[q][1], w[q][2], w[q][3]);
         }
     }

@@ -440,3 +440,46 @@ def test_int8_path_at_larger_n(fx, orc):
     pick = np.array([0, 150, 299])
     o = oracle_run(orc, t, t["codes_raw"][pick])
     compare({k2: r8[k2][pick] for k2 in ("lrt_df", "rank", "pivot", "pval", "lrt_chisq", "coef")}, o)
+
+
+@pytest.mark.parametrize("int8", [True, False])
+def test_many_covariates(fx, orc, int8):
+    """k = 20 design columns (intercept, x, 18 covariates): wide constant block in K3b, 32-column u/b block in K4q pass A."""
+    from flexlmm_b200 import synth
+    n, M, nc = 600, 150, 18
+    t = synth.task(n, M, model="additive", P=4, seed=21, effect=0.1)
+    rng = np.random.default_rng(3)
+    C = rng.standard_normal((n, nc))
+    C[:, 5] = C[:, 4] * 2.0 - C[:, 3]          # an exactly collinear covariate: rejected by the rank rule in both models
+    one = np.ones(n)
+    t["M0"], t["M1"], t["M2"] = (np.column_stack([one, np.full(n, v), C]) for v in (0.0, 1.0, 2.0))
+    Xn = np.column_stack([one, C])
+    y = orc.forwardsolve(np.eye(n), t["L"] @ t["y_mm"])[:, 0] + C[:, 0] * 0.3
+    t["y_mm"] = orc.forwardsolve(t["L"], y)[:, 0]; t["X_null"] = orc.forwardsolve(t["L"], Xn)
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    t["ll_null"], t["df_null"] = nm["ll"], nm["df"]
+    t["y_pred"], t["U1"], t["e_p"] = nm["y_pred"], nm["U1"], nm["e_p"]
+    r, st = _run(fx, t, int8, M)
+    assert st["int8_path"] == (1 if int8 else 0)
+    o = oracle_run(orc, t, t["codes_raw"])
+    compare(r, o)
+    assert set(r["rank"].tolist()) == {19} and r["pivot"][0].tolist()[-1] == 8     # column 8 = the collinear covariate
+    want = np.array([oracle_run(orc, t, t["codes_raw"], seed=int(s))["min_pval"] for s in t["seeds"]])
+    assert_logp_close(r["min_pval"], want)
+
+
+def test_reset_permutations_between_runs(fx, orc):
+    """flx_set_perm after a run re-derives the setup; results follow the new seeds (and stay on the int8 route for small n)."""
+    from flexlmm_b200 import synth
+    t = synth.task(300, 80, model="additive", P=3, seed=31)
+    fm = make(fx, t)
+    vi = np.arange(1, 81, dtype=np.int32)
+    r1 = fm.run(vi)
+    fm.set_perm(t["y_pred"], t["U1"], t["e_p"], [7, 8])
+    r2 = fm.run(vi)
+    st = fm.stats()
+    fm.close()
+    assert st["int8_path"] == 1 and r2["min_pval"].size == 2
+    want = np.array([oracle_run(orc, t, t["codes_raw"], seed=s)["min_pval"] for s in (7, 8)])
+    assert_logp_close(r2["min_pval"], want)
+    assert np.array_equal(r1["lrt_chisq"], r2["lrt_chisq"])
