@@ -15,7 +15,7 @@ FLX_MAX_S = 8
 ERR_NAMES = {0: "FLX_OK", -1: "FLX_ERR_BAD_ARG", -2: "FLX_ERR_MISSING_GENOTYPE", -3: "FLX_ERR_CUDA", -4: "FLX_ERR_NCCL",
              -5: "FLX_ERR_OOM", -6: "FLX_ERR_PGEN", -7: "FLX_ERR_STATE", -8: "FLX_ERR_NO_DEVICE"}
 
-EXPORTS = ["flx_last_error", "flx_version", "flx_device_count", "flx_create", "flx_destroy", "flx_set_whitening",
+EXPORTS = ["flx_last_error", "flx_version", "flx_device_count", "flx_create", "flx_destroy", "flx_set_whitening", "flx_decorrelate",
            "flx_set_null", "flx_set_design", "flx_set_perm", "flx_open_pgen", "flx_pgen_info", "flx_set_packed", "flx_make_resident",
            "flx_run", "flx_get_stats", "flx_perm_indices", "flx_decode_tile", "flx_whiten", "flx_comm_unique_id",
            "flx_comm_attach", "flx_minp_threshold"]
@@ -71,6 +71,7 @@ def load(build_if_missing=True):
     L.flx_destroy.argtypes = [vp]
     L.flx_destroy.restype = None
     L.flx_set_whitening.argtypes = [vp, vp, i64, i64, C.c_int]
+    L.flx_decorrelate.argtypes = [vp, vp, i64, dbl, dbl, vp, vp, i32, dbl, dbl, vp, vp, vp, C.POINTER(i32)]
     L.flx_set_null.argtypes = [vp, vp, i32, vp, dbl, i32]
     L.flx_set_design.argtypes = [vp, vp, vp, vp, i32]
     L.flx_set_perm.argtypes = [vp, vp, vp, vp, i64, vp, i32]

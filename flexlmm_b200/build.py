@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcublas", "-lnccl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcublas", "-lcusolver", "-lnccl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -2,6 +2,7 @@
 //   K1 decode -> K2 whiten -> K3a gram -> K3b solve -> K4 permutation contraction (+ min-p finalise)
 // over SNP batches of (SM count) column tiles, on one CUDA stream with double-buffered H2D staging.
 #include <cublas_v2.h>
+#include <cusolverDn.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -223,26 +224,22 @@ extern "C" void flx_destroy(flx_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse) {
-    if (!h || !L || n <= 0 || ld < n) { set_error("flx_set_whitening: bad arguments"); return FLX_ERR_BAD_ARG; }
-    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+// L (or L^-1) dense on the device, n x n column-major with leading dimension n: build every whitening operand from it
+static int whitening_from_device(flx_handle* h, double* Ld, int64_t n, int is_inverse) {
     h->n = n;
     h->n_pad = (n + TJ - 1) / TJ * TJ;
     h->KC = (int)(h->n_pad / KCH);
     h->T = (int)(h->n_pad / TJ);
     h->dirty = true;
     // dense L and L^-1 live on the device during setup (n <= ~45000 in this round)
-    DevBuf<double> Ld;
-    FLX_TRY(Ld.ensure((size_t)n * n));
-    FLX_CUDA_TRY(cudaMemcpy2DAsync(Ld.p, n * sizeof(double), L, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
     FLX_TRY(h->Zdense.ensure((size_t)n * n));
     if (!is_inverse) {
         // Z = L^-1 by a triangular solve against the identity (setup only; library call outside the hot loop)
         FLX_TRY(launch_set_identity(h->Zdense.p, n, n, h->stream));
         const double one = 1.0;
-        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)n, &one, Ld.p, (int)n, h->Zdense.p, (int)n));
+        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)n, &one, Ld, (int)n, h->Zdense.p, (int)n));
     } else {
-        FLX_CUDA_TRY(cudaMemcpyAsync(h->Zdense.p, Ld.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        FLX_CUDA_TRY(cudaMemcpyAsync(h->Zdense.p, Ld, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         FLX_TRY(launch_zero_upper(h->Zdense.p, n, n, h->stream));
     }
     h->have_Z = true;
@@ -250,6 +247,103 @@ extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int6
     FLX_TRY(launch_pack_tri(h->Zdense.p, n, n, h->T, h->linv.p, h->stream));
     FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return FLX_OK;
+}
+
+extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse) {
+    if (!h || !L || n <= 0 || ld < n) { set_error("flx_set_whitening: bad arguments"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DevBuf<double> Ld;
+    FLX_TRY(Ld.ensure((size_t)n * n));
+    FLX_CUDA_TRY(cudaMemcpy2DAsync(Ld.p, n * sizeof(double), L, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
+    return whitening_from_device(h, Ld.p, n, is_inverse);
+}
+
+#define FLX_CUSOLVER_TRY(expr)                                                             \
+    do {                                                                                   \
+        cusolverStatus_t _s = (expr);                                                      \
+        if (_s != CUSOLVER_STATUS_SUCCESS) {                                               \
+            set_error("%s:%d: %s failed: cusolver status %d", __FILE__, __LINE__, #expr, (int)_s); \
+            if (cs) cusolverDnDestroy(cs);                                                 \
+            return FLX_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double s2g, double s2e, const double* y, const double* X, int32_t c,
+                               double min_allowed_eig, double eig_replacement, double* L_out, double* y_mm_out, double* X_mm_out, int32_t* clipped_eigs) {
+    if (!h || !K || n <= 0 || c < 0 || (c > 0 && !X)) { set_error("flx_decorrelate: bad arguments"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cusolverDnHandle_t cs = nullptr;
+    FLX_CUSOLVER_TRY(cusolverDnCreate(&cs));
+    FLX_CUSOLVER_TRY(cusolverDnSetStream(cs, h->stream));
+    DevBuf<double> V, work;
+    DevBuf<int> info_d;
+    FLX_TRY(V.ensure((size_t)n * n));
+    FLX_TRY(info_d.ensure(1));
+    auto build_V = [&]() -> int {
+        FLX_CUDA_TRY(cudaMemcpyAsync(V.p, K, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        return launch_scale_add_diag(V.p, n, n, s2g, s2e, h->stream);       // V = s2g*K + s2e*I   (decorrelate.nf:54)
+    };
+    if (int rc = build_V()) { cusolverDnDestroy(cs); return rc; }
+    int lwork = 0, info = 0, nclip = 0;
+    FLX_CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, &lwork));
+    FLX_TRY(work.ensure((size_t)lwork));
+    FLX_CUSOLVER_TRY(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, work.p, lwork, info_d.p));   // L = t(chol(V)) (:57)
+    FLX_CUDA_TRY(cudaMemcpyAsync(&info, info_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (info != 0) {
+        // not positive definite: force it by replacing the non-positive eigenvalues (:58-69)
+        if (int rc = build_V()) { cusolverDnDestroy(cs); return rc; }
+        DevBuf<double> lam, U, T2;
+        FLX_TRY(lam.ensure(n)); FLX_TRY(U.ensure((size_t)n * n)); FLX_TRY(T2.ensure((size_t)n * n));
+        FLX_CUSOLVER_TRY(cusolverDnDsyevd_bufferSize(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, lam.p, &lwork));
+        FLX_TRY(work.ensure((size_t)lwork));
+        FLX_CUSOLVER_TRY(cusolverDnDsyevd(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, lam.p, work.p, lwork, info_d.p));
+        std::vector<double> lh(n);
+        FLX_CUDA_TRY(cudaMemcpyAsync(lh.data(), lam.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        FLX_CUDA_TRY(cudaMemcpyAsync(&info, info_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (info != 0) { set_error("flx_decorrelate: eigen-decomposition failed (info %d)", info); cusolverDnDestroy(cs); return FLX_ERR_CUDA; }
+        for (int64_t i = 0; i < n; i++) {
+            if (!(lh[i] >= min_allowed_eig)) {
+                set_error("flx_decorrelate: eigenvalue %.6g below min_allowed_eig %.6g (decorrelate.nf:65 stopifnot)", lh[i], min_allowed_eig);
+                cusolverDnDestroy(cs);
+                return FLX_ERR_BAD_ARG;
+            }
+            if (lh[i] <= 0.0) { lh[i] = eig_replacement; nclip++; }
+            lh[i] = std::fabs(lh[i]);
+        }
+        FLX_CUDA_TRY(cudaMemcpyAsync(lam.p, lh.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        // V <- U diag(|lambda|) U'
+        FLX_CUDA_TRY(cudaMemcpyAsync(U.p, V.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        FLX_CUBLAS_TRY(cublasDdgmm(h->cublas, CUBLAS_SIDE_RIGHT, (int)n, (int)n, U.p, (int)n, lam.p, 1, T2.p, (int)n));
+        const double one = 1.0, zero = 0.0;
+        FLX_CUBLAS_TRY(cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)n, (int)n, &one, T2.p, (int)n, U.p, (int)n, &zero, V.p, (int)n));
+        FLX_CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, &lwork));
+        FLX_TRY(work.ensure((size_t)lwork));
+        FLX_CUSOLVER_TRY(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, work.p, lwork, info_d.p));
+        FLX_CUDA_TRY(cudaMemcpyAsync(&info, info_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (info != 0) { set_error("flx_decorrelate: V is not positive definite even after eigenvalue replacement (info %d)", info); cusolverDnDestroy(cs); return FLX_ERR_BAD_ARG; }
+    }
+    cusolverDnDestroy(cs);
+    cs = nullptr;
+    if (clipped_eigs) *clipped_eigs = nclip;
+    FLX_TRY(launch_zero_upper(V.p, n, n, h->stream));     // potrf leaves the input above the diagonal
+    // y.mm, X.mm = forwardsolve(L, .)  (:71-72)
+    const int nrhs = c + (y ? 1 : 0);
+    if (nrhs > 0 && (y_mm_out || X_mm_out)) {
+        DevBuf<double> B;
+        FLX_TRY(B.ensure((size_t)n * nrhs));
+        if (y) FLX_CUDA_TRY(cudaMemcpyAsync(B.p, y, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (c > 0) FLX_CUDA_TRY(cudaMemcpyAsync(B.p + (y ? n : 0), X, (size_t)n * c * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const double one = 1.0;
+        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, nrhs, &one, V.p, (int)n, B.p, (int)n));
+        if (y && y_mm_out) FLX_CUDA_TRY(cudaMemcpyAsync(y_mm_out, B.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (c > 0 && X_mm_out) FLX_CUDA_TRY(cudaMemcpyAsync(X_mm_out, B.p + (y ? n : 0), (size_t)n * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (L_out) FLX_CUDA_TRY(cudaMemcpyAsync(L_out, V.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return whitening_from_device(h, V.p, n, 0);
 }
 
 extern "C" int flx_set_null(flx_handle* h, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null) {

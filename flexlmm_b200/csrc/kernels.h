@@ -154,6 +154,8 @@ struct PermPrepArgs {
 int launch_perm_prep(const PermPrepArgs& a, cudaStream_t st);
 // E[j, p] = e_p[idx[p*m + j] - 1]
 int launch_gather_ep(const double* e_p, const int32_t* idx, int64_t m, int P, double* E, cudaStream_t st);
+// V = a*V + b*I in place (decorrelate.nf:54)
+int launch_scale_add_diag(double* V, int64_t n, int64_t ld, double a, double b, cudaStream_t st);
 // fill identity
 int launch_set_identity(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 // finalize min-p: minp[p] = min over df of pchisq_upper(N*(lrs0p[p] - log1p(-maxratio[df][p])), df)

@@ -80,6 +80,22 @@ int launch_set_identity(double* Z, int64_t n, int64_t ld, cudaStream_t st) {
     return 0;
 }
 
+__global__ void scale_add_diag_kernel(double* V, int64_t n, int64_t ld, double a, double b) {
+    const int64_t j = blockIdx.x;
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x) {
+        const double v = a * V[i + j * ld];
+        V[i + j * ld] = (i == j) ? v + b : v;
+    }
+}
+int launch_scale_add_diag(double* V, int64_t n, int64_t ld, double a, double b, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const unsigned gy = (unsigned)((n + 255) / 256 > 64 ? 64 : (n + 255) / 256);
+    scale_add_diag_kernel<<<dim3((unsigned)n, gy), 256, 0, st>>>(V, n, ld, a, b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("scale_add_diag launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
 // ---- E[j, p] = e_p[idx[p*m + j] - 1]   (sample(e.p), fit_model.nf:98)
 __global__ void gather_ep_kernel(const double* __restrict__ e_p, const int32_t* __restrict__ idx, int64_t m, double* __restrict__ E) {
     const int64_t p = blockIdx.x;

@@ -65,6 +65,19 @@ class FitModel:
         self.n = L.shape[0]
         check(self._lib.flx_set_whitening(self._h, ptr(L), self.n, self.n, int(bool(is_inverse))))
 
+    def decorrelate(self, K, s2g, s2e, y, X, min_allowed_eig=-1e-6, eig_replacement=1e-10, want_L=True):
+        """DECORRELATE on the GPU (decorrelate.nf:50-77).  Returns dict(L, y_mm, X_mm, clipped_eigs); the factor becomes this
+        handle's whitening matrix without a host round trip."""
+        K = f64(K, fortran=True); n = K.shape[0]
+        y = f64(y); X = f64(X, fortran=True).reshape(n, -1, order="F")
+        L = np.empty((n, n), order="F") if want_L else None
+        y_mm = np.empty(n); X_mm = np.empty_like(X, order="F")
+        nclip = C.c_int32(0)
+        check(self._lib.flx_decorrelate(self._h, ptr(K), n, float(s2g), float(s2e), ptr(y), ptr(X), X.shape[1], float(min_allowed_eig),
+                                        float(eig_replacement), ptr(L), ptr(y_mm), ptr(X_mm), C.byref(nclip)))
+        self.n = n
+        return dict(L=L, y_mm=y_mm, X_mm=X_mm, clipped_eigs=nclip.value)
+
     def set_null(self, X_null, y_mm, ll_null, df_null):
         """X.mm, y.mm (fit_model.nf:59-60) and ll.null with attr df (fit_model.nf:63)."""
         X = f64(X_null, fortran=True).reshape(self.n, -1, order="F")

@@ -93,6 +93,17 @@ void flx_destroy(flx_handle* h);
  * exactly what forwardsolve(L, X) reads (fit_model.nf:128).  is_inverse != 0: the matrix already is L^-1. */
 int  flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse);
 
+/* DECORRELATE on the GPU (/root/reference/modules/local/r/decorrelate.nf:50-77) — the producer of the hot path's largest input:
+ *   V = s2g*K + s2e*I (:54);  L = t(chol(V)) (:57);  if the Cholesky fails, eigen-decompose V, require every eigenvalue
+ *   >= min_allowed_eig (:65), replace those <= 0 by eig_replacement, V <- U |lambda| U' and factor again (:58-69);
+ *   y.mm / X.mm = forwardsolve(L, .) (:71-72).
+ * K: n x n column-major symmetric GRM;  X: n x c.  Outputs are host arrays and may be NULL (L_out is n x n, lower triangle,
+ * zeros above).  The factor also becomes this handle's whitening matrix, exactly as if flx_set_whitening(L_out) had been
+ * called, without the n^2 round trip through the host.  *clipped_eigs (may be NULL): number of eigenvalues replaced, 0 when
+ * the plain Cholesky succeeded.  Defaults of the reference: min_allowed_eig = -1e-6, eig_replacement = 1e-10 (nextflow.config:54-56). */
+int  flx_decorrelate(flx_handle* h, const double* K, int64_t n, double s2g, double s2e, const double* y, const double* X, int32_t c,
+                     double min_allowed_eig, double eig_replacement, double* L_out, double* y_mm_out, double* X_mm_out, int32_t* clipped_eigs);
+
 /* y.mm, X.mm (null design, whitened) and the null log-likelihood with its df attribute
  * (fit_model.nf:59-60,63; fit_null_model.nf:33-34,72).  df_null = attr(ll, "df") = rank + 1. */
 int  flx_set_null(flx_handle* h, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null);

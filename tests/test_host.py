@@ -151,3 +151,33 @@ def test_shim_and_module_cover_every_abi_step():
                  "tuple val(meta2), path(pgen), path(pvar), path(psam)", "path model", "tuple val(meta3), path(model_frame)", "val use_dosage",
                  "path \"versions.yml\" , emit: versions", "chr\\\\tpos\\\\tid\\\\tref\\\\talt\\\\tlrt_chisq\\\\tlrt_df\\\\tpval\\\\tbeta"):
         assert line in nf, line
+
+
+def test_cat_perm_and_summarise_by_chr(fx, orc, tmp_path):
+    """get_null_p_dist.nf: concatenate per-(seed, chr) outputs, min over chromosomes, type-7 threshold (make_plots.nf:31-32)."""
+    import gzip
+    rng = np.random.default_rng(0)
+    seeds = [1, 2, 3, 4]
+    paths, rows = [], []
+    for chrom in ("14", "15"):
+        mp = rng.random(4) * 0.2
+        p = tmp_path / f"{chrom}.perm.tsv.gz"
+        fx.write_perm_tsv(p, seeds, chrom, mp, 11)
+        paths.append(p)
+        rows += [(s, chrom, float(f"{m:.15g}"), 11) for s, m in zip(seeds, mp)]
+    cat = tmp_path / "all.tsv.gz"
+    fx.cat_perm(paths, cat)
+    got = fx.read_perm_table(cat)
+    assert [(a, b, d) for a, b, _, d in got] == [(a, b, d) for a, b, _, d in rows]
+    table = fx.summarise_by_chr(got, 4)
+    want = orc.summarise_minp(got)
+    assert [(t[0], t[1], t[2]) for t in table] == [(k, want[k][0], want[k][1]) for k in sorted(want)]
+    assert all(t[2] == 22 for t in table)
+    with pytest.raises(ValueError):
+        fx.summarise_by_chr(got, 5)
+    out = tmp_path / "gw.tsv.gz"
+    fx.write_genome_wide_min_p(out, table)
+    assert gzip.open(out, "rt").readline() == '"permutation"\t"min_pval"\t"nvars"\n'
+    th = fx.thresholds(table, n_tests=22, p_thr=0.05)
+    assert th["bonferroni"] == 0.05 / 22
+    assert th["perm_thr"] == pytest.approx(orc.quantile7([t[1] for t in table], 0.05), abs=1e-16)

@@ -483,3 +483,52 @@ def test_reset_permutations_between_runs(fx, orc):
     want = np.array([oracle_run(orc, t, t["codes_raw"], seed=s)["min_pval"] for s in (7, 8)])
     assert_logp_close(r2["min_pval"], want)
     assert np.array_equal(r1["lrt_chisq"], r2["lrt_chisq"])
+
+
+# ------------------------------------------------------------------------------------------------ DECORRELATE on the GPU (§8f rank 1)
+def test_decorrelate_matches_reference_steps(fx, orc):
+    """decorrelate.nf:50-77: V = s2g K + s2e I, L = t(chol(V)), forwardsolve of y and X; then the hot path runs on that factor."""
+    from flexlmm_b200 import synth
+    n, M = 500, 60
+    rng = np.random.default_rng(2)
+    Z = rng.standard_normal((n, 700)); K = Z @ Z.T / 700
+    t = synth.task(n, M, model="additive", P=2, seed=6)
+    y = rng.standard_normal(n); Xn = np.column_stack([np.ones(n), t["M0"][:, 2]])
+    want = orc.decorrelate(K, 0.6, 0.4, y, Xn)
+    with fx.FitModel() as fm:
+        got = fm.decorrelate(K, 0.6, 0.4, y, Xn)
+        assert got["clipped_eigs"] == 0
+        np.testing.assert_allclose(got["L"], want["L"], rtol=1e-11, atol=1e-13)
+        assert np.all(np.triu(got["L"], 1) == 0)
+        np.testing.assert_allclose(got["y_mm"], want["y_mm"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(got["X_mm"], want["X_mm"], rtol=1e-10, atol=1e-12)
+        # the handle is ready: same results as feeding L back through flx_set_whitening
+        nm = orc.fit_null_model(want["y_mm"], want["X_mm"])
+        fm.set_null(got["X_mm"], got["y_mm"], nm["ll"], nm["df"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r = fm.run(np.arange(1, M + 1, dtype=np.int32))
+    o = orc.fit_model(want["L"], want["y_mm"], want["X_mm"], nm["ll"], nm["df"], t["M0"], t["M1"], t["M2"], t["codes_raw"])
+    compare(r, o)
+
+
+def test_decorrelate_eigenvalue_clipping_fallback(fx):
+    """decorrelate.nf:58-69: a GRM with slightly negative eigenvalues is forced positive definite; too negative is an error."""
+    n = 120
+    rng = np.random.default_rng(5)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.abs(rng.standard_normal(n)) + 0.1
+    lam[:3] = [-2e-7, -5e-8, 0.0]
+    K = (Q * lam) @ Q.T
+    K = 0.5 * (K + K.T)
+    y = rng.standard_normal(n); X = np.ones((n, 1))
+    with fx.FitModel() as fm:
+        got = fm.decorrelate(K, 1.0, 0.0, y, X)                 # V = K: not positive definite
+        assert got["clipped_eigs"] == 3
+        w, U = np.linalg.eigh(K)
+        w2 = np.where(w <= 0, 1e-10, w)
+        V2 = (U * np.abs(w2)) @ U.T
+        np.testing.assert_allclose(got["L"] @ got["L"].T, V2, rtol=1e-7, atol=1e-12)
+        K_bad = K - 1e-3 * np.outer(Q[:, 0], Q[:, 0])
+        with pytest.raises(fx.FlxError) as e:
+            fm.decorrelate(K_bad, 1.0, 0.0, y, X)
+        assert "min_allowed_eig" in str(e.value)
