@@ -16,7 +16,7 @@ ERR_NAMES = {0: "FLX_OK", -1: "FLX_ERR_BAD_ARG", -2: "FLX_ERR_MISSING_GENOTYPE",
              -5: "FLX_ERR_OOM", -6: "FLX_ERR_PGEN", -7: "FLX_ERR_STATE", -8: "FLX_ERR_NO_DEVICE"}
 
 EXPORTS = ["flx_last_error", "flx_version", "flx_device_count", "flx_create", "flx_destroy", "flx_set_whitening", "flx_decorrelate",
-           "flx_set_null", "flx_set_design", "flx_set_perm", "flx_open_pgen", "flx_pgen_info", "flx_set_packed", "flx_make_resident",
+           "flx_set_null", "flx_set_design", "flx_set_perm", "flx_set_perm_implicit", "flx_fit_null_model", "flx_open_pgen", "flx_pgen_info", "flx_set_packed", "flx_make_resident",
            "flx_run", "flx_get_stats", "flx_perm_indices", "flx_decode_tile", "flx_whiten", "flx_comm_unique_id",
            "flx_comm_attach", "flx_minp_threshold"]
 
@@ -75,6 +75,8 @@ def load(build_if_missing=True):
     L.flx_set_null.argtypes = [vp, vp, i32, vp, dbl, i32]
     L.flx_set_design.argtypes = [vp, vp, vp, vp, i32]
     L.flx_set_perm.argtypes = [vp, vp, vp, vp, i64, vp, i32]
+    L.flx_set_perm_implicit.argtypes = [vp, vp, i32]
+    L.flx_fit_null_model.argtypes = [vp, i32, vp, i64, C.POINTER(dbl), C.POINTER(i32), vp, vp, vp, vp, C.POINTER(i64)]
     L.flx_open_pgen.argtypes = [vp, C.c_char_p, vp, i64]
     L.flx_pgen_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.flx_set_packed.argtypes = [vp, vp, i64, i64, i64, vp, i64]

@@ -104,6 +104,8 @@ struct flx_handle {
     std::vector<double> M0, M1, M2;
     // permutations (raw inputs kept until finalisation)
     bool have_perm = false;
+    bool perm_implicit = false;   // U1 is the implicit Householder complement of the null design
+    NullFit nullfit;
     std::vector<double> y_pred, e_p;
     const double* U1_host = nullptr;  // caller-owned until finalise
     std::vector<double> U1_copy;
@@ -376,7 +378,43 @@ extern "C" int flx_set_perm(flx_handle* h, const double* y_pred, const double* U
     h->U1_copy.assign(U1, U1 + (size_t)h->n * m);  // R owns U1 only for the duration of the call
     h->m = m;
     h->seeds.assign(seeds, seeds + P);
-    h->P = P; h->have_perm = true; h->dirty = true;
+    h->P = P; h->have_perm = true; h->perm_implicit = false; h->dirty = true;
+    return FLX_OK;
+}
+
+extern "C" int flx_set_perm_implicit(flx_handle* h, const int32_t* seeds, int32_t P) {
+    if (!h || P < 0 || (P > 0 && !seeds)) { set_error("flx_set_perm_implicit: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (P == 0) { h->have_perm = false; h->P = 0; h->dirty = true; return FLX_OK; }
+    if (!h->have_null) { set_error("flx_set_perm_implicit: call flx_set_null first"); return FLX_ERR_STATE; }
+    null_fit_householder(h->X_null.data(), h->n, h->c_null, h->y_mm.data(), h->nullfit);
+    h->y_pred = h->nullfit.fitted;
+    h->e_p = h->nullfit.e_p;
+    h->m = (int64_t)h->e_p.size();
+    h->U1_copy.clear();
+    h->seeds.assign(seeds, seeds + P);
+    h->P = P; h->have_perm = true; h->perm_implicit = true; h->dirty = true;
+    return FLX_OK;
+}
+
+extern "C" int flx_fit_null_model(const double* X_mm, int32_t c, const double* y_mm, int64_t n, double* ll, int32_t* df,
+                                  double* y_pred, double* resid, double* e_p, double* U1, int64_t* m) {
+    if (!y_mm || n <= 0 || c < 0 || (c > 0 && !X_mm)) { set_error("flx_fit_null_model: bad arguments"); return FLX_ERR_BAD_ARG; }
+    NullFit nf;
+    null_fit_householder(X_mm, n, c, y_mm, nf);
+    const int64_t mm = n - nf.rank;
+    if (ll) *ll = nf.ll;
+    if (df) *df = nf.rank + 1;
+    if (m) *m = mm;
+    if (y_pred) memcpy(y_pred, nf.fitted.data(), n * sizeof(double));
+    if (resid) memcpy(resid, nf.resid.data(), n * sizeof(double));
+    if (e_p) memcpy(e_p, nf.e_p.data(), mm * sizeof(double));
+    if (U1)
+        for (int64_t j = 0; j < mm; j++) {
+            double* col = U1 + j * n;
+            for (int64_t i = 0; i < n; i++) col[i] = 0.0;
+            col[nf.rank + j] = 1.0;
+            nf.apply_Q(col);
+        }
     return FLX_OK;
 }
 
@@ -632,20 +670,32 @@ static int finalize_setup(flx_handle* h) {
         FLX_TRY(idx_d.ensure(idx.size()));
         FLX_TRY(ep_d.ensure(m));
         FLX_TRY(E.ensure((size_t)m * P));
-        FLX_TRY(U1d.ensure((size_t)n * m));
+        if (!h->perm_implicit) FLX_TRY(U1d.ensure((size_t)n * m));
         FLX_TRY(UE.ensure((size_t)n_pad * h->P_pad));
         FLX_TRY(ypred_d.ensure(n));
         FLX_TRY(rssf_d.ensure(P));
         FLX_TRY(rss0_d.ensure(P));
         FLX_CUDA_TRY(cudaMemcpyAsync(idx_d.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         FLX_CUDA_TRY(cudaMemcpyAsync(ep_d.p, h->e_p.data(), m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        FLX_CUDA_TRY(cudaMemcpyAsync(U1d.p, h->U1_copy.data(), (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (!h->perm_implicit) FLX_CUDA_TRY(cudaMemcpyAsync(U1d.p, h->U1_copy.data(), (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         FLX_CUDA_TRY(cudaMemcpyAsync(ypred_d.p, h->y_pred.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         FLX_CUDA_TRY(cudaMemsetAsync(UE.p, 0, (size_t)n_pad * h->P_pad * sizeof(double), h->stream));
-        FLX_TRY(launch_gather_ep(ep_d.p, idx_d.p, m, P, E.p, h->stream));
         const double one = 1.0, zero = 0.0;
-        // U1 %*% sample(e.p) for every seed: one plain library GEMM (setup, outside the hot loop)
-        FLX_CUBLAS_TRY(cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, U1d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
+        if (h->perm_implicit) {
+            // U1 = Q[:, rank:] of the Householder QR of the null design, applied as reflectors: O(n c P), no n x m matrix
+            DevBuf<double> Vd, bd;
+            const int rk = h->nullfit.rank;
+            FLX_TRY(Vd.ensure((size_t)n * std::max(rk, 1)));
+            FLX_TRY(bd.ensure(std::max(rk, 1)));
+            FLX_CUDA_TRY(cudaMemcpyAsync(Vd.p, h->nullfit.V.data(), (size_t)n * std::max(rk, 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(bd.p, h->nullfit.beta.data(), std::max(rk, 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            FLX_TRY(launch_implicit_u1(ep_d.p, idx_d.p, m, P, Vd.p, bd.p, rk, n, n_pad, UE.p, h->stream));
+            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        } else {
+            FLX_TRY(launch_gather_ep(ep_d.p, idx_d.p, m, P, E.p, h->stream));
+            // U1 %*% sample(e.p) for every seed: one plain library GEMM (setup, outside the hot loop)
+            FLX_CUBLAS_TRY(cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, U1d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
+        }
         PermPrepArgs pa{};
         pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.crp = gram_padded_width(cr); pa.Qn = h->Qn.p; pa.cn = h->cn; pa.cnp = gram_padded_width(h->cn);
         pa.n = n; pa.n_pad = n_pad; pa.P = P; pa.rss_f = rssf_d.p; pa.rss0 = rss0_d.p;

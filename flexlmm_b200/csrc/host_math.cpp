@@ -122,6 +122,88 @@ int orth_basis(const double* C, int64_t n, int nc, std::vector<double>& Q, std::
 }
 
 // ------------------------------------------------------------------------------------------------
+// Null fit with implicit complement basis
+// ------------------------------------------------------------------------------------------------
+void NullFit::apply_Q(double* z) const {
+    for (int j = rank - 1; j >= 0; --j) {
+        const double* v = V.data() + static_cast<int64_t>(j) * n;
+        const long double t = ldot(v + j, z + j, n - j) * beta[j];
+        for (int64_t i = j; i < n; ++i) z[i] -= static_cast<double>(t) * v[i];
+    }
+}
+void NullFit::apply_Qt(double* z) const {
+    for (int j = 0; j < rank; ++j) {
+        const double* v = V.data() + static_cast<int64_t>(j) * n;
+        const long double t = ldot(v + j, z + j, n - j) * beta[j];
+        for (int64_t i = j; i < n; ++i) z[i] -= static_cast<double>(t) * v[i];
+    }
+}
+
+void null_fit_householder(const double* X, int64_t n, int c, const double* y, NullFit& out) {
+    out.n = n;
+    // accepted columns by the in-order rank rule (same rule as orth_basis)
+    std::vector<double> Qtmp, Rtmp;
+    std::vector<int> keep;
+    {
+        std::vector<double> q(static_cast<size_t>(n) * (c > 0 ? c : 1)), v(static_cast<size_t>(n));
+        int r = 0;
+        for (int j = 0; j < c; ++j) {
+            const double* cj = X + static_cast<int64_t>(j) * n;
+            const double orig = std::sqrt(static_cast<double>(ldot(cj, cj, n)));
+            std::memcpy(v.data(), cj, sizeof(double) * n);
+            for (int pass = 0; pass < 2; ++pass)
+                for (int i = 0; i < r; ++i) {
+                    const double* qi = q.data() + static_cast<int64_t>(i) * n;
+                    const double t = static_cast<double>(ldot(qi, v.data(), n));
+                    for (int64_t k = 0; k < n; ++k) v[k] -= t * qi[k];
+                }
+            const double rem = std::sqrt(static_cast<double>(ldot(v.data(), v.data(), n)));
+            if (rem < ((orig == 0.0) ? 1.0 : orig) * 1e-7) continue;
+            double* qr = q.data() + static_cast<int64_t>(r) * n;
+            for (int64_t k = 0; k < n; ++k) qr[k] = v[k] / rem;
+            keep.push_back(j);
+            ++r;
+        }
+    }
+    const int r = static_cast<int>(keep.size());
+    out.rank = r;
+    out.V.assign(static_cast<size_t>(n) * (r > 0 ? r : 1), 0.0);
+    out.beta.assign(r > 0 ? r : 1, 0.0);
+    // Householder QR of the accepted columns
+    std::vector<double> A(static_cast<size_t>(n) * (r > 0 ? r : 1));
+    for (int j = 0; j < r; ++j) std::memcpy(A.data() + static_cast<int64_t>(j) * n, X + static_cast<int64_t>(keep[j]) * n, sizeof(double) * n);
+    for (int j = 0; j < r; ++j) {
+        double* a = A.data() + static_cast<int64_t>(j) * n;
+        const double alpha = a[j];
+        const double nrm = std::sqrt(static_cast<double>(ldot(a + j, a + j, n - j)));
+        double* v = out.V.data() + static_cast<int64_t>(j) * n;
+        if (nrm == 0.0) { out.beta[j] = 0.0; continue; }
+        const double s = (alpha >= 0.0) ? -nrm : nrm;       // a_j -> s e_j
+        for (int64_t i = j; i < n; ++i) v[i] = a[i];
+        v[j] = alpha - s;
+        const double vnorm2 = static_cast<double>(ldot(v + j, v + j, n - j));
+        out.beta[j] = (vnorm2 > 0.0) ? 2.0 / vnorm2 : 0.0;
+        for (int k = j; k < r; ++k) {
+            double* ak = A.data() + static_cast<int64_t>(k) * n;
+            const double t = static_cast<double>(ldot(v + j, ak + j, n - j)) * out.beta[j];
+            for (int64_t i = j; i < n; ++i) ak[i] -= t * v[i];
+        }
+    }
+    // lm.fit: Q'y, fitted = Q [Q'y](1:r; 0), residuals = Q (0; [Q'y](r+1:n))
+    std::vector<double> qty(y, y + n);
+    out.apply_Qt(qty.data());
+    out.e_p.assign(qty.begin() + r, qty.end());
+    out.fitted.assign(static_cast<size_t>(n), 0.0);
+    for (int i = 0; i < r; ++i) out.fitted[i] = qty[i];
+    out.apply_Q(out.fitted.data());
+    out.resid.resize(static_cast<size_t>(n));
+    long double rss = 0.0L;
+    for (int64_t i = 0; i < n; ++i) { out.resid[i] = y[i] - out.fitted[i]; rss += static_cast<long double>(out.resid[i]) * out.resid[i]; }
+    const double N = static_cast<double>(n);
+    out.ll = 0.5 * (0.0 - N * (std::log(2.0 * 3.14159265358979323846) + 1.0 - std::log(N) + std::log(static_cast<double>(rss))));
+}
+
+// ------------------------------------------------------------------------------------------------
 // .pgen (plink-ng pgenlib on-disk format), hard calls only.
 // ------------------------------------------------------------------------------------------------
 PgenFile::~PgenFile() {

@@ -16,6 +16,22 @@ void r_sample_int(int32_t seed, int64_t m, int32_t* out);
 // columns in that basis (col-major, ld = r).
 int orth_basis(const double* C, int64_t n, int nc, std::vector<double>& Q, std::vector<double>& R);
 
+// Null-model fit with an IMPLICIT orthonormal basis of the complement of the null design (FIT_NULL_MODEL without the n x n
+// eigen-decomposition, fit_null_model.nf:33-72).  Householder QR of the accepted columns of X (dqrdc2's rank rule):
+//   reflectors V (n x r, column j zero above row j), beta (r);  Q = H_1 ... H_r,  U1 = Q[:, r:]  (never formed).
+struct NullFit {
+    int64_t n = 0;
+    int rank = 0;
+    std::vector<double> V, beta;      // reflectors
+    std::vector<double> fitted, resid;  // lm.fit
+    std::vector<double> e_p;          // U1' e  (length n - rank)
+    double ll = 0.0;                  // stats:::logLik.lm
+    // z (n) <- Q z   /   z <- Q' z
+    void apply_Q(double* z) const;
+    void apply_Qt(double* z) const;
+};
+void null_fit_householder(const double* X, int64_t n, int c, const double* y, NullFit& out);
+
 // .pgen access for hard calls (pgenlibr::NewPgen / ReadHardcalls, fit_model.nf:39-40,123).
 class PgenFile {
 public:

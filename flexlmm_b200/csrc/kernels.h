@@ -152,6 +152,8 @@ struct PermPrepArgs {
     double* rss_f; double* rss0;  // [P]
 };
 int launch_perm_prep(const PermPrepArgs& a, cudaStream_t st);
+// Y[:, p] = Q [0 (r rows); e_p[idx_p]]  with Q = H_1 ... H_r given by reflectors V (n x r) and beta (implicit U1)
+int launch_implicit_u1(const double* e_p, const int32_t* idx, int64_t m, int P, const double* V, const double* beta, int r, int64_t n, int64_t ldy, double* Y, cudaStream_t st);
 // E[j, p] = e_p[idx[p*m + j] - 1]
 int launch_gather_ep(const double* e_p, const int32_t* idx, int64_t m, int P, double* E, cudaStream_t st);
 // V = a*V + b*I in place (decorrelate.nf:54)

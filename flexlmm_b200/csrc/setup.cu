@@ -111,6 +111,38 @@ int launch_gather_ep(const double* e_p, const int32_t* idx, int64_t m, int P, do
     return 0;
 }
 
+// ---- implicit U1: Y[:, p] = H_1 ... H_r [0; e_p[idx_p]]   (one CTA per permutation column)
+__global__ void __launch_bounds__(256) implicit_u1_kernel(const double* __restrict__ e_p, const int32_t* __restrict__ idx, int64_t m,
+                                                          const double* __restrict__ V, const double* __restrict__ beta, int r, int64_t n, int64_t ldy,
+                                                          double* __restrict__ Y) {
+    __shared__ double sh[8];
+    const int64_t p = blockIdx.x;
+    double* col = Y + p * ldy;
+    for (int64_t i = threadIdx.x; i < n; i += 256) col[i] = (i < r) ? 0.0 : e_p[idx[p * m + (i - r)] - 1];
+    __syncthreads();
+    for (int j = r - 1; j >= 0; --j) {
+        const double* v = V + (int64_t)j * n;
+        double t = 0.0;
+        for (int64_t i = j + threadIdx.x; i < n; i += 256) t += v[i] * col[i];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < 8; w++) tot += sh[w];
+        tot *= beta[j];
+        for (int64_t i = j + threadIdx.x; i < n; i += 256) col[i] -= tot * v[i];
+        __syncthreads();
+    }
+}
+int launch_implicit_u1(const double* e_p, const int32_t* idx, int64_t m, int P, const double* V, const double* beta, int r, int64_t n, int64_t ldy, double* Y, cudaStream_t st) {
+    if (P <= 0) return 0;
+    implicit_u1_kernel<<<(unsigned)P, 256, 0, st>>>(e_p, idx, m, V, beta, r, n, ldy, Y);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("implicit_u1 launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
 // ---- permutation prologue, one CTA per permutation column
 //   y* = y_pred + U1 E[:, p]                                       (fit_model.nf:98)
 //   rss0[p]  = || y* - Qn Qn' y* ||^2   (null refit, fit_model.nf:100-101)

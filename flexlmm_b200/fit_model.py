@@ -27,6 +27,23 @@ def minp_threshold(min_pval, p_thr=0.05):
     return _capi.load().flx_minp_threshold(x.ctypes.data, x.size, float(p_thr))
 
 
+def fit_null_model(X_mm, y_mm, want_U1=False):
+    """FIT_NULL_MODEL without the n x n eigen (fit_null_model.nf:33-72): ll, df, y_pred, resid, e_p and, on request, an explicit
+    copy of the implicit Householder complement basis U1.  Host-only."""
+    X = f64(X_mm, fortran=True); y = f64(y_mm)
+    n = y.size
+    X = X.reshape(n, -1, order="F")
+    ll, df, m = C.c_double(), C.c_int32(), C.c_int64()
+    y_pred = np.empty(n); resid = np.empty(n); e_p = np.empty(n)
+    check(_capi.load().flx_fit_null_model(ptr(X), X.shape[1], ptr(y), n, C.byref(ll), C.byref(df), ptr(y_pred), ptr(resid), ptr(e_p), None, C.byref(m)))
+    out = dict(ll=ll.value, df=df.value, y_pred=y_pred, resid=resid, e_p=e_p[: m.value].copy(), m=m.value)
+    if want_U1:
+        U1 = np.empty((n, m.value), order="F")
+        check(_capi.load().flx_fit_null_model(ptr(X), X.shape[1], ptr(y), n, None, None, None, None, None, ptr(U1), None))
+        out["U1"] = U1
+    return out
+
+
 class FitModel:
     """One FIT_MODEL task bound to one B200.  Method order mirrors the R script: inputs (:30-66), then run (:120-171)."""
 
@@ -100,6 +117,12 @@ class FitModel:
             return
         y_pred = f64(y_pred); U1 = f64(U1, fortran=True); e_p = f64(np.ravel(e_p))
         check(self._lib.flx_set_perm(self._h, ptr(y_pred), ptr(U1), ptr(e_p), e_p.size, ptr(seeds), self.P))
+
+    def set_perm_implicit(self, seeds):
+        """Permutations from the implicit Householder complement of the null design given to set_null (no U1 matrix)."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        self.P = int(seeds.size)
+        check(self._lib.flx_set_perm_implicit(self._h, ptr(seeds), self.P))
 
     def open_pgen(self, path, pgen_order=None, n=None):
         """pgenlibr::NewPgen + match(samples, psam$IID) (fit_model.nf:40,70). pgen_order is 1-based."""

@@ -118,6 +118,22 @@ int  flx_set_design(flx_handle* h, const double* M0, const double* M1, const dou
 int  flx_set_perm(flx_handle* h, const double* y_pred, const double* U1, const double* e_p, int64_t m,
                   const int32_t* seeds, int32_t P);
 
+/* FIT_NULL_MODEL without the n x n eigen-decomposition (/root/reference/modules/local/r/fit_null_model.nf:33-72).
+ * The reference needs SOME orthonormal basis U1 of the orthogonal complement of the null design to decorrelate the
+ * residuals (e.p = U1' e, :65) and takes the LAPACK eigenvectors of I - QQ' (:52-62) — an O(n^3) step with three n x n
+ * matrices, and an arbitrary basis of a repeated eigenvalue.  Here the basis is the implicit Householder complement
+ * Q[:, rank:] of the QR of X.mm: O(nc) storage, never materialised.
+ *   outputs (host, any may be NULL): ll (+ df = rank + 1), y_pred = fitted (n), resid (n), e_p (m = n - rank),
+ *   U1 (n x m column-major, explicit copy of the implicit basis — for tests / for feeding the reference's own PERM path).
+ * Host-only; no GPU needed. */
+int  flx_fit_null_model(const double* X_mm, int32_t c, const double* y_mm, int64_t n, double* ll, int32_t* df,
+                        double* y_pred, double* resid, double* e_p, double* U1, int64_t* m);
+
+/* Permutations from the implicit basis: same as flx_set_perm(y_pred, U1, e_p, ...) with the y_pred / U1 / e_p that
+ * flx_fit_null_model derives from the null model already given to flx_set_null, but U1 (n x m, 80 GB at n = 10^5) is never
+ * formed: y* = y_pred + Q [0; e_p[idx]] costs O(ncP).  Index order is R's set.seed(seed); sample(e.p) as always. */
+int  flx_set_perm_implicit(flx_handle* h, const int32_t* seeds, int32_t P);
+
 /* Genotype source A: a .pgen file (fit_model.nf:39-40,54,123).  pgen_order[i] = 1-based raw-sample index of
  * model sample i (fit_model.nf:70,124: match(samples, psam$IID)). Modes 0x02 and 0x10 (hard calls). */
 int  flx_open_pgen(flx_handle* h, const char* path, const int32_t* pgen_order, int64_t n);

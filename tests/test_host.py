@@ -181,3 +181,25 @@ def test_cat_perm_and_summarise_by_chr(fx, orc, tmp_path):
     th = fx.thresholds(table, n_tests=22, p_thr=0.05)
     assert th["bonferroni"] == 0.05 / 22
     assert th["perm_thr"] == pytest.approx(orc.quantile7([t[1] for t in table], 0.05), abs=1e-16)
+
+
+def test_fit_null_model_implicit_basis(fx, orc):
+    """FIT_NULL_MODEL without the n x n eigen: lm.fit quantities equal the oracle's; the implicit complement basis is an
+    orthonormal basis of the orthogonal complement of the null design (what fit_null_model.nf:52-65 needs of U1)."""
+    rng = np.random.default_rng(0)
+    n = 150
+    X = np.column_stack([np.ones(n), rng.standard_normal(n), np.zeros(n), rng.standard_normal(n)])
+    X[:, 3] = 2 * X[:, 1] - 1                                   # rank 2 of 4
+    X = np.column_stack([X, rng.standard_normal(n)])           # rank 3 of 5
+    y = rng.standard_normal(n)
+    r = fx.fit_null_model(X, y, want_U1=True)
+    f = orc.lm_fit(X, y)
+    assert r["df"] == f["rank"] + 1 == 4 and r["m"] == n - 3
+    assert r["ll"] == pytest.approx(orc.loglik_lm(f["residuals"]), rel=1e-13)
+    np.testing.assert_allclose(r["resid"], f["residuals"], atol=1e-13)
+    np.testing.assert_allclose(r["y_pred"], y - f["residuals"], atol=1e-13)
+    U1 = r["U1"]
+    np.testing.assert_allclose(U1.T @ U1, np.eye(r["m"]), atol=1e-13)
+    np.testing.assert_allclose(U1.T @ X, 0, atol=1e-13)
+    np.testing.assert_allclose(U1.T @ f["residuals"], r["e_p"], atol=1e-13)
+    np.testing.assert_allclose(U1 @ r["e_p"], f["residuals"], atol=1e-13)     # e = U1 e.p: the decorrelation is lossless

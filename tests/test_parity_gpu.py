@@ -532,3 +532,26 @@ def test_decorrelate_eigenvalue_clipping_fallback(fx):
         with pytest.raises(fx.FlxError) as e:
             fm.decorrelate(K_bad, 1.0, 0.0, y, X)
         assert "min_allowed_eig" in str(e.value)
+
+
+# ------------------------------------------------------------------------------------------------ implicit U1 (§8f rank 2)
+@pytest.mark.parametrize("model,int8", [("additive", True), ("domgxe", False)])
+def test_implicit_complement_permutations(fx, orc, model, int8):
+    """flx_set_perm_implicit == flx_set_perm with the (y_pred, U1, e_p) of flx_fit_null_model == the oracle's PERM tasks on them."""
+    from flexlmm_b200 import synth
+    n, M, P = 260, 70, 4
+    t = synth.task(n, M, model=model, P=P, seed=12)
+    nf = fx.fit_null_model(t["X_null"], t["y_mm"], want_U1=True)
+    assert nf["df"] == t["df_null"] and nf["ll"] == pytest.approx(t["ll_null"], rel=1e-12)
+    vi = np.arange(1, M + 1, dtype=np.int32)
+    with fx.FitModel(int8=int8) as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], nf["ll"], nf["df"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        fm.set_perm_implicit(t["seeds"])
+        r_imp = fm.run(vi)
+        fm.set_perm(nf["y_pred"], nf["U1"], nf["e_p"], t["seeds"])
+        r_exp = fm.run(vi)
+    assert_logp_close(r_imp["min_pval"], r_exp["min_pval"])
+    t2 = dict(t); t2.update(y_pred=nf["y_pred"], U1=nf["U1"], e_p=nf["e_p"], ll_null=nf["ll"], df_null=nf["df"])
+    want = np.array([oracle_run(orc, t2, t["codes_raw"], seed=int(s))["min_pval"] for s in t["seeds"]])
+    assert_logp_close(r_imp["min_pval"], want)
