@@ -837,10 +837,26 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                     if (contiguous) memcpy(st, h->packed_host + (size_t)(var_idx[s0] - 1) * bpv, (size_t)nsnp * bpv);
                     else for (int64_t i = 0; i < nsnp; i++) memcpy(st + i * bpv, h->packed_host + (size_t)(var_idx[s0 + i] - 1) * bpv, bpv);
                 } else if (h->src == 1) {
-                    for (int64_t i = 0; i < nsnp; i++) {
-                        std::string e = h->pgen->read_packed((uint32_t)(var_idx[s0 + i] - 1), st + i * bpv);
-                        if (!e.empty()) { set_error("pgen variant %d: %s", var_idx[s0 + i], e.c_str()); return FLX_ERR_PGEN; }
+                    // host expansion of LD / difflist / 1-bit records to packed 2-bit, one slice of the batch per host thread
+                    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 32u), nsnp / 256));
+                    std::vector<std::string> errs(nt);
+                    std::vector<int64_t> err_at(nt, -1);
+                    auto work = [&](unsigned ti) {
+                        PgenFile::LdCache cache;
+                        const int64_t lo = nsnp * ti / nt, hi = nsnp * (ti + 1) / nt;
+                        for (int64_t i = lo; i < hi; i++) {
+                            std::string e = h->pgen->read_packed((uint32_t)(var_idx[s0 + i] - 1), st + i * bpv, cache);
+                            if (!e.empty()) { errs[ti] = e; err_at[ti] = i; return; }
+                        }
+                    };
+                    if (nt == 1) work(0);
+                    else {
+                        std::vector<std::thread> th;
+                        for (unsigned ti = 0; ti < nt; ti++) th.emplace_back(work, ti);
+                        for (auto& x : th) x.join();
                     }
+                    for (unsigned ti = 0; ti < nt; ti++)
+                        if (err_at[ti] >= 0) { set_error("pgen variant %d: %s", var_idx[s0 + err_at[ti]], errs[ti].c_str()); return FLX_ERR_PGEN; }
                 } else { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
                 src_ptr = st;
             }

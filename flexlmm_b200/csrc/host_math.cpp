@@ -357,7 +357,7 @@ std::string PgenFile::decode_main(const Rec& r, uint8_t* out) const {
     return "";
 }
 
-std::string PgenFile::read_packed(uint32_t v, uint8_t* out) {
+std::string PgenFile::read_packed(uint32_t v, uint8_t* out, LdCache& cache) const {
     if (v >= variant_ct_) return "variant index out of range";
     const int64_t bpv = bytes_per_variant();
     if (mode_ == 0x02) {
@@ -369,13 +369,13 @@ std::string PgenFile::read_packed(uint32_t v, uint8_t* out) {
     if ((r.vrtype & 6) != 2) return decode_main(r, out);
     // LD-compressed against the nearest earlier non-LD variant
     const uint32_t b = ldbase_[v];
-    if (cached_base_ != b) {
-        base_geno_.resize(static_cast<size_t>(bpv));
-        std::string e = decode_main(recs_[b], base_geno_.data());
+    if (cache.base != b) {
+        cache.geno.resize(static_cast<size_t>(bpv));
+        std::string e = decode_main(recs_[b], cache.geno.data());
         if (!e.empty()) return e;
-        cached_base_ = b;
+        cache.base = b;
     }
-    std::memcpy(out, base_geno_.data(), static_cast<size_t>(bpv));
+    std::memcpy(out, cache.geno.data(), static_cast<size_t>(bpv));
     const uint8_t* p = data_ + r.off;
     std::string e = apply_difflist(p, p + r.len, out);
     if (!e.empty()) return e;

@@ -47,7 +47,10 @@ public:
     // If the file is mode 0x02 the records are already packed 2-bit: pointer to record v (0-based).
     const uint8_t* fixed_record(uint32_t v) const { return data_ + 12 + (int64_t)v * bytes_per_variant(); }
     // Expand variant v (0-based) to packed 2-bit (bytes_per_variant() bytes, pad bits 0). Any mode.
-    std::string read_packed(uint32_t v, uint8_t* out);
+    // The decoded LD base lives in the caller's cache, so several threads can expand disjoint variant ranges concurrently.
+    struct LdCache { int64_t base = -1; std::vector<uint8_t> geno; };
+    std::string read_packed(uint32_t v, uint8_t* out, LdCache& cache) const;
+    std::string read_packed(uint32_t v, uint8_t* out) { return read_packed(v, out, own_cache_); }
 private:
     struct Rec { uint64_t off; uint32_t len; uint8_t vrtype; };
     std::string parse();
@@ -62,8 +65,7 @@ private:
     bool has_dosage_ = false;
     std::vector<Rec> recs_;           // mode 0x10
     std::vector<uint32_t> ldbase_;    // mode 0x10: index of the LD base record for LD-compressed variants
-    int64_t cached_base_ = -1;
-    std::vector<uint8_t> base_geno_;
+    LdCache own_cache_;
 };
 
 }  // namespace flx

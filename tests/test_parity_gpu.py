@@ -555,3 +555,31 @@ def test_implicit_complement_permutations(fx, orc, model, int8):
     t2 = dict(t); t2.update(y_pred=nf["y_pred"], U1=nf["U1"], e_p=nf["e_p"], ll_null=nf["ll"], df_null=nf["df"])
     want = np.array([oracle_run(orc, t2, t["codes_raw"], seed=int(s))["min_pval"] for s in t["seeds"]])
     assert_logp_close(r_imp["min_pval"], want)
+
+
+def test_pgen_mode10_threaded_expansion(fx, tmp_path):
+    """Enough variants that the host expansion of LD / difflist records is split over threads, each with its own LD-base cache."""
+    from flexlmm_b200 import synth
+    from pgen_writer import write_pgen
+    rng = np.random.default_rng(9)
+    n, M = 97, 5000
+    c = rng.integers(0, 3, size=(M, n)).astype(np.uint8)
+    for v in range(1, M):                       # LD-friendly: most variants differ from the previous one in a few samples
+        if v % 7:
+            c[v] = c[v - 1]
+            flip = rng.choice(n, size=3, replace=False)
+            c[v, flip] = rng.integers(0, 3, size=3)
+    vt = [0] + [int(x) for x in rng.choice([0, 1, 2, 2, 2, 3, 4, 6], size=M - 1)]
+    path = tmp_path / "big.pgen"
+    path.write_bytes(write_pgen(c, vt))
+    t = synth.task(n, 8, model="simple", seed=1)
+    with fx.FitModel() as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.open_pgen(path, None)
+        info = fm.pgen_info()
+        assert info == dict(variant_ct=M, sample_ct=n, has_dosage=False)
+        vi = np.arange(1, M + 1, dtype=np.int32)
+        _, cd = fm.decode_tile(vi, want_X=False)
+        assert np.array_equal(cd, c)
+        r = fm.run(vi)
+        assert r["nvars_tested"] == M and np.isfinite(r["lrt_chisq"]).all()
