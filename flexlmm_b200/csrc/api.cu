@@ -919,6 +919,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.QG = QG; q.Q = h->Q; q.NKB = h->NKB;
             q.NKB_live = (int)((h->n + 63) / 64);
             q.n_items = (int64_t)h->T256 * NJ * QG;
+            q.use_cluster = (h->cfg.flags & FLX_FLAG_CLUSTER_MULTICAST) ? 1 : 0;
             DevBuf<long long> prof_d;
             const bool prof = h->cfg.verbose >= 2 && bi == 0;
             if (prof) { FLX_TRY(prof_d.ensure(3 * (size_t)h->num_sms)); q.prof = prof_d.p; }

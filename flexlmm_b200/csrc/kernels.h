@@ -39,6 +39,7 @@ struct QfArgs {
     int T256, NJ, QG, Q;
     int NKB;                  // k-blocks per X8 tile (n_pad256 / 64)
     int NKB_live;             // k-blocks that hold real samples
+    int use_cluster;          // 1: 2-CTA clusters with multicast of the digit-plane blocks
     long long* prof;          // optional [3 * grid]: MMA-issuer cycles total / waiting for the epilogue / waiting for TMA
 };
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
