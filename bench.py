@@ -140,7 +140,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)
 
     def start(self):
         self._t = threading.Thread(target=self._loop, daemon=True); self._t.start()
@@ -221,7 +221,7 @@ def stage_roofline(w, acc, steps, int8_path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -243,7 +243,7 @@ def main():
         if rank != 0:
             return 0
         # each "step" = a bounded sample of the workload on all host cores
-        auto = max(4, int(round(64 * (5000.0 / w["n"]) ** 2)))
+        auto = max(4, int(round(16 * (5000.0 / w["n"]) ** 2)))       # ~3 s of CPU work per step on every core
         snps = a.cpu_snps or auto
         tasks = 3  # 1 ORIG + 2 PERM tasks per SNP sample
         vals = []
