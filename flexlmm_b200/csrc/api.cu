@@ -191,6 +191,7 @@ extern "C" int flx_create(const flx_config* cfg, flx_handle** out) {
     }
     flx_handle* h = new flx_handle();
     if (cfg) h->cfg = *cfg;
+    h->Q = (h->cfg.flags & FLX_FLAG_PLANES_5) ? 5 : 6;
     if (h->cfg.device < 0 || h->cfg.device >= cnt) { set_error("flx_create: device %d out of range (%d devices)", h->cfg.device, cnt); delete h; return FLX_ERR_BAD_ARG; }
     cudaError_t e = cudaSetDevice(h->cfg.device);
     if (e != cudaSuccess) { set_error("cudaSetDevice: %s", cudaGetErrorString(e)); delete h; return FLX_ERR_CUDA; }
@@ -754,7 +755,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const int cr = h->cr;
     const int crp = use_fast ? h->NB_A : gram_padded_width(cr);
     constexpr int KS_MAX = 32;
-    const int QG = h->Q / 2;
+    const int QG = (h->Q + 1) / 2;
     const bool decode_only = (X_out_dense != nullptr) || (codes_out != nullptr);
 
     // validate indices; contiguity lets the resident path skip the index map
@@ -966,6 +967,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         sa.chisq = h->chisq.p; sa.pval = h->pval.p; sa.df = h->df.p; sa.rank = h->rank.p; sa.pivot = h->pivot.p; sa.coef = h->coef.p;
         sa.snp_df = do_perm ? h->snp_df.p : nullptr; sa.snp_sm = do_perm ? h->snp_sm.p : nullptr;
         sa.df_count = h->df_count.p;
+        sa.refit_thr = std::ldexp(1e-5, 8 * (6 - h->Q));   // the digit planes resolve 2^-8Q of x'V^-1x: keep ~9 digits of A
         sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * QG * 2;
         sa.refit_flag = use_fast ? h->refit_flag.p + s0 : nullptr;
         FLX_TRY(launch_snp_solve(sa, h->stream));

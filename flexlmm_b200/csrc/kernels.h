@@ -130,6 +130,7 @@ struct SolveArgs {
     const int32_t* out_map;   // optional: run-wide output slot of batch SNP q (refit pass), else out_offset + q
     // fast (int8 quadratic form) mode, s == 1: A_raw = 2 * sum of qf_nparts partials; u, b from the H sweep (u_part)
     int fast;
+    double refit_thr;         // re-fit in FP64 when A <= refit_thr * A_raw
     const double* qf_part; int qf_nparts;
     int32_t* refit_flag;      // [nsnp] set to 1 when the SNP must be re-fitted on the FP64 path (near-collinear with the constant columns)
 };

@@ -110,12 +110,13 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
                 const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + QF_QC * qg) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
+                const int np = min(QF_QC, g.Q - QF_QC * qg);      // an odd plane count leaves the last item a single plane
                 for (int kb = 0; kb < nkb; kb++) {
                     qbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
-                    qbar_expect_tx(&full_bar[stage], QF_STAGE_BYTES);
+                    qbar_expect_tx(&full_bar[stage], QF_A_BYTES + np * QF_B_BYTES);
                     qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
-                    qtma_bulk_g2s(dst + QF_A_BYTES, b_src + (int64_t)kb * g.Q * QF_B_BYTES, QF_QC * QF_B_BYTES, &full_bar[stage]);
+                    qtma_bulk_g2s(dst + QF_A_BYTES, b_src + (int64_t)kb * g.Q * QF_B_BYTES, np * QF_B_BYTES, &full_bar[stage]);
                     if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             const long long t_begin = g.prof ? clock64() : 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
+                const int np = min(QF_QC, g.Q - QF_QC * ((int)(item % per_I) / g.NJ));
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 if (g.prof) t0 = clock64();
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                     const uint32_t sa = qsmem_u32(smem + (size_t)stage * QF_STAGE_BYTES);
 #pragma unroll
                     for (int q = 0; q < QF_QC; q++) {
+                        if (q >= np) break;
                         const uint32_t sb = sa + QF_A_BYTES + q * QF_B_BYTES;
 #pragma unroll
                         for (int j = 0; j < QF_KB / 32; j++) {
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             const int I = g.T256 - 1 - (int)(item / per_I);
             const int rem = (int)(item % per_I);
             const int qg = rem / g.NJ, J = rem % g.NJ;
+            const bool two = (g.Q - QF_QC * qg) >= 2;
             // this SNP's own genotypes at the rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
             const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
             const double* rs = g.rowscale + 256 * (int64_t)I + cbase;
@@ -187,13 +191,13 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             double sum = 0.0;
             uint32_t hi[2][16], lo[2][16];
             XG_TMEM_LD16(hi[0], trow);
-            XG_TMEM_LD16(lo[0], trow + 256);
+            if (two) XG_TMEM_LD16(lo[0], trow + 256);
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;");
                 if (c + 1 < 8) {      // next 16 rows in flight while these are reduced
                     XG_TMEM_LD16(hi[(c + 1) & 1], trow + 16 * (c + 1));
-                    XG_TMEM_LD16(lo[(c + 1) & 1], trow + 256 + 16 * (c + 1));
+                    if (two) XG_TMEM_LD16(lo[(c + 1) & 1], trow + 256 + 16 * (c + 1));
                 }
                 const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
 #pragma unroll
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                     // planes combined exactly in int64 (|hi*256 + lo| < 2^40, times |x| <= 127), then to FP64 without I2F
                     // (int->double conversions run at 16/clk/SM and were the epilogue's bottleneck): 2^52 + 2^51 + v has v in
                     // its mantissa, one DADD removes the bias.
-                    const long long cx = ((long long)(int)hi[c & 1][j] * 256 + (long long)(int)lo[c & 1][j]) * x;
+                    const long long cx = ((long long)(int)hi[c & 1][j] * 256 + (two ? (long long)(int)lo[c & 1][j] : 0LL)) * x;
                     const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
                     sum = fma(d, rs[16 * c + j], sum);
                 }

@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
         A[0][0] = araw - uu;
         bq[0] = bsum;
         // the subtraction loses log2(A_raw / A) bits: hand near-collinear SNPs (monomorphic, ...) to the FP64 path
-        refit = !(A[0][0] > 1e-5 * araw);
+        refit = !(A[0][0] > a.refit_thr * araw);
     } else {
         // partial sums of the sample splits, fixed order
         int q = 0;

@@ -47,10 +47,10 @@ def fit_null_model(X_mm, y_mm, want_U1=False):
 class FitModel:
     """One FIT_MODEL task bound to one B200.  Method order mirrors the R script: inputs (:30-66), then run (:120-171)."""
 
-    def __init__(self, device=0, batch_tiles=0, verbose=0, int8=True):
+    def __init__(self, device=0, batch_tiles=0, verbose=0, int8=True, planes=6):
         self._lib = _capi.load()
         self._h = C.c_void_p()
-        cfg = FlxConfig(int(device), int(batch_tiles), int(verbose), 0 if int8 else 1)
+        cfg = FlxConfig(int(device), int(batch_tiles), int(verbose), (0 if int8 else 1) | (4 if planes == 5 else 0))
         check(self._lib.flx_create(C.byref(cfg), C.byref(self._h)))
         self._keep = {}
         self.n = None
