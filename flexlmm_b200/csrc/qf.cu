@@ -18,6 +18,7 @@
 //             the SNP's own genotype at that row, scale by the row's power of two and sum over the 256 rows IN THE THREAD
 //             (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane pair, SNP).
 // Work item = (row tile I of 256 rows, SNP tile J of 128, plane pair qg); k runs over the lower-triangular range.
+#include <cuda.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,10 +26,10 @@ namespace flx {
 
 constexpr int QF_KB = 64;                     // k bytes per stage
 constexpr int QF_A_BYTES = 128 * QF_KB;       // 8 KB  (X8 tile block)
-constexpr int QF_B_BYTES = 256 * QF_KB;       // 16 KB (one digit plane block)
+constexpr int QF_B_BYTES = 128 * QF_KB;       // 8 KB: THIS CTA's half (128 of the 256 rows) of one digit-plane block
 constexpr int QF_QC = 2;                      // planes per work item (2 x 256 TMEM columns)
 constexpr int QF_STAGE_BYTES = QF_A_BYTES + QF_QC * QF_B_BYTES;
-constexpr int QF_STAGES = 5;
+constexpr int QF_STAGES = 8;
 constexpr int QF_SMEM = QF_STAGES * QF_STAGE_BYTES + 256;
 constexpr int QF_THREADS = 320;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int XG_THREADS = 192;
@@ -73,7 +74,40 @@ constexpr uint32_t QF_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) 
                    "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
                  : "r"(taddr))
 
-__global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void qbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(qsmem_u32(bar)), "r"(cta) : "memory");
+}
+// 2-D tensor-map TMA of one 8 KB block (64 rows x 128 B); with .cta_group::2 the completion may be signalled on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_block_2sm(void* dst, const CUtensorMap* tm, int row, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(qsmem_u32(dst)), "l"(tm),
+                 "r"(leader_bar), "r"(0), "r"(row)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// tcgen05.commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(qsmem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// instruction descriptor for the CTA pair: M = 256 (128 SNPs per CTA), N = 256 rows of T
+constexpr uint32_t QF_IDESC_2SM = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
+// K2q as a CTA PAIR (tcgen05 cta_group::2): the two CTAs of a cluster own SNP tiles 2p and 2p+1 and share every block of
+// digit planes — each CTA stages only ITS HALF of the 256 rows of T (8 KB per plane instead of 16 KB), the tensor cores of the two
+// SMs exchange the halves.  Per-SM operand ingest drops from 40 KB to 24 KB per 64 samples, so 8 stages (192 KB) cover
+// ~4000 cycles of L2 latency instead of ~2500 and the MMA issuer no longer starves.  Both CTAs' TMA loads complete on the
+// leader's barrier (.cta_group::2), the leader issues the MMAs for both, tcgen05.commit multicasts stage-free and
+// accumulator-ready to both CTAs, each CTA's epilogue drains its own TMEM.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const __grid_constant__ QfArgs g) {
+    const uint32_t crank = cluster_ctarank();
+    const int64_t cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + QF_STAGES;
@@ -85,55 +119,60 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < QF_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 1); }
         qbar_init(acc_full, 1);
-        qbar_init(acc_empty, 8);
+        qbar_init(acc_empty, 16);      // 8 epilogue warps of each CTA of the pair (the peer's arrive remotely on the leader)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qsmem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qsmem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    cluster_sync_all();      // both CTAs' barriers and TMEM are ready before any remote arrive / 2-SM instruction
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
 
-    const int per_I = g.NJ * g.QG;
+    const int NJp = (g.NJ + 1) / 2;
+    const int per_I = NJp * g.QG;
+    const int64_t n_pair_items = (int64_t)g.T256 * per_I;
     if (warp == 0) {
-        // ---------------- TMA producer
+        // ---------------- TMA producer (both CTAs): own X8 block + own half of each digit-plane block
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+            for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
                 const int rem = (int)(item % per_I);
-                const int qg = rem / g.NJ, J = rem % g.NJ;
+                const int qg = rem / NJp;
+                const int J = min(2 * (rem % NJp) + (int)crank, g.NJ - 1);   // an odd tile count leaves the last pair's second CTA a duplicate
+                const int np = min(QF_QC, g.Q - QF_QC * qg);                 // an odd plane count leaves the last item a single plane
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
-                const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
-                const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + QF_QC * qg) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
-                const int np = min(QF_QC, g.Q - QF_QC * qg);      // an odd plane count leaves the last item a single plane
+                const uint32_t stage_bytes = QF_A_BYTES + np * QF_B_BYTES;
                 for (int kb = 0; kb < nkb; kb++) {
                     qbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
-                    qbar_expect_tx(&full_bar[stage], QF_A_BYTES + np * QF_B_BYTES);
-                    qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
-                    qtma_bulk_g2s(dst + QF_A_BYTES, b_src + (int64_t)kb * g.Q * QF_B_BYTES, np * QF_B_BYTES, &full_bar[stage]);
+                    const uint32_t lbar = qsmem_u32(&full_bar[stage]) & 0xFEFFFFFFu;     // the leader CTA's barrier (peer bit cleared)
+                    if (crank == 0) qbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    tma_block_2sm(dst, &g.tmX, (int)(((int64_t)J * g.NKB + kb) * 64), lbar);
+                    const int64_t tb = ((int64_t)2 * I * (I + 1) + kb) * g.Q + QF_QC * qg;   // plane index of (I, kb, first plane of the item)
+                    for (int q = 0; q < np; q++) tma_block_2sm(dst + QF_A_BYTES + q * QF_B_BYTES, &g.tmT, (int)(((tb + q) * 2 + crank) * 64), lbar);
                     if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer
-        if (lane == 0) {
+        // ---------------- MMA issuer: the leader CTA issues for the pair
+        if (lane == 0 && crank == 0) {
             uint32_t stage = 0, phase = 0, aphase = 0;
             long long t_acc = 0, t_full = 0, t0 = 0;
             const long long t_begin = g.prof ? clock64() : 0;
-            for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+            for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
-                const int np = min(QF_QC, g.Q - QF_QC * ((int)(item % per_I) / g.NJ));
+                const int np = min(QF_QC, g.Q - QF_QC * ((int)(item % per_I) / NJp));
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 if (g.prof) t0 = clock64();
-                qbar_wait(acc_empty, aphase ^ 1);           // epilogue has drained the accumulators of the previous item
+                qbar_wait(acc_empty, aphase ^ 1);           // both epilogues have drained the accumulators of the previous item
                 if (g.prof) t_acc += clock64() - t0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < nkb; kb++) {
@@ -148,20 +187,19 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                         const uint32_t sb = sa + QF_A_BYTES + q * QF_B_BYTES;
 #pragma unroll
                         for (int j = 0; j < QF_KB / 32; j++) {
-                            // A block: [k16 chunk 4][row group 16][8 rows][16 B]  -> LBO 2048 B, SBO 128 B
-                            // B block: [k16 chunk 4][row group 32][8 rows][16 B]  -> LBO 4096 B, SBO 128 B
+                            // A block (this CTA's 128 SNPs) and B half-block (this CTA's 128 rows of T): [k16 chunk 4][group 16][8][16 B]
                             const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
-                            const uint64_t bd = umma_desc(sb + j * 8192, 4096, 128);
-                            umma_i8(tmem_base + q * 256, ad, bd, QF_IDESC, (kb > 0 || j > 0) ? 1u : 0u);
+                            const uint64_t bd = umma_desc(sb + j * 4096, 2048, 128);
+                            umma_i8_2sm(tmem_base + q * 256, ad, bd, QF_IDESC_2SM, (kb > 0 || j > 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);
+                    umma_commit_2sm(&empty_bar[stage]);      // frees the stage in both CTAs
                     if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(acc_full);
+                umma_commit_2sm(acc_full);                   // accumulators ready in both CTAs
                 aphase ^= 1;
             }
-            if (g.prof) { g.prof[3 * blockIdx.x] = clock64() - t_begin; g.prof[3 * blockIdx.x + 1] = t_acc; g.prof[3 * blockIdx.x + 2] = t_full; }
+            if (g.prof) { g.prof[3 * cl_id] = clock64() - t_begin; g.prof[3 * cl_id + 1] = t_acc; g.prof[3 * cl_id + 2] = t_full; }
         }
     } else {
         // ---------------- epilogue: thread = TMEM lane = SNP of the tile; the two warps of a lane quadrant split the 256 rows
@@ -170,10 +208,13 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         const int snp_l = quad * 32 + lane;
         const int cbase = half * 128;
         uint32_t aphase = 0;
-        for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
             const int I = g.T256 - 1 - (int)(item / per_I);
             const int rem = (int)(item % per_I);
-            const int qg = rem / g.NJ, J = rem % g.NJ;
+            const int qg = rem / NJp;
+            const int Jraw = 2 * (rem % NJp) + (int)crank;
+            const bool live_tile = Jraw < g.NJ;
+            const int J = min(Jraw, g.NJ - 1);
             const bool two = (g.Q - QF_QC * qg) >= 2;
             // this SNP's own genotypes at the rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
             const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
@@ -213,220 +254,55 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
-            if (lane == 0) qbar_arrive(acc_empty);
-            const int64_t snp = (int64_t)J * 128 + snp_l;
-            if (snp < g.nsnp) g.part[(((int64_t)I * g.QG + qg) * 2 + half) * g.nsnp + snp] = sum * g.group_scale[qg];
-        }
-    }
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-}
-
-// ---- cluster variant: two CTAs (SNP tiles 2p and 2p+1) walk the same (row tile, plane pair) sequence in lock step; each
-// loads ONE of the two digit-plane blocks of a stage and multicasts it into both CTAs' shared memory, halving the L2 read
-// traffic of the shared operand.  A stage is free when BOTH tensor cores have consumed it (tcgen05.commit multicast).
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void qtma_bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(qsmem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(qsmem_u32(bar)), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(qsmem_u32(bar)), "h"(mask) : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QF_THREADS, 1) qf_i8_mc_kernel(const QfArgs g) {
-    const int crank = (int)cluster_ctarank();
-    const int64_t cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + QF_STAGES;
-    uint64_t* acc_full = empty_bar + QF_STAGES;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < QF_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 2); }
-        qbar_init(acc_full, 1);
-        qbar_init(acc_empty, 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qsmem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / multicast
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int NJp = (g.NJ + 1) / 2;
-    const int per_I = NJp * g.QG;
-    const int64_t n_pair_items = (int64_t)g.T256 * per_I;
-    if (warp == 0) {
-        // ---------------- TMA producer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
-                const int I = g.T256 - 1 - (int)(item / per_I);
-                const int rem = (int)(item % per_I);
-                const int qg = rem / NJp;
-                const int J = min(2 * (rem % NJp) + crank, g.NJ - 1);   // an odd tile count leaves the last pair's second CTA a duplicate
-                int nkb = 4 * (I + 1);
-                if (nkb > g.NKB_live) nkb = g.NKB_live;
-                const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
-                const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + QF_QC * qg) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
-                for (int kb = 0; kb < nkb; kb++) {
-                    qbar_wait(&empty_bar[stage], phase ^ 1);
-                    unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
-                    qbar_expect_tx(&full_bar[stage], QF_STAGE_BYTES);
-                    qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
-                    // this CTA fetches plane `crank` of the pair and multicasts it to both CTAs (same offsets, both full barriers)
-                    qtma_bulk_g2s_mc(dst + QF_A_BYTES + crank * QF_B_BYTES, b_src + ((int64_t)kb * g.Q + crank) * QF_B_BYTES, QF_B_BYTES, &full_bar[stage], (uint16_t)3);
-                    if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
-                }
+            if (lane == 0) {
+                if (crank == 0) qbar_arrive(acc_empty);
+                else qbar_arrive_remote(acc_empty, 0);
             }
-        }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, aphase = 0;
-            long long t_acc = 0, t_full = 0, t0 = 0;
-            const long long t_begin = g.prof ? clock64() : 0;
-            for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
-                const int I = g.T256 - 1 - (int)(item / per_I);
-                int nkb = 4 * (I + 1);
-                if (nkb > g.NKB_live) nkb = g.NKB_live;
-                if (g.prof) t0 = clock64();
-                qbar_wait(acc_empty, aphase ^ 1);           // epilogue has drained the accumulators of the previous item
-                if (g.prof) t_acc += clock64() - t0;
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                for (int kb = 0; kb < nkb; kb++) {
-                    if (g.prof) t0 = clock64();
-                    qbar_wait(&full_bar[stage], phase);
-                    if (g.prof) t_full += clock64() - t0;
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t sa = qsmem_u32(smem + (size_t)stage * QF_STAGE_BYTES);
-#pragma unroll
-                    for (int q = 0; q < QF_QC; q++) {
-                        const uint32_t sb = sa + QF_A_BYTES + q * QF_B_BYTES;
-#pragma unroll
-                        for (int j = 0; j < QF_KB / 32; j++) {
-                            // A block: [k16 chunk 4][row group 16][8 rows][16 B]  -> LBO 2048 B, SBO 128 B
-                            // B block: [k16 chunk 4][row group 32][8 rows][16 B]  -> LBO 4096 B, SBO 128 B
-                            const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
-                            const uint64_t bd = umma_desc(sb + j * 8192, 4096, 128);
-                            umma_i8(tmem_base + q * 256, ad, bd, QF_IDESC, (kb > 0 || j > 0) ? 1u : 0u);
-                        }
-                    }
-                    umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees this stage in BOTH CTAs once these MMAs have read it
-                    if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
-                }
-                umma_commit(acc_full);
-                aphase ^= 1;
-            }
-            if (g.prof) { g.prof[3 * blockIdx.x] = clock64() - t_begin; g.prof[3 * blockIdx.x + 1] = t_acc; g.prof[3 * blockIdx.x + 2] = t_full; }
-        }
-    } else {
-        // ---------------- epilogue: thread = TMEM lane = SNP of the tile; the two warps of a lane quadrant split the 256 rows
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int snp_l = quad * 32 + lane;
-        const int cbase = half * 128;
-        uint32_t aphase = 0;
-        for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
-            const int I = g.T256 - 1 - (int)(item / per_I);
-            const int rem = (int)(item % per_I);
-            const int qg = rem / NJp;
-            const int Jraw = 2 * (rem % NJp) + crank;
-            const bool live_tile = Jraw < g.NJ;
-            const int J = min(Jraw, g.NJ - 1);
-            // this SNP's own genotypes at the rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
-            const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
-            const double* rs = g.rowscale + 256 * (int64_t)I + cbase;
-            uint4 xq[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int r = cbase + 16 * c;
-                xq[c] = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)(r >> 6) * QF_A_BYTES + (((r & 63) >> 4) * 16) * 128));
-            }
-            qbar_wait(acc_full, aphase);
-            aphase ^= 1;
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + cbase;
-            double sum = 0.0;
-            uint32_t hi[2][16], lo[2][16];
-            XG_TMEM_LD16(hi[0], trow);
-            XG_TMEM_LD16(lo[0], trow + 256);
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
-                if (c + 1 < 8) {      // next 16 rows in flight while these are reduced
-                    XG_TMEM_LD16(hi[(c + 1) & 1], trow + 16 * (c + 1));
-                    XG_TMEM_LD16(lo[(c + 1) & 1], trow + 256 + 16 * (c + 1));
-                }
-                const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int x = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xff);
-                    // planes combined exactly in int64 (|hi*256 + lo| < 2^40, times |x| <= 127), then to FP64 without I2F
-                    // (int->double conversions run at 16/clk/SM and were the epilogue's bottleneck): 2^52 + 2^51 + v has v in
-                    // its mantissa, one DADD removes the bias.
-                    const long long cx = ((long long)(int)hi[c & 1][j] * 256 + (long long)(int)lo[c & 1][j]) * x;
-                    const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
-                    sum = fma(d, rs[16 * c + j], sum);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) qbar_arrive(acc_empty);
             const int64_t snp = (int64_t)J * 128 + snp_l;
             if (live_tile && snp < g.nsnp) g.part[(((int64_t)I * g.QG + qg) * 2 + half) * g.nsnp + snp] = sum * g.group_scale[qg];
         }
     }
     __syncthreads();
-    cluster_sync_all();      // no CTA exits while its peer may still multicast into it or arrive on its barriers
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    cluster_sync_all();      // no CTA exits (or frees TMEM) while its peer may still use it
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
+// tensor map over a buffer of contiguous 8 KB blocks: 2-D uint8 tensor {128 B, bytes / 128}, box {128, 64}, no swizzle
+int make_block_tensor_map(CUtensorMap* out, const void* base, size_t bytes) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !encode) { set_error("cuTensorMapEncodeTiled entry point: %s", cudaGetErrorString(e)); encode = nullptr; return -3; }
+    }
+    const cuuint64_t dims[2] = {128, (cuuint64_t)(bytes / 128)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {128, 64};
+    const cuuint32_t es[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
+    return 0;
+}
 
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
     static bool configured = false;
-    static int max_clusters = 0;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qf_i8_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(qf): %s", cudaGetErrorString(e)); return -3; }
-        // how many 2-CTA clusters can be co-resident (one CTA per SM)
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(QF_THREADS); cfg.dynamicSmemBytes = QF_SMEM;
-        cudaLaunchAttribute attr{};
-        attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, qf_i8_mc_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = num_sms / 2; }
-        if (max_clusters > num_sms / 2) max_clusters = num_sms / 2;
         configured = true;
     }
     if (g.n_items <= 0) return 0;
     const int64_t n_pair_items = (int64_t)g.T256 * g.QG * ((g.NJ + 1) / 2);
-    if (g.use_cluster && max_clusters > 0 && g.NJ >= 2) {
-        const int64_t ncl = n_pair_items < max_clusters ? n_pair_items : max_clusters;
-        qf_i8_mc_kernel<<<(unsigned)(2 * ncl), QF_THREADS, QF_SMEM, st>>>(g);
-    } else {
-        const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
-        qf_i8_kernel<<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
-    }
+    const int64_t max_cl = num_sms / 2;
+    const int64_t ncl = n_pair_items < max_cl ? n_pair_items : max_cl;
+    qf_i8_kernel<<<(unsigned)(2 * ncl), QF_THREADS, QF_SMEM, st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("qf launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
 }
-int qf_max_clusters() { return 0; }
 
 // ------------------------------------------------------------------------------------------------
 // K1q: packed 2-bit hard calls -> int8 tile in the UMMA canonical K-major layout (A operand of K2q)
@@ -515,7 +391,7 @@ __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __rest
     const int64_t i = (int64_t)I * 256 + rl;
     const double inv = (i < n) ? 1.0 / rowscale[i] : 0.0;
     const double up = ldexp(1.0, 8 * Q);
-    int8_t* blk = T8 + ((int64_t)2 * I * (I + 1) + kb) * Q * QF_B_BYTES;
+    int8_t* blk = T8 + ((int64_t)2 * I * (I + 1) + kb) * Q * (2 * QF_B_BYTES);   // per plane: [row half 2][k16 chunk 4][row group 16][8][16 B]
     for (int ch = 0; ch < 4; ch++) {
         uint32_t w[7][4];
         for (int q = 0; q < Q; q++) w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
@@ -531,7 +407,8 @@ __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __rest
             }
         }
         for (int q = 0; q < Q; q++) {
-            uint4* dst = reinterpret_cast<uint4*>(blk + (int64_t)q * QF_B_BYTES + ((ch * 32 + (rl >> 3)) * 8 + (rl & 7)) * 16);
+            const int rh = rl & 127;
+            uint4* dst = reinterpret_cast<uint4*>(blk + ((int64_t)q * 2 + (rl >> 7)) * QF_B_BYTES + ((ch * 16 + (rh >> 3)) * 8 + (rh & 7)) * 16);
             *dst = make_uint4(w[q][0], w[q][1], w[q][2], w[q][3]);
         }
     }
