@@ -920,19 +920,18 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.QG = QG; q.Q = h->Q; q.NKB = h->NKB;
             q.NKB_live = (int)((h->n + 63) / 64);
             q.n_items = (int64_t)h->T256 * NJ * QG;
-            FLX_TRY(make_block_tensor_map(&q.tmX, h->X8.p, h->X8.cap));
-            FLX_TRY(make_block_tensor_map(&q.tmT, h->T8.p, h->T8.cap));
+            q.use_cluster = (h->cfg.flags & FLX_FLAG_CLUSTER_MULTICAST) ? 1 : 0;
             DevBuf<long long> prof_d;
             const bool prof = h->cfg.verbose >= 2 && bi == 0;
-            if (prof) { FLX_TRY(prof_d.ensure(3 * (size_t)h->num_sms)); FLX_CUDA_TRY(cudaMemsetAsync(prof_d.p, 0, 3 * (size_t)h->num_sms * sizeof(long long), h->stream)); q.prof = prof_d.p; }
+            if (prof) { FLX_TRY(prof_d.ensure(3 * (size_t)h->num_sms)); q.prof = prof_d.p; }
             FLX_TRY(launch_qf(q, h->num_sms, h->stream));
             if (prof) {
                 std::vector<long long> pv(3 * (size_t)h->num_sms);
                 FLX_CUDA_TRY(cudaMemcpy(pv.data(), prof_d.p, pv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
                 double a0 = 0, a1 = 0, a2 = 0;
                 for (int i = 0; i < h->num_sms; i++) { a0 += pv[3 * i]; a1 += pv[3 * i + 1]; a2 += pv[3 * i + 2]; }
-                fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA pair, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA, items/CTA %.1f\n",
-                        a0 / (h->num_sms / 2), 100 * a1 / a0, 100 * a2 / a0, (double)q.n_items / h->num_sms);
+                fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA, items/CTA %.1f\n",
+                        a0 / h->num_sms, 100 * a1 / a0, 100 * a2 / a0, (double)q.n_items / h->num_sms);
             }
             h->stats.launches += 1; h->stats.launches_whiten++;
             mark();  // [3] fit start

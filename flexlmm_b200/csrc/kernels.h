@@ -1,7 +1,6 @@
 // kernels.h — launch interfaces of the sm_100a kernels (host side of csrc/*.cu).
 #pragma once
 #include <cstdint>
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace flx {
@@ -30,10 +29,8 @@ int launch_perm_contract(const GemmArgs& g, int s, int num_sms, cudaStream_t st)
 
 // ---------------------------------------------------------------- K2q (qf.cu): x' V^-1 x on the int8 tensor cores
 struct QfArgs {
-    CUtensorMap tmX;          // X8 viewed as rows of 128 B, box = one 8 KB block (64 rows)
-    CUtensorMap tmT;          // T8 likewise
     const int8_t* X8;         // [NJ][NKB][8 KB]  int8 genotype tiles (128 SNPs x 64 samples per block, UMMA canonical K-major)
-    const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][row half 2][8 KB] digit planes of T = tril(V^-1) (half diagonal)
+    const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(V^-1) (half diagonal)
     const double* rowscale;   // [n_pad256] power-of-two scale of each row of T
     double group_scale[4];    // 2^-16(qg+1)
     double* part;             // [T256][QG][2 row halves][nsnp] partial quadratic forms
@@ -42,10 +39,10 @@ struct QfArgs {
     int T256, NJ, QG, Q;
     int NKB;                  // k-blocks per X8 tile (n_pad256 / 64)
     int NKB_live;             // k-blocks that hold real samples
+    int use_cluster;          // 1: 2-CTA clusters with multicast of the digit-plane blocks
     long long* prof;          // optional [3 * grid]: MMA-issuer cycles total / waiting for the epilogue / waiting for TMA
 };
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
-int make_block_tensor_map(CUtensorMap* out, const void* base, size_t bytes);   // rows of 128 B, 64-row (8 KB) boxes
 
 // K4q (qf.cu): X8 against digit planes of a column block of G = L^-T [Qc | r | R_f]
 struct XgArgs {
