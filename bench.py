@@ -36,6 +36,8 @@ WORKLOADS = {
     "C2-small": dict(n=5000, M=100_000, model="additive", P=100, s=1, c=2, k=3,
                      desc="synthetic n=5,000 x 100k SNPs (reduced M, NOT the headline config)"),
     "tiny": dict(n=1000, M=20_000, model="additive", P=20, s=1, c=2, k=3, desc="debug"),
+    "A20k": dict(n=20000, M=100_000, model="additive", P=1000, s=1, c=2, k=3,
+                 desc="synthetic n=20,000, additive, 1,000 permutations, 100k SNPs per GPU (int8 route at a larger n)"),
     "C3-1gpu": dict(n=20000, M=100_000, model="domgxe", P=1000, s=3, c=2, k=5,
                     desc="synthetic n=20,000, dominance + GxE, 1,000 permutations, 100k SNPs per GPU (per-GPU slice of configs[2])"),
 }
