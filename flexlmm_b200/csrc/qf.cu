@@ -200,16 +200,19 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                     if (two) XG_TMEM_LD16(lo[(c + 1) & 1], trow + 256 + 16 * (c + 1));
                 }
                 const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
+                // the 16 rows of a chunk share one power-of-two scale, so the chunk is reduced exactly in int64
+                // (|acc| < 2^30, |x| <= 127: |sum| < 2^49) and converted once, without I2F (16/clk/SM): 2^52 + 2^51 + v has v
+                // in its mantissa, one DADD removes the bias.
+                long long sh = 0, sl = 0;
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const int x = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xff);
-                    // planes combined exactly in int64 (|hi*256 + lo| < 2^40, times |x| <= 127), then to FP64 without I2F
-                    // (int->double conversions run at 16/clk/SM and were the epilogue's bottleneck): 2^52 + 2^51 + v has v in
-                    // its mantissa, one DADD removes the bias.
-                    const long long cx = ((long long)(int)hi[c & 1][j] * 256 + (two ? (long long)(int)lo[c & 1][j] : 0LL)) * x;
-                    const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
-                    sum = fma(d, rs[16 * c + j], sum);
+                    sh += (long long)(int)hi[c & 1][j] * x;
+                    if (two) sl += (long long)(int)lo[c & 1][j] * x;
                 }
+                const long long cx = sh * 256 + sl;
+                const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
+                sum = fma(d, rs[16 * c], sum);
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
@@ -494,17 +497,18 @@ int launch_decode_i8(const DecodeArgs& a, int8_t* X8, int NJ, int NKB, cudaStrea
 //        packed as the B operand:  T8[row tile I][kb < 4(I+1)][plane q][k16 chunk 4][row group 32][8 rows][16 B]
 // ------------------------------------------------------------------------------------------------
 __global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int64_t ld, int64_t n_pad, double* __restrict__ rowscale) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pad) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // grid covers n_pad exactly (multiple of 256)
     double m = 0.0;
     if (i < n) {
         for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(V[i + j * ld]));
         m = fmax(m, 0.5 * fabs(V[i + i * ld]));
     }
+    // one scale per 16 consecutive rows (= one tcgen05.ld chunk of the K2q epilogue, which then reduces the chunk in int64)
+    for (int off = 8; off >= 1; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
     // scale = 2^(e+1) with max < 2^e  =>  |T / scale| < 0.5
     int e = 0;
     if (m > 0.0) { frexp(m, &e); }            // m = f * 2^e, f in [0.5, 1)  =>  m < 2^e
-    rowscale[i] = (m > 0.0) ? ldexp(1.0, e + 1) : 1.0;
+    if (i < n_pad) rowscale[i] = (m > 0.0) ? ldexp(1.0, e + 1) : 1.0;
 }
 
 __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __restrict__ V, int64_t n, int64_t ld, const double* __restrict__ rowscale, int Q,
