@@ -755,7 +755,6 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const int cr = h->cr;
     const int crp = use_fast ? h->NB_A : gram_padded_width(cr);
     constexpr int KS_MAX = 32;
-    const int QG = (h->Q + 1) / 2;
     const bool decode_only = (X_out_dense != nullptr) || (codes_out != nullptr);
 
     // validate indices; contiguity lets the resident path skip the index map
@@ -770,7 +769,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         if (!use_fast) FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
         if (use_fast) {
             FLX_TRY(h->X8.ensure((size_t)tiles_per_batch * h->NKB * 8192));
-            FLX_TRY(h->qf_part.ensure((size_t)h->T256 * QG * 2 * snps_per_batch));
+            FLX_TRY(h->qf_part.ensure((size_t)h->T256 * h->Q * snps_per_batch));
             FLX_TRY(h->refit_flag.ensure(M_total));
         }
         FLX_TRY(h->n_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
@@ -916,22 +915,21 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             // K2q: the exact quadratic form x' V^-1 x on the i8 tensor pipe
             QfArgs q{};
             q.X8 = h->X8.p; q.T8 = h->T8.p; q.rowscale = h->rowscale.p; q.part = h->qf_part.p;
-            for (int i = 0; i < 4; i++) q.group_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-            q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.QG = QG; q.Q = h->Q; q.NKB = h->NKB;
+            for (int i = 0; i < 8; i++) q.plane_scale[i] = std::ldexp(1.0, -8 * (i + 1));
+            q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.Q = h->Q; q.NKB = h->NKB;
             q.NKB_live = (int)((h->n + 63) / 64);
-            q.n_items = (int64_t)h->T256 * NJ * QG;
-            q.use_cluster = (h->cfg.flags & FLX_FLAG_CLUSTER_MULTICAST) ? 1 : 0;
+            q.n_items = (int64_t)h->T256 * h->Q * ((NJ + 1) / 2);
             DevBuf<long long> prof_d;
             const bool prof = h->cfg.verbose >= 2 && bi == 0;
-            if (prof) { FLX_TRY(prof_d.ensure(3 * (size_t)h->num_sms)); q.prof = prof_d.p; }
+            if (prof) { FLX_TRY(prof_d.ensure(4 * (size_t)h->num_sms)); q.prof = prof_d.p; }
             FLX_TRY(launch_qf(q, h->num_sms, h->stream));
             if (prof) {
-                std::vector<long long> pv(3 * (size_t)h->num_sms);
+                std::vector<long long> pv(4 * (size_t)h->num_sms);
                 FLX_CUDA_TRY(cudaMemcpy(pv.data(), prof_d.p, pv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-                double a0 = 0, a1 = 0, a2 = 0;
-                for (int i = 0; i < h->num_sms; i++) { a0 += pv[3 * i]; a1 += pv[3 * i + 1]; a2 += pv[3 * i + 2]; }
-                fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA, items/CTA %.1f\n",
-                        a0 / h->num_sms, 100 * a1 / a0, 100 * a2 / a0, (double)q.n_items / h->num_sms);
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                for (int i = 0; i < h->num_sms; i++) { a0 += pv[4 * i]; a1 += pv[4 * i + 1]; a2 += pv[4 * i + 2]; a3 += pv[4 * i + 3]; }
+                fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA (%.1f%% in the first ring of an item), items/CTA %.1f\n",
+                        a0 / h->num_sms, 100 * a1 / a0, 100 * a2 / a0, 100 * a3 / a0, (double)q.n_items / h->num_sms);
             }
             h->stats.launches += 1; h->stats.launches_whiten++;
             mark();  // [3] fit start
@@ -968,7 +966,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         sa.snp_df = do_perm ? h->snp_df.p : nullptr; sa.snp_sm = do_perm ? h->snp_sm.p : nullptr;
         sa.df_count = h->df_count.p;
         sa.refit_thr = std::ldexp(1e-5, 8 * (6 - h->Q));   // the digit planes resolve 2^-8Q of x'V^-1x: keep ~9 digits of A
-        sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * QG * 2;
+        sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * h->Q;
         sa.refit_flag = use_fast ? h->refit_flag.p + s0 : nullptr;
         FLX_TRY(launch_snp_solve(sa, h->stream));
         h->stats.launches += 1;

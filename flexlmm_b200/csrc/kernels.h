@@ -31,16 +31,15 @@ int launch_perm_contract(const GemmArgs& g, int s, int num_sms, cudaStream_t st)
 struct QfArgs {
     const int8_t* X8;         // [NJ][NKB][8 KB]  int8 genotype tiles (128 SNPs x 64 samples per block, UMMA canonical K-major)
     const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(V^-1) (half diagonal)
-    const double* rowscale;   // [n_pad256] power-of-two scale of each row of T
-    double group_scale[4];    // 2^-16(qg+1)
-    double* part;             // [T256][QG][2 row halves][nsnp] partial quadratic forms
+    const double* rowscale;   // [n_pad256] power-of-two scale of each row of T (one value per 16 consecutive rows)
+    double plane_scale[8];    // 2^-8(q+1)
+    double* part;             // [T256][Q][nsnp] partial quadratic forms
     int64_t n_items;
     int64_t nsnp;
-    int T256, NJ, QG, Q;
+    int T256, NJ, Q;
     int NKB;                  // k-blocks per X8 tile (n_pad256 / 64)
     int NKB_live;             // k-blocks that hold real samples
-    int use_cluster;          // 1: 2-CTA clusters with multicast of the digit-plane blocks
-    long long* prof;          // optional [3 * grid]: MMA-issuer cycles total / waiting for the epilogue / waiting for TMA
+    long long* prof;          // optional [4 * grid]: MMA-issuer cycles total / waiting for the epilogue / waiting for TMA / of which in the first ring of an item
 };
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
 

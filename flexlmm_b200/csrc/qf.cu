@@ -11,13 +11,15 @@
 //
 // Kernel: persistent, warp-specialised, one CTA per SM.
 //   warp 0  : TMA producer — 1-D bulk copies of pre-packed operand blocks (UMMA canonical K-major, no swizzle: 8 x 16 B
-//             core matrices) into a 5-stage x 40 KB ring.
+//             core matrices) into a 7-stage x 32 KB ring.  The kernel runs at the L2 -> SM throughput cap, so the work
+//             item is shaped for operand reuse: TWO SNP tiles (2 x 8 KB) against ONE digit-plane block (16 KB).
 //   warp 1  : allocates 512 TMEM columns; one lane issues tcgen05.mma.cta_group::1.kind::i8, M = 128 SNPs (A = X8 tile),
-//             N = 256 rows of T (B = two digit planes per work item), K = 32 per instruction; tcgen05.commit frees stages.
-//   warps 2-5: epilogue — tcgen05.ld the two 128 x 256 s32 accumulators, combine the planes exactly in int64, multiply by
-//             the SNP's own genotype at that row, scale by the row's power of two and sum over the 256 rows IN THE THREAD
-//             (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane pair, SNP).
-// Work item = (row tile I of 256 rows, SNP tile J of 128, plane pair qg); k runs over the lower-triangular range.
+//             N = 256 rows of T (B = one digit plane), K = 32 per instruction, one 128 x 256 s32 accumulator per SNP tile;
+//             tcgen05.commit frees stages.
+//   warps 2-9: epilogue — tcgen05.ld an accumulator 16 rows at a time, multiply by the SNP's own genotype at that row,
+//             reduce the 16 rows exactly in int64 (they share one power-of-two scale), scale and sum over the 256 rows
+//             IN THE THREAD (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane, SNP).
+// Work item = (row tile I of 256 rows, digit plane q, pair of SNP tiles); k runs over the lower-triangular range.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,9 +28,8 @@ namespace flx {
 constexpr int QF_KB = 64;                     // k bytes per stage
 constexpr int QF_A_BYTES = 128 * QF_KB;       // 8 KB  (X8 tile block)
 constexpr int QF_B_BYTES = 256 * QF_KB;       // 16 KB (one digit plane block)
-constexpr int QF_QC = 2;                      // planes per work item (2 x 256 TMEM columns)
-constexpr int QF_STAGE_BYTES = QF_A_BYTES + QF_QC * QF_B_BYTES;
-constexpr int QF_STAGES = 5;
+constexpr int QF_STAGE_BYTES = 2 * QF_A_BYTES + QF_B_BYTES;   // two SNP tiles share one digit-plane block
+constexpr int QF_STAGES = 7;
 constexpr int QF_SMEM = QF_STAGES * QF_STAGE_BYTES + 256;
 constexpr int QF_THREADS = 320;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int XG_THREADS = 192;
@@ -73,6 +74,13 @@ constexpr uint32_t QF_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) 
                    "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
                  : "r"(taddr))
 
+// sign-extended byte b of w in one PRMT (selector nibble 8|b replicates the byte's sign bit)
+__device__ __forceinline__ int sext_byte(uint32_t w, int b) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(w), "r"(0x8880u + 0x1111u * (uint32_t)b));
+    return (int)d;
+}
+
 __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
@@ -97,7 +105,9 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
 
-    const int per_I = g.NJ * g.QG;
+    // item -> (row tile I, digit plane q, SNP tile pair JP); long row tiles first
+    const int NJ2 = (g.NJ + 1) >> 1;
+    const int per_I = NJ2 * g.Q;
     if (warp == 0) {
         // ---------------- TMA producer
         if (lane == 0) {
@@ -105,18 +115,19 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
                 const int rem = (int)(item % per_I);
-                const int qg = rem / g.NJ, J = rem % g.NJ;
+                const int q = rem / NJ2, JP = rem % NJ2;
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
-                const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
-                const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + QF_QC * qg) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
-                const int np = min(QF_QC, g.Q - QF_QC * qg);      // an odd plane count leaves the last item a single plane
+                const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;      // an odd tile count leaves the last pair a single tile
+                const int8_t* a_src = g.X8 + (int64_t)(2 * JP) * g.NKB * QF_A_BYTES;
+                const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + q) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
                 for (int kb = 0; kb < nkb; kb++) {
                     qbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
-                    qbar_expect_tx(&full_bar[stage], QF_A_BYTES + np * QF_B_BYTES);
+                    qbar_expect_tx(&full_bar[stage], nt * QF_A_BYTES + QF_B_BYTES);
+                    qtma_bulk_g2s(dst + 2 * QF_A_BYTES, b_src + (int64_t)kb * g.Q * QF_B_BYTES, QF_B_BYTES, &full_bar[stage]);
                     qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
-                    qtma_bulk_g2s(dst + QF_A_BYTES, b_src + (int64_t)kb * g.Q * QF_B_BYTES, np * QF_B_BYTES, &full_bar[stage]);
+                    if (nt == 2) qtma_bulk_g2s(dst + QF_A_BYTES, a_src + ((int64_t)g.NKB + kb) * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
                     if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -125,11 +136,12 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         // ---------------- MMA issuer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, aphase = 0;
-            long long t_acc = 0, t_full = 0, t0 = 0;
+            long long t_acc = 0, t_full = 0, t_head = 0, t0 = 0;
             const long long t_begin = g.prof ? clock64() : 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
-                const int np = min(QF_QC, g.Q - QF_QC * ((int)(item % per_I) / g.NJ));
+                const int JP = (int)(item % per_I) % NJ2;
+                const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 if (g.prof) t0 = clock64();
@@ -139,20 +151,20 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                 for (int kb = 0; kb < nkb; kb++) {
                     if (g.prof) t0 = clock64();
                     qbar_wait(&full_bar[stage], phase);
-                    if (g.prof) t_full += clock64() - t0;
+                    if (g.prof) { const long long dt = clock64() - t0; t_full += dt; if (kb < QF_STAGES) t_head += dt; }
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t sa = qsmem_u32(smem + (size_t)stage * QF_STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * QF_A_BYTES;
 #pragma unroll
-                    for (int q = 0; q < QF_QC; q++) {
-                        if (q >= np) break;
-                        const uint32_t sb = sa + QF_A_BYTES + q * QF_B_BYTES;
+                    for (int t = 0; t < 2; t++) {
+                        if (t >= nt) break;
 #pragma unroll
                         for (int j = 0; j < QF_KB / 32; j++) {
                             // A block: [k16 chunk 4][row group 16][8 rows][16 B]  -> LBO 2048 B, SBO 128 B
                             // B block: [k16 chunk 4][row group 32][8 rows][16 B]  -> LBO 4096 B, SBO 128 B
-                            const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
+                            const uint64_t ad = umma_desc(sa + t * QF_A_BYTES + j * 4096, 2048, 128);
                             const uint64_t bd = umma_desc(sb + j * 8192, 4096, 128);
-                            umma_i8(tmem_base + q * 256, ad, bd, QF_IDESC, (kb > 0 || j > 0) ? 1u : 0u);
+                            umma_i8(tmem_base + t * 256, ad, bd, QF_IDESC, (kb > 0 || j > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
@@ -161,275 +173,77 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                 umma_commit(acc_full);
                 aphase ^= 1;
             }
-            if (g.prof) { g.prof[3 * blockIdx.x] = clock64() - t_begin; g.prof[3 * blockIdx.x + 1] = t_acc; g.prof[3 * blockIdx.x + 2] = t_full; }
+            if (g.prof) { g.prof[4 * blockIdx.x] = clock64() - t_begin; g.prof[4 * blockIdx.x + 1] = t_acc; g.prof[4 * blockIdx.x + 2] = t_full; g.prof[4 * blockIdx.x + 3] = t_head; }
         }
     } else {
-        // ---------------- epilogue: thread = TMEM lane = SNP of the tile; the two warps of a lane quadrant split the 256 rows
+        // ---------------- epilogue: thread = TMEM lane = SNP; warps 2-5 own the first SNP tile of the pair, warps 6-9 the second
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int t = (warp - 2) >> 2;
         const int snp_l = quad * 32 + lane;
-        const int cbase = half * 128;
         uint32_t aphase = 0;
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             const int I = g.T256 - 1 - (int)(item / per_I);
             const int rem = (int)(item % per_I);
-            const int qg = rem / g.NJ, J = rem % g.NJ;
-            const bool two = (g.Q - QF_QC * qg) >= 2;
+            const int q = rem / NJ2, JP = rem % NJ2;
+            const int J = 2 * JP + t;
+            const bool live = J < g.NJ;
             // this SNP's own genotypes at the rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
-            const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
-            const double* rs = g.rowscale + 256 * (int64_t)I + cbase;
-            uint4 xq[8];
+            const int8_t* xa = g.X8 + ((int64_t)(live ? J : 0) * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
+            const double* rs = g.rowscale + 256 * (int64_t)I;
+            uint4 xq[16];
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int r = cbase + 16 * c;
-                xq[c] = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)(r >> 6) * QF_A_BYTES + (((r & 63) >> 4) * 16) * 128));
-            }
+            for (int c = 0; c < 16; c++) xq[c] = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)(c >> 2) * QF_A_BYTES + ((c & 3) * 16) * 128));
             qbar_wait(acc_full, aphase);
             aphase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + cbase;
             double sum = 0.0;
-            uint32_t hi[2][16], lo[2][16];
-            XG_TMEM_LD16(hi[0], trow);
-            if (two) XG_TMEM_LD16(lo[0], trow + 256);
+            if (live) {
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
+                uint32_t acc[2][16];
+                XG_TMEM_LD16(acc[0], trow);
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
-                if (c + 1 < 8) {      // next 16 rows in flight while these are reduced
-                    XG_TMEM_LD16(hi[(c + 1) & 1], trow + 16 * (c + 1));
-                    if (two) XG_TMEM_LD16(lo[(c + 1) & 1], trow + 256 + 16 * (c + 1));
-                }
-                const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
-                // the 16 rows of a chunk share one power-of-two scale, so the chunk is reduced exactly in int64
-                // (|acc| < 2^30, |x| <= 127: |sum| < 2^49) and converted once, without I2F (16/clk/SM): 2^52 + 2^51 + v has v
-                // in its mantissa, one DADD removes the bias.
-                long long sh = 0, sl = 0;
+                for (int c = 0; c < 16; c++) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;");
+                    if (c + 1 < 16) XG_TMEM_LD16(acc[(c + 1) & 1], trow + 16 * (c + 1));     // next 16 rows in flight while these are reduced
+                    const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
+                    // the 16 rows of a chunk share one power-of-two scale, so the chunk is reduced exactly in s32
+                    // (|acc| <= 128 n |x|max, |x|max <= 2 on this route: launch_qf refuses n that could overflow) and
+                    // converted once, without I2F (16/clk/SM): 2^52 + 2^51 + v has v in its mantissa, one DADD removes the bias.
+                    int cx32 = 0;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int x = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xff);
-                    sh += (long long)(int)hi[c & 1][j] * x;
-                    if (two) sl += (long long)(int)lo[c & 1][j] * x;
-                }
-                const long long cx = sh * 256 + sl;
-                const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
-                sum = fma(d, rs[16 * c], sum);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) qbar_arrive(acc_empty);
-            const int64_t snp = (int64_t)J * 128 + snp_l;
-            if (snp < g.nsnp) g.part[(((int64_t)I * g.QG + qg) * 2 + half) * g.nsnp + snp] = sum * g.group_scale[qg];
-        }
-    }
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-}
-
-// ---- cluster variant: two CTAs (SNP tiles 2p and 2p+1) walk the same (row tile, plane pair) sequence in lock step; each
-// loads ONE of the two digit-plane blocks of a stage and multicasts it into both CTAs' shared memory, halving the L2 read
-// traffic of the shared operand.  A stage is free when BOTH tensor cores have consumed it (tcgen05.commit multicast).
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void qtma_bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(qsmem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(qsmem_u32(bar)), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(qsmem_u32(bar)), "h"(mask) : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QF_THREADS, 1) qf_i8_mc_kernel(const QfArgs g) {
-    const int crank = (int)cluster_ctarank();
-    const int64_t cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + QF_STAGES;
-    uint64_t* acc_full = empty_bar + QF_STAGES;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < QF_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 2); }
-        qbar_init(acc_full, 1);
-        qbar_init(acc_empty, 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qsmem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / multicast
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int NJp = (g.NJ + 1) / 2;
-    const int per_I = NJp * g.QG;
-    const int64_t n_pair_items = (int64_t)g.T256 * per_I;
-    if (warp == 0) {
-        // ---------------- TMA producer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
-                const int I = g.T256 - 1 - (int)(item / per_I);
-                const int rem = (int)(item % per_I);
-                const int qg = rem / NJp;
-                const int J = min(2 * (rem % NJp) + crank, g.NJ - 1);   // an odd tile count leaves the last pair's second CTA a duplicate
-                int nkb = 4 * (I + 1);
-                if (nkb > g.NKB_live) nkb = g.NKB_live;
-                const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
-                const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + QF_QC * qg) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
-                for (int kb = 0; kb < nkb; kb++) {
-                    qbar_wait(&empty_bar[stage], phase ^ 1);
-                    unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
-                    qbar_expect_tx(&full_bar[stage], QF_STAGE_BYTES);
-                    qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
-                    // this CTA fetches plane `crank` of the pair and multicasts it to both CTAs (same offsets, both full barriers)
-                    qtma_bulk_g2s_mc(dst + QF_A_BYTES + crank * QF_B_BYTES, b_src + ((int64_t)kb * g.Q + crank) * QF_B_BYTES, QF_B_BYTES, &full_bar[stage], (uint16_t)3);
-                    if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, aphase = 0;
-            long long t_acc = 0, t_full = 0, t0 = 0;
-            const long long t_begin = g.prof ? clock64() : 0;
-            for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
-                const int I = g.T256 - 1 - (int)(item / per_I);
-                int nkb = 4 * (I + 1);
-                if (nkb > g.NKB_live) nkb = g.NKB_live;
-                if (g.prof) t0 = clock64();
-                qbar_wait(acc_empty, aphase ^ 1);           // epilogue has drained the accumulators of the previous item
-                if (g.prof) t_acc += clock64() - t0;
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                for (int kb = 0; kb < nkb; kb++) {
-                    if (g.prof) t0 = clock64();
-                    qbar_wait(&full_bar[stage], phase);
-                    if (g.prof) t_full += clock64() - t0;
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t sa = qsmem_u32(smem + (size_t)stage * QF_STAGE_BYTES);
-#pragma unroll
-                    for (int q = 0; q < QF_QC; q++) {
-                        const uint32_t sb = sa + QF_A_BYTES + q * QF_B_BYTES;
-#pragma unroll
-                        for (int j = 0; j < QF_KB / 32; j++) {
-                            // A block: [k16 chunk 4][row group 16][8 rows][16 B]  -> LBO 2048 B, SBO 128 B
-                            // B block: [k16 chunk 4][row group 32][8 rows][16 B]  -> LBO 4096 B, SBO 128 B
-                            const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
-                            const uint64_t bd = umma_desc(sb + j * 8192, 4096, 128);
-                            umma_i8(tmem_base + q * 256, ad, bd, QF_IDESC, (kb > 0 || j > 0) ? 1u : 0u);
-                        }
-                    }
-                    umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees this stage in BOTH CTAs once these MMAs have read it
-                    if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
-                }
-                umma_commit(acc_full);
-                aphase ^= 1;
-            }
-            if (g.prof) { g.prof[3 * blockIdx.x] = clock64() - t_begin; g.prof[3 * blockIdx.x + 1] = t_acc; g.prof[3 * blockIdx.x + 2] = t_full; }
-        }
-    } else {
-        // ---------------- epilogue: thread = TMEM lane = SNP of the tile; the two warps of a lane quadrant split the 256 rows
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int snp_l = quad * 32 + lane;
-        const int cbase = half * 128;
-        uint32_t aphase = 0;
-        for (int64_t item = cl_id; item < n_pair_items; item += n_cl) {
-            const int I = g.T256 - 1 - (int)(item / per_I);
-            const int rem = (int)(item % per_I);
-            const int qg = rem / NJp;
-            const int Jraw = 2 * (rem % NJp) + crank;
-            const bool live_tile = Jraw < g.NJ;
-            const int J = min(Jraw, g.NJ - 1);
-            // this SNP's own genotypes at the rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
-            const int8_t* xa = g.X8 + ((int64_t)J * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
-            const double* rs = g.rowscale + 256 * (int64_t)I + cbase;
-            uint4 xq[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int r = cbase + 16 * c;
-                xq[c] = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)(r >> 6) * QF_A_BYTES + (((r & 63) >> 4) * 16) * 128));
-            }
-            qbar_wait(acc_full, aphase);
-            aphase ^= 1;
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + cbase;
-            double sum = 0.0;
-            uint32_t hi[2][16], lo[2][16];
-            XG_TMEM_LD16(hi[0], trow);
-            XG_TMEM_LD16(lo[0], trow + 256);
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
-                if (c + 1 < 8) {      // next 16 rows in flight while these are reduced
-                    XG_TMEM_LD16(hi[(c + 1) & 1], trow + 16 * (c + 1));
-                    XG_TMEM_LD16(lo[(c + 1) & 1], trow + 256 + 16 * (c + 1));
-                }
-                const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int x = (int)(int8_t)((xw[j >> 2] >> (8 * (j & 3))) & 0xff);
-                    // planes combined exactly in int64 (|hi*256 + lo| < 2^40, times |x| <= 127), then to FP64 without I2F
-                    // (int->double conversions run at 16/clk/SM and were the epilogue's bottleneck): 2^52 + 2^51 + v has v in
-                    // its mantissa, one DADD removes the bias.
-                    const long long cx = ((long long)(int)hi[c & 1][j] * 256 + (long long)(int)lo[c & 1][j]) * x;
+                    for (int j = 0; j < 16; j++) cx32 += (int)acc[c & 1][j] * sext_byte(xw[j >> 2], j & 3);
+                    const long long cx = cx32;
                     const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
-                    sum = fma(d, rs[16 * c + j], sum);
+                    sum = fma(d, rs[16 * c], sum);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) qbar_arrive(acc_empty);
             const int64_t snp = (int64_t)J * 128 + snp_l;
-            if (live_tile && snp < g.nsnp) g.part[(((int64_t)I * g.QG + qg) * 2 + half) * g.nsnp + snp] = sum * g.group_scale[qg];
+            if (live && snp < g.nsnp) g.part[((int64_t)I * g.Q + q) * g.nsnp + snp] = sum * g.plane_scale[q];
         }
     }
     __syncthreads();
-    cluster_sync_all();      // no CTA exits while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
-
 
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
     static bool configured = false;
-    static int max_clusters = 0;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qf_i8_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(qf): %s", cudaGetErrorString(e)); return -3; }
-        // how many 2-CTA clusters can be co-resident (one CTA per SM)
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(QF_THREADS); cfg.dynamicSmemBytes = QF_SMEM;
-        cudaLaunchAttribute attr{};
-        attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, qf_i8_mc_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = num_sms / 2; }
-        if (max_clusters > num_sms / 2) max_clusters = num_sms / 2;
         configured = true;
     }
     if (g.n_items <= 0) return 0;
-    const int64_t n_pair_items = (int64_t)g.T256 * g.QG * ((g.NJ + 1) / 2);
-    if (g.use_cluster && max_clusters > 0 && g.NJ >= 2) {
-        const int64_t ncl = n_pair_items < max_clusters ? n_pair_items : max_clusters;
-        qf_i8_mc_kernel<<<(unsigned)(2 * ncl), QF_THREADS, QF_SMEM, st>>>(g);
-    } else {
-        const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
-        qf_i8_kernel<<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
-    }
+    // the epilogue reduces 16 rows in s32: 16 * (128 * n_pad * xmax) * xmax with xmax = 2 must stay below 2^31
+    if ((int64_t)g.NKB * QF_KB * 16 * 128 * 4 >= ((int64_t)1 << 31)) { set_error("qf: n too large for the s32 chunk reduction"); return -1; }
+    const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
+    qf_i8_kernel<<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("qf launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
 }
-int qf_max_clusters() { return 0; }
 
 // ------------------------------------------------------------------------------------------------
 // K1q: packed 2-bit hard calls -> int8 tile in the UMMA canonical K-major layout (A operand of K2q)

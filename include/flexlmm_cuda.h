@@ -35,8 +35,7 @@ extern "C" {
 /* flx_config.flags */
 #define FLX_FLAG_NO_INT8   1  /* never use the exact int8 tensor-core path for x' V^-1 x (K2q); always whiten in FP64 (K2) */
 #define FLX_FLAG_PLANES_5   4  /* int8 route with 5 digit planes (40 bits, ~1e-12 relative in x'V^-1x) instead of 6 (48 bits, ~4e-15)        */
-#define FLX_FLAG_CLUSTER_MULTICAST 2 /* K2q as 2-CTA clusters that multicast the digit-plane blocks (measured: no gain, the kernel is
-                                         bound by per-SM operand ingest latency, not by L2 bandwidth; kept as a diagnostic)          */
+
 
 #define FLX_MAX_K   24   /* design columns of the real model (k)            */
 #define FLX_MAX_S    8   /* SNP-dependent design columns (s)                */
