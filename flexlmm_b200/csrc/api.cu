@@ -126,8 +126,18 @@ struct flx_handle {
     // int8 quadratic-form path (K2q)
     bool fast = false;
     int Q = 6, T256 = 0, NKB = 0, crpH = 4;
-    DevBuf<int8_t> T8, X8, GA8, GB8;
-    DevBuf<double> rowscale, qf_part, GA_scale, GB_scale;
+    // every SNP term is g_t(x) * c_t[sample] with an integer triple g_t (|g| <= 2, "alpha") and a per-sample scale c_t ("group")
+    struct QfPass { int mat, amma, ndot, adot[2], slot[2]; };
+    struct FastPlan {
+        int NG = 0, NA = 0, nslots = 0;
+        int grp[8]{}, alp[8]{};
+        int aval[2][3]{};
+        bool ones[2]{};                 // group scale is identically 1
+        std::vector<QfPass> passes;     // one K2q launch each
+        int8_t slot_a[8][8]{}, slot_b[8][8]{};
+    } plan;
+    DevBuf<int8_t> T8[4], X8, GA8[2], GB8[2];      // T8[a * NG + b]: digit planes of tril(C_a V^-1 C_b)
+    DevBuf<double> rowscale[4], qf_part, GA_scale[2], GB_scale[2], cvec_d, bst;
     int NB_A = 16, NB_B = 16, ntilesB = 0;
     DevBuf<int32_t> refit_flag, out_map_d;
     DevBuf<int> df_count, missing;
@@ -615,25 +625,101 @@ static int finalize_setup(flx_handle* h) {
     FLX_TRY(h->Qn.ensure(tmp.size()));
     FLX_CUDA_TRY(cudaMemcpy(h->Qn.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
 
-    // ---- int8 quadratic-form path (K2q): one SNP term whose values are small integers for every sample (x itself, I(x==1), ...)
+    // ---- int8 quadratic-form path (K2q / K4q): every SNP term must factor as g_t(x) * c_t[sample] with an integer triple
+    // |g_t| <= 2 (x itself, I(x==1), ...) and a per-sample scale c_t (1 for main effects, the covariate for x:cov).  Then
+    //   A_raw[t][v] = g_t' C_t V^-1 C_v g_v = g_t' T^(t,v) g_v + g_v' T^(v,t) g_t,   T^(a,b) = tril(C_a V^-1 C_b), half diagonal,
+    // each form an exact int8 contraction against the digit planes of a matrix prepared once per task.
     h->fast = false;
-    if (!(h->cfg.flags & FLX_FLAG_NO_INT8) && h->have_Z && h->s == 1 && (h->uniform_mask & 1u) && cr + 1 <= 24) {
-        bool ints = true;
-        for (int g = 0; g < 3; g++) ints = ints && (h->uni[0][g] == std::floor(h->uni[0][g])) && std::fabs(h->uni[0][g]) <= 2.0;
-        h->fast = ints;
+    flx_handle::FastPlan& pl = h->plan;
+    pl = flx_handle::FastPlan();
+    std::vector<std::vector<double>> cvecs;
+    if (!(h->cfg.flags & FLX_FLAG_NO_INT8) && h->have_Z && h->s <= 4 && cr + 1 <= 24) {
+        bool ok = true;
+        for (int t = 0; t < h->s && ok; t++) {
+            const double* src[3] = {h->M0.data() + (size_t)snp_cols[t] * n, h->M1.data() + (size_t)snp_cols[t] * n, h->M2.data() + (size_t)snp_cols[t] * n};
+            // the sample with the largest entry fixes the integer triple
+            int64_t ibest = 0; double vbest = 0.0;
+            for (int64_t i = 0; i < n; i++)
+                for (int g = 0; g < 3; g++) if (std::fabs(src[g][i]) > vbest) { vbest = std::fabs(src[g][i]); ibest = i; }
+            if (!(vbest > 0.0) || !std::isfinite(vbest)) { ok = false; break; }
+            int a[3] = {0, 0, 0};
+            bool found = false;
+            for (int mlt = 1; mlt <= 2 && !found; mlt++) {
+                bool ints = true;
+                for (int g = 0; g < 3; g++) {
+                    const double v = src[g][ibest] * mlt / vbest;
+                    if (v != std::floor(v)) ints = false; else a[g] = (int)v;
+                }
+                found = ints;
+            }
+            if (!found) { ok = false; break; }
+            int g0 = 0; while (g0 < 3 && a[g0] == 0) g0++;
+            if (a[g0] < 0) for (int g = 0; g < 3; g++) a[g] = -a[g];
+            int gs = 0; for (int g = 1; g < 3; g++) if (std::abs(a[g]) > std::abs(a[gs])) gs = g;
+            std::vector<double> c(n);
+            for (int64_t i = 0; i < n && ok; i++) {
+                c[i] = src[gs][i] / a[gs];                       // exact: a in {+-1, +-2}
+                for (int g = 0; g < 3; g++) if (src[g][i] != a[g] * c[i]) ok = false;
+            }
+            if (!ok) break;
+            int al = -1, gr = -1;
+            for (int q = 0; q < pl.NA; q++) if (pl.aval[q][0] == a[0] && pl.aval[q][1] == a[1] && pl.aval[q][2] == a[2]) al = q;
+            if (al < 0) { if (pl.NA == 2) { ok = false; break; } al = pl.NA++; for (int g = 0; g < 3; g++) pl.aval[al][g] = a[g]; }
+            for (int q = 0; q < pl.NG; q++) if (memcmp(cvecs[q].data(), c.data(), n * sizeof(double)) == 0) gr = q;
+            if (gr < 0) {
+                if (pl.NG == 2) { ok = false; break; }
+                gr = pl.NG++;
+                bool ones = true;
+                for (int64_t i = 0; i < n; i++) ones = ones && (c[i] == 1.0);
+                pl.ones[gr] = ones;
+                cvecs.push_back(std::move(c));
+            }
+            pl.alp[t] = al; pl.grp[t] = gr;
+        }
+        h->fast = ok;
     }
     if (h->fast) {
+        // passes: for every ordered group pair (a, b) and every triple used on the right (group b), one K2q launch whose
+        // epilogue dots with every triple used on the left (group a)
+        int slot_of[2][2][2][2];
+        memset(slot_of, -1, sizeof(slot_of));
+        bool used[2][2] = {{false, false}, {false, false}};
+        for (int t = 0; t < h->s; t++) used[pl.grp[t]][pl.alp[t]] = true;
+        for (int a = 0; a < pl.NG; a++)
+            for (int b = 0; b < pl.NG; b++)
+                for (int ar = 0; ar < pl.NA; ar++) {
+                    if (!used[b][ar]) continue;
+                    flx_handle::QfPass ps{};
+                    ps.mat = a * pl.NG + b; ps.amma = ar; ps.ndot = 0;
+                    for (int al = 0; al < pl.NA; al++)
+                        if (used[a][al]) { ps.adot[ps.ndot] = al; ps.slot[ps.ndot] = pl.nslots; slot_of[a][b][al][ar] = pl.nslots++; ps.ndot++; }
+                    pl.passes.push_back(ps);
+                }
+        for (int t = 0; t < h->s; t++)
+            for (int v = 0; v < h->s; v++) {
+                pl.slot_a[t][v] = (int8_t)slot_of[pl.grp[t]][pl.grp[v]][pl.alp[t]][pl.alp[v]];
+                pl.slot_b[t][v] = (int8_t)slot_of[pl.grp[v]][pl.grp[t]][pl.alp[v]][pl.alp[t]];
+            }
         const double one = 1.0, zero = 0.0;
         h->T256 = (int)((n + 255) / 256);
         h->NKB = h->T256 * 4;
         h->crpH = gram_padded_width(cr + 1);
-        // V^-1 = L^-T L^-1 (lower), digit planes of its lower triangle
+        std::vector<double> cpad((size_t)pl.NG * n_pad, 0.0);
+        for (int gq = 0; gq < pl.NG; gq++) memcpy(cpad.data() + (size_t)gq * n_pad, cvecs[gq].data(), n * sizeof(double));
+        FLX_TRY(h->cvec_d.ensure(cpad.size()));
+        FLX_CUDA_TRY(cudaMemcpy(h->cvec_d.p, cpad.data(), cpad.size() * sizeof(double), cudaMemcpyHostToDevice));
+        auto cptr = [&](int gq) -> const double* { return pl.ones[gq] ? nullptr : h->cvec_d.p + (size_t)gq * n_pad; };
+        // V^-1 = L^-T L^-1 (lower), digit planes of the lower triangle of C_a V^-1 C_b
         DevBuf<double> V;
         FLX_TRY(V.ensure((size_t)n * n));
         FLX_CUBLAS_TRY(cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, (int)n, (int)n, &one, h->Zdense.p, (int)n, &zero, V.p, (int)n));
-        FLX_TRY(h->rowscale.ensure((size_t)h->T256 * 256));
-        FLX_TRY(h->T8.ensure((size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384));
-        FLX_TRY(launch_qf_slice(V.p, n, n, h->T256, h->Q, h->rowscale.p, h->T8.p, h->stream));
+        for (int a = 0; a < pl.NG; a++)
+            for (int b = 0; b < pl.NG; b++) {
+                const int mi = a * pl.NG + b;
+                FLX_TRY(h->rowscale[mi].ensure((size_t)h->T256 * 256));
+                FLX_TRY(h->T8[mi].ensure((size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384));
+                FLX_TRY(launch_qf_slice(V.p, n, n, h->T256, h->Q, cptr(a), cptr(b), h->rowscale[mi].p, h->T8[mi].p, h->stream));
+            }
         // H = L^-T [Qc | r]  (n x (cr+1)), stored row-major padded like Qc
         std::vector<double> Hc((size_t)n * (cr + 1));
         memcpy(Hc.data(), Qc.data(), (size_t)n * cr * sizeof(double));
@@ -642,11 +728,13 @@ static int finalize_setup(flx_handle* h) {
         FLX_TRY(Hd.ensure(Hc.size()));
         FLX_CUDA_TRY(cudaMemcpyAsync(Hd.p, Hc.data(), Hc.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, cr + 1, &one, h->Zdense.p, (int)n, Hd.p, (int)n, Hd.p, (int)n));
-        // digit planes of H for K4q pass A (u = Qc' w, b = r' w)
+        // digit planes of C_g H for K4q pass A (u = Qc' w, b = r' w), one set per scale group
         h->NB_A = ((cr + 1 + 15) / 16) * 16;
-        FLX_TRY(h->GA_scale.ensure(h->NB_A));
-        FLX_TRY(h->GA8.ensure((size_t)h->NKB * h->Q * h->NB_A * 64));
-        FLX_TRY(launch_xg_slice(Hd.p, n, n, cr + 1, h->NB_A, 1, h->Q, h->NKB, h->GA_scale.p, h->GA8.p, h->stream));
+        for (int gq = 0; gq < pl.NG; gq++) {
+            FLX_TRY(h->GA_scale[gq].ensure(h->NB_A));
+            FLX_TRY(h->GA8[gq].ensure((size_t)h->NKB * h->Q * h->NB_A * 64));
+            FLX_TRY(launch_xg_slice(Hd.p, n, n, cr + 1, h->NB_A, 1, h->Q, h->NKB, cptr(gq), h->GA_scale[gq].p, h->GA8[gq].p, h->stream));
+        }
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
 
@@ -710,9 +798,12 @@ static int finalize_setup(flx_handle* h) {
             h->ntilesB = (P + 79) / 80;
             h->NB_B = (((P + h->ntilesB - 1) / h->ntilesB + 15) / 16) * 16;
             inv_len = std::max<int64_t>(inv_len, (int64_t)h->ntilesB * h->NB_B);
-            FLX_TRY(h->GB_scale.ensure((size_t)h->ntilesB * h->NB_B));
-            FLX_TRY(h->GB8.ensure((size_t)h->ntilesB * h->NKB * h->Q * h->NB_B * 64));
-            FLX_TRY(launch_xg_slice(UE.p, n, n_pad, P, h->NB_B, h->ntilesB, h->Q, h->NKB, h->GB_scale.p, h->GB8.p, h->stream));
+            for (int gq = 0; gq < h->plan.NG; gq++) {
+                FLX_TRY(h->GB_scale[gq].ensure((size_t)h->ntilesB * h->NB_B));
+                FLX_TRY(h->GB8[gq].ensure((size_t)h->ntilesB * h->NKB * h->Q * h->NB_B * 64));
+                FLX_TRY(launch_xg_slice(UE.p, n, n_pad, P, h->NB_B, h->ntilesB, h->Q, h->NKB, h->plan.ones[gq] ? nullptr : h->cvec_d.p + (size_t)gq * n_pad,
+                                        h->GB_scale[gq].p, h->GB8[gq].p, h->stream));
+            }
         }
         std::vector<double> rssf(P), rss0(P);
         FLX_CUDA_TRY(cudaMemcpyAsync(rssf.data(), rssf_d.p, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -746,7 +837,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                        double* X_out_dense, uint8_t* codes_out, bool use_fast = false, bool accumulate = false,
                        const int32_t* out_map_host = nullptr, int64_t M_total = 0) {
     if (M_total < M) M_total = M;
-    const TileShape ts = make_tile_shape(h->s);
+    TileShape ts = make_tile_shape(h->s);
+    if (use_fast) ts.snps = 128;          // int8 tiles hold 128 SNPs whatever the number of terms
     const int tiles_per_batch = h->cfg.batch_tiles > 0 ? h->cfg.batch_tiles : h->num_sms;
     const int64_t snps_per_batch = (int64_t)tiles_per_batch * ts.snps;
     const int64_t nbatch = (M + snps_per_batch - 1) / snps_per_batch;
@@ -764,12 +856,15 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         if (i > 0 && var_idx[i] != var_idx[i - 1] + 1) contiguous = false;
     }
     const size_t tile_elems = (size_t)h->KC * CHUNK;
-    FLX_TRY(h->X.ensure((size_t)tiles_per_batch * tile_elems));
+    if (!use_fast || decode_only) FLX_TRY(h->X.ensure((size_t)tiles_per_batch * tile_elems));
+    const size_t x8_stride = (size_t)tiles_per_batch * h->NKB * 8192;
+    const int64_t ldp = (int64_t)h->ntilesB * h->NB_B;
     if (!decode_only) {
         if (!use_fast) FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
         if (use_fast) {
-            FLX_TRY(h->X8.ensure((size_t)tiles_per_batch * h->NKB * 8192));
-            FLX_TRY(h->qf_part.ensure((size_t)h->T256 * h->Q * snps_per_batch));
+            FLX_TRY(h->X8.ensure(x8_stride * h->plan.NA));
+            FLX_TRY(h->qf_part.ensure((size_t)h->plan.nslots * h->T256 * h->Q * snps_per_batch));
+            if (do_perm && h->s > 1) FLX_TRY(h->bst.ensure((size_t)h->s * snps_per_batch * ldp));
             FLX_TRY(h->refit_flag.ensure(M_total));
         }
         FLX_TRY(h->n_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
@@ -875,11 +970,17 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         da.n_pad = h->n_pad; da.X = h->X.p; da.NJ = NJ; da.missing_flag = h->missing.p;
         da.codes_out = codes_out ? codes_d.p : nullptr;
         if (use_fast && !decode_only) {
-            FLX_TRY(launch_decode_i8(da, h->X8.p, NJ, h->NKB, h->stream));   // K1q: int8 tile for the i8 tensor pipe
+            // K1q: one int8 tile set per integer triple of the design (x itself, I(x==1), ...)
+            for (int al = 0; al < h->plan.NA; al++) {
+                for (int g = 0; g < 3; g++) da.uni[0][g] = (double)h->plan.aval[al][g];
+                FLX_TRY(launch_decode_i8(da, h->X8.p + al * x8_stride, NJ, h->NKB, h->stream));
+                h->stats.launches++;
+            }
+            memcpy(da.uni, h->uni, sizeof(da.uni));
         } else {
             FLX_TRY(launch_decode(da, h->stream));
+            h->stats.launches++;
         }
-        h->stats.launches++;
         if (!use_resident) FLX_CUDA_TRY(cudaEventRecord(h->ev_used[buf], h->stream));
         mark();  // [2] whiten start
         if (decode_only) {
@@ -912,35 +1013,44 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         ga.KS = (h->KC + ga.cps - 1) / ga.cps;
         ga.n_part = h->n_part.p; ga.u_part = h->u_part.p; ga.a_part = h->a_part.p; ga.b_part = h->b_part.p;
         if (use_fast) {
-            // K2q: the exact quadratic form x' V^-1 x on the i8 tensor pipe
-            QfArgs q{};
-            q.X8 = h->X8.p; q.T8 = h->T8.p; q.rowscale = h->rowscale.p; q.part = h->qf_part.p;
-            for (int i = 0; i < 8; i++) q.plane_scale[i] = std::ldexp(1.0, -8 * (i + 1));
-            q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.Q = h->Q; q.NKB = h->NKB;
-            q.NKB_live = (int)((h->n + 63) / 64);
-            q.n_items = (int64_t)h->T256 * h->Q * ((NJ + 1) / 2);
-            DevBuf<long long> prof_d;
-            const bool prof = h->cfg.verbose >= 2 && bi == 0;
-            if (prof) { FLX_TRY(prof_d.ensure(4 * (size_t)h->num_sms)); q.prof = prof_d.p; }
-            FLX_TRY(launch_qf(q, h->num_sms, h->stream));
-            if (prof) {
-                std::vector<long long> pv(4 * (size_t)h->num_sms);
-                FLX_CUDA_TRY(cudaMemcpy(pv.data(), prof_d.p, pv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                for (int i = 0; i < h->num_sms; i++) { a0 += pv[4 * i]; a1 += pv[4 * i + 1]; a2 += pv[4 * i + 2]; a3 += pv[4 * i + 3]; }
-                fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA (%.1f%% in the first ring of an item), items/CTA %.1f\n",
-                        a0 / h->num_sms, 100 * a1 / a0, 100 * a2 / a0, 100 * a3 / a0, (double)q.n_items / h->num_sms);
+            // K2q: the exact forms g' C_a V^-1 C_b g' on the i8 tensor pipe, one launch per pass of the plan
+            const int nkb_live = (int)((h->n + 63) / 64);
+            const int64_t nparts = (int64_t)h->T256 * h->Q;
+            for (size_t pi = 0; pi < h->plan.passes.size(); pi++) {
+                const flx_handle::QfPass& ps = h->plan.passes[pi];
+                QfArgs q{};
+                q.X8 = h->X8.p + ps.amma * x8_stride; q.T8 = h->T8[ps.mat].p; q.rowscale = h->rowscale[ps.mat].p;
+                q.ndot = ps.ndot;
+                for (int d = 0; d < ps.ndot; d++) { q.Xd[d] = h->X8.p + ps.adot[d] * x8_stride; q.part[d] = h->qf_part.p + (int64_t)ps.slot[d] * nparts * nsnp; }
+                for (int i = 0; i < 8; i++) q.plane_scale[i] = std::ldexp(1.0, -8 * (i + 1));
+                q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.Q = h->Q; q.NKB = h->NKB;
+                q.NKB_live = nkb_live;
+                q.n_items = (int64_t)h->T256 * h->Q * ((NJ + 1) / 2);
+                DevBuf<long long> prof_d;
+                const bool prof = h->cfg.verbose >= 2 && bi == 0 && pi == 0;
+                if (prof) { FLX_TRY(prof_d.ensure(4 * (size_t)h->num_sms)); q.prof = prof_d.p; }
+                FLX_TRY(launch_qf(q, h->num_sms, h->stream));
+                if (prof) {
+                    std::vector<long long> pv(4 * (size_t)h->num_sms);
+                    FLX_CUDA_TRY(cudaMemcpy(pv.data(), prof_d.p, pv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    for (int i = 0; i < h->num_sms; i++) { a0 += pv[4 * i]; a1 += pv[4 * i + 1]; a2 += pv[4 * i + 2]; a3 += pv[4 * i + 3]; }
+                    fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA (%.1f%% in the first ring of an item), items/CTA %.1f\n",
+                            a0 / h->num_sms, 100 * a1 / a0, 100 * a2 / a0, 100 * a3 / a0, (double)q.n_items / h->num_sms);
+                }
+                h->stats.launches += 1; h->stats.launches_whiten++;
             }
-            h->stats.launches += 1; h->stats.launches_whiten++;
             mark();  // [3] fit start
-            // K4q pass A: u = (L^-T Qc)' x, b = (L^-T r)' x against the digit planes of H
-            XgArgs xa{};
-            xa.X8 = h->X8.p; xa.G8 = h->GA8.p; xa.colscale = h->GA_scale.p;
-            for (int i = 0; i < 3; i++) xa.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-            xa.n_items = NJ; xa.NCT = 1; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_A; xa.NC = cr + 1; xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = q.NKB_live;
-            xa.out = h->u_part.p; xa.ld_out = h->NB_A;
-            FLX_TRY(launch_xg(xa, 0, h->num_sms, h->stream));
-            h->stats.launches += 1;
+            // K4q pass A per term: u_t = (C_t L^-T Qc)' g_t, b_t = (C_t L^-T r)' g_t against the digit planes of C_t H
+            for (int t = 0; t < h->s; t++) {
+                XgArgs xa{};
+                xa.X8 = h->X8.p + h->plan.alp[t] * x8_stride; xa.G8 = h->GA8[h->plan.grp[t]].p; xa.colscale = h->GA_scale[h->plan.grp[t]].p;
+                for (int i = 0; i < 3; i++) xa.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
+                xa.n_items = NJ; xa.NCT = 1; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_A; xa.NC = cr + 1; xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = nkb_live;
+                xa.out = h->u_part.p + (int64_t)t * h->NB_A; xa.ld_out = (int64_t)h->s * h->NB_A;
+                FLX_TRY(launch_xg(xa, 0, h->num_sms, h->stream));
+                h->stats.launches += 1;
+            }
             ga.KS = 1;
         } else {
             GemmArgs g{};
@@ -967,20 +1077,33 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         sa.df_count = h->df_count.p;
         sa.refit_thr = std::ldexp(1e-5, 8 * (6 - h->Q));   // the digit planes resolve 2^-8Q of x'V^-1x: keep ~9 digits of A
         sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * h->Q;
+        memcpy(sa.slot_a, h->plan.slot_a, sizeof(sa.slot_a)); memcpy(sa.slot_b, h->plan.slot_b, sizeof(sa.slot_b));
         sa.refit_flag = use_fast ? h->refit_flag.p + s0 : nullptr;
         FLX_TRY(launch_snp_solve(sa, h->stream));
         h->stats.launches += 1;
         mark();  // [4] perm start
         if (do_perm && use_fast) {
-            // K4q pass B: b* = x' (L^-T r*) for every seed on the i8 pipe, fused max-ratio epilogue
-            XgArgs xb{};
-            xb.X8 = h->X8.p; xb.G8 = h->GB8.p; xb.colscale = h->GB_scale.p;
-            for (int i = 0; i < 3; i++) xb.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-            xb.n_items = (int64_t)h->ntilesB * NJ; xb.NCT = h->ntilesB; xb.nsnp = nsnp; xb.NJ = NJ; xb.NB = h->NB_B; xb.NC = h->P; xb.Q = h->Q; xb.NKB = h->NKB;
-            xb.NKB_live = (int)((h->n + 63) / 64);
-            xb.snp_df = h->snp_df.p; xb.snp_sm = h->snp_sm.p; xb.perm_inv_rss = h->inv_rss.p; xb.perm_maxratio = h->maxratio.p;
-            FLX_TRY(launch_xg(xb, 1, h->num_sms, h->stream));
-            h->stats.launches++;
+            // K4q pass B: b*_t = g_t' (C_t L^-T r*) for every seed on the i8 pipe; one term: fused max-ratio epilogue,
+            // several terms: store b* per term, then one reduction pass forms b*' Sm b* / RSS_f
+            for (int t = 0; t < h->s; t++) {
+                XgArgs xb{};
+                xb.X8 = h->X8.p + h->plan.alp[t] * x8_stride; xb.G8 = h->GB8[h->plan.grp[t]].p; xb.colscale = h->GB_scale[h->plan.grp[t]].p;
+                for (int i = 0; i < 3; i++) xb.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
+                xb.n_items = (int64_t)h->ntilesB * NJ; xb.NCT = h->ntilesB; xb.nsnp = nsnp; xb.NJ = NJ; xb.NB = h->NB_B; xb.NC = h->P; xb.Q = h->Q; xb.NKB = h->NKB;
+                xb.NKB_live = (int)((h->n + 63) / 64);
+                xb.snp_df = h->snp_df.p; xb.snp_sm = h->snp_sm.p; xb.perm_inv_rss = h->inv_rss.p; xb.perm_maxratio = h->maxratio.p;
+                xb.out = h->bst.p + (int64_t)t * nsnp * ldp; xb.ld_out = ldp;
+                FLX_TRY(launch_xg(xb, h->s == 1 ? 1 : 0, h->num_sms, h->stream));
+                h->stats.launches++;
+            }
+            if (h->s > 1) {
+                PermReduceArgs pr{};
+                pr.bst = h->bst.p; pr.term_stride = nsnp * ldp; pr.ldp = ldp;
+                pr.snp_df = h->snp_df.p; pr.snp_sm = h->snp_sm.p; pr.perm_inv_rss = h->inv_rss.p; pr.perm_maxratio = h->maxratio.p;
+                pr.nsnp = nsnp; pr.P = h->P; pr.P_pad = h->P_pad; pr.s = h->s;
+                FLX_TRY(launch_perm_reduce(pr, h->stream));
+                h->stats.launches++;
+            }
         } else if (do_perm) {
             GemmArgs gp{};
             gp.A = h->W.p; gp.B = h->Rpk.p; gp.NJ = NJ; gp.NP = h->NP; gp.KC = h->KC; gp.n_items = (int64_t)NJ * h->NP;

@@ -29,11 +29,13 @@ int launch_perm_contract(const GemmArgs& g, int s, int num_sms, cudaStream_t st)
 
 // ---------------------------------------------------------------- K2q (qf.cu): x' V^-1 x on the int8 tensor cores
 struct QfArgs {
-    const int8_t* X8;         // [NJ][NKB][8 KB]  int8 genotype tiles (128 SNPs x 64 samples per block, UMMA canonical K-major)
+    const int8_t* X8;         // [NJ][NKB][8 KB]  int8 genotype tiles (128 SNPs x 64 samples per block, UMMA canonical K-major): MMA operand g'
+    const int8_t* Xd[2];      // tiles of the left vectors g of the forms g' T g' (same layout; Xd[0] == X8 for a plain quadratic form)
+    int ndot;                 // 1 or 2 left vectors per pass
     const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(V^-1) (half diagonal)
     const double* rowscale;   // [n_pad256] power-of-two scale of each row of T (one value per 16 consecutive rows)
     double plane_scale[8];    // 2^-8(q+1)
-    double* part;             // [T256][Q][nsnp] partial quadratic forms
+    double* part[2];          // per left vector: [T256][Q][nsnp] partial forms
     int64_t n_items;
     int64_t nsnp;
     int T256, NJ, Q;
@@ -59,8 +61,10 @@ struct XgArgs {
     const int32_t* snp_df; const double* snp_sm; const double* perm_inv_rss; double* perm_maxratio;
 };
 int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st);
-int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, double* colscale, int8_t* G8, cudaStream_t st);
-int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, double* rowscale, int8_t* T8, cudaStream_t st);
+// rowmul (optional, [n]): the planes are those of diag(rowmul) G
+int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul, double* colscale, int8_t* G8, cudaStream_t st);
+// ca, cb (optional, [n]): the planes are those of tril(diag(ca) V diag(cb)) with half diagonal
+int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st);
 int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 
 // ---------------------------------------------------------------- K1 (decode.cu)
@@ -127,10 +131,12 @@ struct SolveArgs {
     int32_t* snp_df; double* snp_sm;
     int* df_count;            // [9] run-wide count of SNPs per lrt_df (1..8)
     const int32_t* out_map;   // optional: run-wide output slot of batch SNP q (refit pass), else out_offset + q
-    // fast (int8 quadratic form) mode, s == 1: A_raw = 2 * sum of qf_nparts partials; u, b from the H sweep (u_part)
+    // fast (int8 quadratic form) mode: A_raw[t][v] = S[slot_a[t][v]] + S[slot_b[t][v]], S[slot] = sum of the qf_nparts partials
+    // of K2q pass `slot` (qf_part: [slot][qf_nparts][nsnp]); u, b from the K4q-A sweeps (u_part: [snp][s][crp], KS = 1)
     int fast;
-    double refit_thr;         // re-fit in FP64 when A <= refit_thr * A_raw
+    double refit_thr;         // re-fit in FP64 when a Cholesky pivot <= refit_thr * A_raw[t][t]
     const double* qf_part; int qf_nparts;
+    int8_t slot_a[8][8], slot_b[8][8];
     int32_t* refit_flag;      // [nsnp] set to 1 when the SNP must be re-fitted on the FP64 path (near-collinear with the constant columns)
 };
 int upload_fit_const(const FitConst& c);
@@ -162,6 +168,13 @@ int launch_scale_add_diag(double* V, int64_t n, int64_t ld, double a, double b, 
 // fill identity
 int launch_set_identity(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 // finalize min-p: minp[p] = min over df of pchisq_upper(N*(lrs0p[p] - log1p(-maxratio[df][p])), df)
+// int8 route, s > 1: bst [s][nsnp_ld][ldp] = b*_t(snp, perm) -> running max over SNPs of b*' Sm b* / RSS_f per (perm, df)
+struct PermReduceArgs {
+    const double* bst; int64_t term_stride; int64_t ldp;
+    const int32_t* snp_df; const double* snp_sm; const double* perm_inv_rss; double* perm_maxratio;
+    int64_t nsnp; int P; int64_t P_pad; int s;
+};
+int launch_perm_reduce(const PermReduceArgs& a, cudaStream_t st);
 int launch_minp_finalize(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp, cudaStream_t st);
 
 }  // namespace flx

@@ -81,6 +81,7 @@ __device__ __forceinline__ int sext_byte(uint32_t w, int b) {
     return (int)d;
 }
 
+template <int NDOT>
 __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
@@ -187,16 +188,21 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             const int q = rem / NJ2, JP = rem % NJ2;
             const int J = 2 * JP + t;
             const bool live = J < g.NJ;
-            // this SNP's own genotypes at the rows of the tile: k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
-            const int8_t* xa = g.X8 + ((int64_t)(live ? J : 0) * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
+            // the left vectors at the rows of the tile (for a plain quadratic form the SNP's own genotypes):
+            // k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
+            const int64_t xoff = ((int64_t)(live ? J : 0) * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
             const double* rs = g.rowscale + 256 * (int64_t)I;
-            uint4 xq[16];
+            uint4 xq[NDOT][16];
 #pragma unroll
-            for (int c = 0; c < 16; c++) xq[c] = __ldg(reinterpret_cast<const uint4*>(xa + (int64_t)(c >> 2) * QF_A_BYTES + ((c & 3) * 16) * 128));
+            for (int d = 0; d < NDOT; d++)
+#pragma unroll
+                for (int c = 0; c < 16; c++) xq[d][c] = __ldg(reinterpret_cast<const uint4*>(g.Xd[d] + xoff + (int64_t)(c >> 2) * QF_A_BYTES + ((c & 3) * 16) * 128));
             qbar_wait(acc_full, aphase);
             aphase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            double sum = 0.0;
+            double sum[NDOT];
+#pragma unroll
+            for (int d = 0; d < NDOT; d++) sum[d] = 0.0;
             if (live) {
                 const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
                 uint32_t acc[2][16];
@@ -205,23 +211,29 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                 for (int c = 0; c < 16; c++) {
                     asm volatile("tcgen05.wait::ld.sync.aligned;");
                     if (c + 1 < 16) XG_TMEM_LD16(acc[(c + 1) & 1], trow + 16 * (c + 1));     // next 16 rows in flight while these are reduced
-                    const uint32_t xw[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
                     // the 16 rows of a chunk share one power-of-two scale, so the chunk is reduced exactly in s32
                     // (|acc| <= 128 n |x|max, |x|max <= 2 on this route: launch_qf refuses n that could overflow) and
                     // converted once, without I2F (16/clk/SM): 2^52 + 2^51 + v has v in its mantissa, one DADD removes the bias.
-                    int cx32 = 0;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) cx32 += (int)acc[c & 1][j] * sext_byte(xw[j >> 2], j & 3);
-                    const long long cx = cx32;
-                    const double d = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
-                    sum = fma(d, rs[16 * c], sum);
+                    for (int d = 0; d < NDOT; d++) {
+                        const uint32_t xw[4] = {xq[d][c].x, xq[d][c].y, xq[d][c].z, xq[d][c].w};
+                        int cx32 = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) cx32 += (int)acc[c & 1][j] * sext_byte(xw[j >> 2], j & 3);
+                        const long long cx = cx32;
+                        const double dv = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
+                        sum[d] = fma(dv, rs[16 * c], sum[d]);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) qbar_arrive(acc_empty);
             const int64_t snp = (int64_t)J * 128 + snp_l;
-            if (live && snp < g.nsnp) g.part[((int64_t)I * g.Q + q) * g.nsnp + snp] = sum * g.plane_scale[q];
+            if (live && snp < g.nsnp) {
+#pragma unroll
+                for (int d = 0; d < NDOT; d++) g.part[d][((int64_t)I * g.Q + q) * g.nsnp + snp] = sum[d] * g.plane_scale[q];
+            }
         }
     }
     __syncthreads();
@@ -231,7 +243,8 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(qf_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(qf): %s", cudaGetErrorString(e)); return -3; }
         configured = true;
     }
@@ -239,7 +252,9 @@ int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
     // the epilogue reduces 16 rows in s32: 16 * (128 * n_pad * xmax) * xmax with xmax = 2 must stay below 2^31
     if ((int64_t)g.NKB * QF_KB * 16 * 128 * 4 >= ((int64_t)1 << 31)) { set_error("qf: n too large for the s32 chunk reduction"); return -1; }
     const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
-    qf_i8_kernel<<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
+    if (g.ndot == 1) qf_i8_kernel<1><<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
+    else if (g.ndot == 2) qf_i8_kernel<2><<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
+    else { set_error("qf: ndot must be 1 or 2"); return -1; }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("qf launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
@@ -310,28 +325,39 @@ int launch_decode_i8(const DecodeArgs& a, int8_t* X8, int NJ, int NKB, cudaStrea
 // setup: T = tril(V^-1) with half diagonal  ->  per-row power-of-two scale + Q balanced base-256 digit planes,
 //        packed as the B operand:  T8[row tile I][kb < 4(I+1)][plane q][k16 chunk 4][row group 32][8 rows][16 B]
 // ------------------------------------------------------------------------------------------------
-__global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int64_t ld, int64_t n_pad, double* __restrict__ rowscale) {
+// power-of-two scale of a group of values with largest magnitude m: the leading balanced base-256 digit of v / scale is
+// round(256 v / scale) and must fit int8, i.e. stay <= 127 — m / scale < 0.5 is NOT enough (it allows 128).
+__device__ __forceinline__ double digit_scale(double m) {
+    if (!(m > 0.0)) return 1.0;
+    int e = 0;
+    frexp(m, &e);                              // m = f * 2^e, f in [0.5, 1)
+    double sc = ldexp(1.0, e + 1);             // m / sc = f / 2 in [0.25, 0.5)
+    if (m * 256.0 > 127.0 * sc) sc *= 2.0;     // f > 127/128: one more bit of headroom
+    return sc;
+}
+
+__global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int64_t ld, int64_t n_pad, const double* __restrict__ ca,
+                                   const double* __restrict__ cb, double* __restrict__ rowscale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // grid covers n_pad exactly (multiple of 256)
     double m = 0.0;
     if (i < n) {
-        for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(V[i + j * ld]));
-        m = fmax(m, 0.5 * fabs(V[i + i * ld]));
+        const double ai = ca ? ca[i] : 1.0;
+        for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(ai * V[i + j * ld] * (cb ? cb[j] : 1.0)));
+        m = fmax(m, 0.5 * fabs(ai * V[i + i * ld] * (cb ? cb[i] : 1.0)));
     }
     // one scale per 16 consecutive rows (= one tcgen05.ld chunk of the K2q epilogue, which then reduces the chunk in int64)
     for (int off = 8; off >= 1; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-    // scale = 2^(e+1) with max < 2^e  =>  |T / scale| < 0.5
-    int e = 0;
-    if (m > 0.0) { frexp(m, &e); }            // m = f * 2^e, f in [0.5, 1)  =>  m < 2^e
-    if (i < n_pad) rowscale[i] = (m > 0.0) ? ldexp(1.0, e + 1) : 1.0;
+    if (i < n_pad) rowscale[i] = digit_scale(m);
 }
 
-__global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __restrict__ V, int64_t n, int64_t ld, const double* __restrict__ rowscale, int Q,
-                                                           int8_t* __restrict__ T8) {
+__global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __restrict__ V, int64_t n, int64_t ld, const double* __restrict__ ca,
+                                                           const double* __restrict__ cb, const double* __restrict__ rowscale, int Q, int8_t* __restrict__ T8) {
     const int I = blockIdx.y, kb = blockIdx.x;
     if (kb >= 4 * (I + 1)) return;
     const int rl = threadIdx.x;                         // row within the 256-row tile
     const int64_t i = (int64_t)I * 256 + rl;
     const double inv = (i < n) ? 1.0 / rowscale[i] : 0.0;
+    const double ai = (ca && i < n) ? ca[i] : 1.0;
     const double up = ldexp(1.0, 8 * Q);
     int8_t* blk = T8 + ((int64_t)2 * I * (I + 1) + kb) * Q * QF_B_BYTES;
     for (int ch = 0; ch < 4; ch++) {
@@ -340,7 +366,7 @@ __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __rest
         for (int b = 0; b < 16; b++) {
             const int64_t j = (int64_t)kb * QF_KB + ch * 16 + b;
             double t = 0.0;
-            if (i < n && j <= i) t = (j == i) ? 0.5 * V[i + j * ld] : V[i + j * ld];
+            if (i < n && j <= i) t = ((j == i) ? 0.5 : 1.0) * (ai * V[i + j * ld] * (cb ? cb[j] : 1.0));
             long long ri = __double2ll_rn(t * inv * up);
             for (int q = Q - 1; q >= 0; q--) {
                 const long long d = ((ri + 128) & 255) - 128;
@@ -355,10 +381,10 @@ __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __rest
     }
 }
 
-int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, double* rowscale, int8_t* T8, cudaStream_t st) {
+int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st) {
     const int64_t n_pad = (int64_t)T256 * 256;
-    qf_rowscale_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(V, n, ld, n_pad, rowscale);
-    qf_slice_pack_kernel<<<dim3((unsigned)(4 * T256), (unsigned)T256), 256, 0, st>>>(V, n, ld, rowscale, Q, T8);
+    qf_rowscale_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(V, n, ld, n_pad, ca, cb, rowscale);
+    qf_slice_pack_kernel<<<dim3((unsigned)(4 * T256), (unsigned)T256), 256, 0, st>>>(V, n, ld, ca, cb, rowscale, Q, T8);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("qf_slice launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
@@ -543,26 +569,25 @@ int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st) {
 
 // ---- setup: G (n x NC dense, column-major) -> per-column power-of-two scale + Q digit planes, packed per column block:
 //      G8[col block ct][kb][plane q][k16 chunk 4][col group NB/8][8 cols][16 B]
-__global__ void xg_colscale_kernel(const double* __restrict__ G, int64_t n, int64_t ld, int NC, int NC_pad, double* __restrict__ colscale) {
+__global__ void xg_colscale_kernel(const double* __restrict__ G, int64_t n, int64_t ld, int NC, int NC_pad, const double* __restrict__ rowmul,
+                                   double* __restrict__ colscale) {
     const int col = blockIdx.x;
     __shared__ double sh[8];
     double m = 0.0;
     if (col < NC)
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(G[i + (int64_t)col * ld]));
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(G[i + (int64_t)col * ld] * (rowmul ? rowmul[i] : 1.0)));
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmax(m, sh[w]);
-        int e = 0;
-        if (m > 0.0) frexp(m, &e);
-        colscale[col] = (m > 0.0) ? ldexp(1.0, e + 1) : 1.0;
+        colscale[col] = digit_scale(m);
     }
     (void)NC_pad;
 }
 
 __global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __restrict__ G, int64_t n, int64_t ld, int NC, int NB, int Q, int NKB,
-                                                           const double* __restrict__ colscale, int8_t* __restrict__ G8) {
+                                                           const double* __restrict__ rowmul, const double* __restrict__ colscale, int8_t* __restrict__ G8) {
     const int ct = blockIdx.y, kb = blockIdx.x;
     const int plane_bytes = NB * QF_KB;
     int8_t* blk = G8 + ((int64_t)ct * NKB + kb) * Q * plane_bytes;
@@ -576,7 +601,7 @@ __global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __rest
         for (int q = 0; q < 6; q++) w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
         for (int b = 0; b < 16; b++) {
             const int64_t k = (int64_t)kb * QF_KB + ch * 16 + b;
-            const double t = (col < NC && k < n) ? G[k + (int64_t)col * ld] : 0.0;
+            const double t = (col < NC && k < n) ? G[k + (int64_t)col * ld] * (rowmul ? rowmul[k] : 1.0) : 0.0;
             long long ri = __double2ll_rn(t * inv * up);
             for (int q = Q - 1; q >= 0; q--) {
                 const long long d = ((ri + 128) & 255) - 128;
@@ -592,9 +617,10 @@ __global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __rest
     }
 }
 
-int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, double* colscale, int8_t* G8, cudaStream_t st) {
-    xg_colscale_kernel<<<(unsigned)(NB * ntiles), 256, 0, st>>>(G, n, ld, NC, NB * ntiles, colscale);
-    xg_slice_pack_kernel<<<dim3((unsigned)NKB, (unsigned)ntiles), 256, 0, st>>>(G, n, ld, NC, NB, Q, NKB, colscale, G8);
+int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul, double* colscale, int8_t* G8,
+                    cudaStream_t st) {
+    xg_colscale_kernel<<<(unsigned)(NB * ntiles), 256, 0, st>>>(G, n, ld, NC, NB * ntiles, rowmul, colscale);
+    xg_slice_pack_kernel<<<dim3((unsigned)NKB, (unsigned)ntiles), 256, 0, st>>>(G, n, ld, NC, NB, Q, NKB, rowmul, colscale, G8);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("xg_slice launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;

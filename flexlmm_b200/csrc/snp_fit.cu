@@ -327,38 +327,37 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     bool alive[MAXS];
     bool refit = false;
     if (a.fast) {
-        // s == 1: A_raw = x' V^-1 x = 2 * sum of the int8 partials; u_j = h_j' x (columns 0..cr-1 of H), b = h_r' x (column cr)
-        double araw = 0.0;
-        {
-            // same fixed summation order, but eight loads in flight per thread (the serial version is latency bound)
-            const double* __restrict__ qp = a.qf_part + snp;
+        // A_raw[t][v] = g_t' V^-1 g_v from the int8 passes (K2q), u_t = (L^-T Qc)' g_t and b_t = (L^-T r)' g_t from K4q-A
+        double S[8];
+        int nslots = 0;
+        for (int t = 0; t < s; t++)
+            for (int v = t; v < s; v++) { nslots = max(nslots, (int)a.slot_a[t][v] + 1); nslots = max(nslots, (int)a.slot_b[t][v] + 1); }
+        for (int sl = 0; sl < nslots; sl++) {
+            // fixed summation order, eight loads in flight per thread (the serial version is latency bound)
+            const double* __restrict__ qp = a.qf_part + (int64_t)sl * a.qf_nparts * a.nsnp + snp;
+            double acc = 0.0;
             int p = 0;
             for (; p + 8 <= a.qf_nparts; p += 8) {
                 double v[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) v[e] = __ldg(qp + (int64_t)(p + e) * a.nsnp);
 #pragma unroll
-                for (int e = 0; e < 8; e++) araw += v[e];
+                for (int e = 0; e < 8; e++) acc += v[e];
             }
-            for (; p < a.qf_nparts; p++) araw += __ldg(qp + (int64_t)p * a.nsnp);
+            for (; p < a.qf_nparts; p++) acc += __ldg(qp + (int64_t)p * a.nsnp);
+            S[sl] = acc;
         }
-        araw *= 2.0;
-        double uu = 0.0, bsum = 0.0;
-        {
-            double acc[MAXK + 1];
-            for (int j = 0; j <= cr; j++) acc[j] = 0.0;
-            for (int p = 0; p < a.KS; p++) {
-                const double* __restrict__ up = a.u_part + ((int64_t)p * a.nsnp + snp) * a.crp;
-                for (int j = 0; j <= cr; j++) acc[j] += __ldg(up + j);
+        const double* __restrict__ ub = a.u_part + snp * s * a.crp;     // [t][crp]: u_t (cr values) then b_t
+        for (int t = 0; t < s; t++) {
+            bq[t] = __ldg(ub + t * a.crp + cr);
+            for (int v = t; v < s; v++) {
+                double uu = 0.0;
+                for (int j = 0; j < cr; j++) uu += __ldg(ub + t * a.crp + j) * __ldg(ub + v * a.crp + j);
+                const double araw = S[a.slot_a[t][v]] + S[a.slot_b[t][v]];
+                if (v == t) nrm2[t] = araw;
+                A[t][v] = A[v][t] = araw - uu;
             }
-            for (int j = 0; j < cr; j++) uu += acc[j] * acc[j];
-            bsum = acc[cr];
         }
-        nrm2[0] = araw;
-        A[0][0] = araw - uu;
-        bq[0] = bsum;
-        // the subtraction loses log2(A_raw / A) bits: hand near-collinear SNPs (monomorphic, ...) to the FP64 path
-        refit = !(A[0][0] > a.refit_thr * araw);
     } else {
         // partial sums of the sample splits, fixed order
         int q = 0;
@@ -375,12 +374,18 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             bq[t] = ab; nrm2[t] = an;
         }
     }
-    if (a.refit_flag) a.refit_flag[snp] = refit ? 1 : 0;
     // guarded Cholesky A = Rs' Rs in term order; a vanished pivot leaves a zero row (direction dropped)
     for (int l = 0; l < s; l++) {
         double d = A[l][l];
         for (int i = 0; i < l; i++) d -= Rs[i][l] * Rs[i][l];
         alive[l] = (d > 0.0) && (d > 1e-22 * nrm2[l]);
+        if (a.fast) {
+            // A_raw - U U' and the pivots lose log2(A_raw / d) bits of the 2^-48 the digit planes resolve: hand near-collinear
+            // SNPs (monomorphic, ...) to the FP64 path.  A term that DUPLICATES an earlier one (x and I(x==1) of a SNP without
+            // hom-alt calls) has bit-identical int8 sums, its pivot is rounding noise of the Cholesky itself: dropped here.
+            if (l > 0 && A[l][l] > a.refit_thr * nrm2[l] && d <= 1e-15 * A[l][l]) alive[l] = false;
+            else if (!(d > a.refit_thr * nrm2[l])) refit = true;
+        }
         for (int j = 0; j < s; j++) Rs[l][j] = 0.0;
         if (alive[l]) {
             const double rll = sqrt(d);
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             }
         }
     }
+    if (a.refit_flag) a.refit_flag[snp] = refit ? 1 : 0;
     // Mq: q = Rs^-T b as a linear map (lower triangular), qsr = Mq b
     for (int l = 0; l < s; l++) {
         for (int cidx = 0; cidx < s; cidx++) Mq[l][cidx] = 0.0;
@@ -587,6 +593,49 @@ int launch_snp_solve(const SolveArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // min-p finalisation: one thread per permutation
 // ------------------------------------------------------------------------------------------------
+// int8 route with s > 1 terms: K4q stores b*_t = g_t' (L^-T r*_p) per term; this pass forms b*' Sm b* / RSS_f per (SNP, permutation)
+// and keeps the running max over SNPs per (df, permutation).  HBM bound: one read of s * nsnp * P doubles.
+__global__ void __launch_bounds__(128) perm_reduce_kernel(const PermReduceArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.y * 64;
+    const int64_t q1 = min(q0 + 64, a.nsnp);
+    const int s = a.s, nsym = s * (s + 1) / 2;
+    __shared__ double sm_s[64][MAXS * (MAXS + 1) / 2];
+    __shared__ int df_s[64];
+    for (int e = threadIdx.x; e < 64; e += blockDim.x) df_s[e] = (q0 + e < q1) ? a.snp_df[q0 + e] : 0;
+    for (int e = threadIdx.x; e < 64 * nsym; e += blockDim.x) {
+        const int qi = e / nsym, c = e % nsym;
+        sm_s[qi][c] = (q0 + qi < q1) ? a.snp_sm[(q0 + qi) * nsym + c] : 0.0;
+    }
+    __syncthreads();
+    if (p >= a.P) return;
+    const double inv = a.perm_inv_rss[p];
+    double mx[MAXS];
+    for (int t = 0; t < s; t++) mx[t] = 0.0;
+    for (int64_t q = q0; q < q1; q++) {
+        const int df = df_s[q - q0];
+        if (df <= 0) continue;
+        double z[MAXS];
+        for (int t = 0; t < s; t++) z[t] = a.bst[(int64_t)t * a.term_stride + q * a.ldp + p];
+        double quad = 0.0;
+        int c = 0;
+        for (int t = 0; t < s; t++)
+            for (int u = t; u < s; u++) { quad += ((u == t) ? 1.0 : 2.0) * sm_s[q - q0][c] * z[t] * z[u]; c++; }
+        const double ratio = fmax(quad * inv, 0.0);
+        mx[df - 1] = fmax(mx[df - 1], ratio);
+    }
+    for (int t = 0; t < s; t++)
+        if (mx[t] > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&a.perm_maxratio[(int64_t)t * a.P_pad + p]), (unsigned long long)__double_as_longlong(mx[t]));
+}
+
+int launch_perm_reduce(const PermReduceArgs& a, cudaStream_t st) {
+    if (a.P <= 0 || a.nsnp <= 0) return 0;
+    perm_reduce_kernel<<<dim3((unsigned)((a.P + 127) / 128), (unsigned)((a.nsnp + 63) / 64)), 128, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("perm_reduce launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
 __global__ void minp_finalize_kernel(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;

@@ -420,11 +420,90 @@ def test_int8_path_for_an_indicator_term(fx, orc):
     compare(r8, oracle_run(orc, t, t["codes_raw"]))
 
 
-def test_int8_path_not_used_for_real_valued_terms(fx):
+def test_int8_path_not_used_for_non_separable_terms(fx, orc):
+    """A term that is not g(x) * c[sample] with an integer triple g (here exp(x * cov)) stays on the FP64 route."""
     from flexlmm_b200 import synth
-    t = synth.task(300, 50, model="domgxe", P=0, seed=1)
-    _, st = _run(fx, t, True, 50, perm=False)
+    n, M = 300, 50
+    t = synth.task(n, M, model="additive", P=0, seed=1)
+    cov = t["M0"][:, 2]
+    one = np.ones(n)
+    t["M0"], t["M1"], t["M2"] = (np.column_stack([one, np.exp(0.3 * v * cov), cov]) for v in (0.0, 1.0, 2.0))
+    r, st = _run(fx, t, True, M, perm=False)
     assert st["int8_path"] == 0
+    compare(r, oracle_run(orc, t, t["codes_raw"]))
+
+
+@pytest.mark.parametrize("n,M", [(300, 200), (1500, 700)])
+def test_int8_path_multi_term_model(fx, orc, n, M):
+    """y ~ x + I(x==1) + x:cov1 + cov1: three SNP terms, two integer triples, two per-sample scales -> six int8 passes.
+    Compared with the FP64 route (same numbers, other arithmetic) and with the oracle (per-SNP results and min-p)."""
+    from flexlmm_b200 import synth
+    t = synth.task(n, M, model="domgxe", P=5, seed=n + 1, effect=0.1)
+    r8, st8 = _run(fx, t, True, M)
+    r64, st64 = _run(fx, t, False, M)
+    assert st8["int8_path"] == 1 and st64["int8_path"] == 0
+    assert st8["refit_snps"] < M // 4
+    assert np.array_equal(r8["lrt_df"], r64["lrt_df"]) and np.array_equal(r8["pivot"], r64["pivot"])
+    np.testing.assert_allclose(r8["lrt_chisq"], r64["lrt_chisq"], rtol=1e-8, atol=1e-9)
+    assert_logp_close(r8["pval"], r64["pval"])
+    assert_logp_close(r8["min_pval"], r64["min_pval"])
+    if n <= 300:
+        compare(r8, oracle_run(orc, t, t["codes_raw"]))
+        want = np.array([oracle_run(orc, t, t["codes_raw"], seed=int(s))["min_pval"] for s in t["seeds"]])
+        assert_logp_close(r8["min_pval"], want)
+
+
+def test_int8_path_factor_interaction_and_rare_variants(fx, orc):
+    """The reference's test formula shape, y ~ x + I(x==1) + x:group + group with a two-level factor (indicator scale), on
+    SNPs many of which have no hom-alt call: there I(x==1) duplicates x exactly and is dropped by the rank rule WITHOUT a
+    trip through the FP64 refit."""
+    from flexlmm_b200 import synth
+    n, M = 420, 160
+    t = synth.task(n, M, model="additive", P=3, seed=12, effect=0.1)
+    rng = np.random.default_rng(9)
+    grp = (rng.random(n) < 0.4).astype(float)
+    c = t["codes_raw"].copy()
+    c[:80][c[:80] == 2] = 1                       # the first 80 SNPs carry no hom-alt genotype
+    c[5] = np.where(grp > 0, c[5], 0)             # x:group == x for this SNP: a second exact duplicate
+    t["packed"] = synth.pack_2bit(c)
+    one = np.ones(n)
+    t["M0"], t["M1"], t["M2"] = (np.column_stack([one, np.full(n, float(v)), np.full(n, float(v == 1)), v * grp, grp]) for v in (0, 1, 2))
+    Xn = np.column_stack([one, grp])
+    t["X_null"] = orc.forwardsolve(t["L"], Xn)
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    t["ll_null"], t["df_null"] = nm["ll"], nm["df"]
+    t["y_pred"], t["U1"], t["e_p"] = nm["y_pred"], nm["U1"], nm["e_p"]
+    r8, st8 = _run(fx, t, True, M)
+    assert st8["int8_path"] == 1
+    assert st8["refit_snps"] <= 8, st8["refit_snps"]
+    o = oracle_run(orc, t, c)
+    compare(r8, o)
+    assert (r8["lrt_df"][:80] <= 2).all()
+    want = np.array([oracle_run(orc, t, c, seed=int(s))["min_pval"] for s in t["seeds"]])
+    assert_logp_close(r8["min_pval"], want)
+
+
+def test_int8_digit_planes_when_the_leading_digit_would_be_128(fx, orc):
+    """Regression: a row (or column) whose largest entry has a mantissa above 127/128 needs one more bit of headroom in
+    its power-of-two scale, or its leading balanced digit is 128 and wraps.  V^-1 = diag(1 / sigma^2) is built so that
+    half of the rows sit exactly there."""
+    from flexlmm_b200 import synth
+    n, M = 330, 120
+    t = synth.task(n, M, model="additive", P=3, seed=17, effect=0.1)
+    y_raw = t["L"] @ t["y_mm"]; Xn_raw = t["L"] @ t["X_null"]
+    rng = np.random.default_rng(2)
+    target = np.where(rng.random(n) < 0.5, 0.9995, 0.7) * 2.0 ** rng.integers(-2, 3, n)     # wanted 0.5 * V^-1_ii
+    sigma = np.sqrt(0.5 / target)
+    t["L"] = np.diag(sigma)
+    t["y_mm"] = y_raw / sigma; t["X_null"] = Xn_raw / sigma[:, None]
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    t["ll_null"], t["df_null"] = nm["ll"], nm["df"]
+    t["y_pred"], t["U1"], t["e_p"] = nm["y_pred"], nm["U1"], nm["e_p"]
+    r8, st8 = _run(fx, t, True, M)
+    assert st8["int8_path"] == 1 and st8["refit_snps"] == 0
+    compare(r8, oracle_run(orc, t, t["codes_raw"]))
+    want = np.array([oracle_run(orc, t, t["codes_raw"], seed=int(s))["min_pval"] for s in t["seeds"]])
+    assert_logp_close(r8["min_pval"], want)
 
 
 def test_int8_path_at_larger_n(fx, orc):
