@@ -208,9 +208,10 @@ def stage_roofline(w, acc, steps, int8_path):
     raw = (n + 3) // 4
     if int8_path:
         put("K1q decode_i8", M * (raw + n256), "GB/s", acc["ms_decode"], hbm, "hbm")
-        put("K2q qf_i8 (x'V^-1x, 6 planes)", 6.0 * n * n * M, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
-        put("K4q-A + K3b (u, b, fit, LRT)", M * (n256 * 2.0), "GB/s", acc["ms_fit"], hbm, "hbm")
-        put("K4q-B perm contraction (6 planes)", 6.0 * 2 * n * P * M, "TFLOP/s", acc["ms_perm"], i8_peak()[0], "tensor(i8)")
+        passes = max(1, int(round(acc.get("int8_passes", steps) / steps)))
+        put("K2q qf_i8 (g'C V^-1 C g, 6 planes x %d passes)" % passes, 6.0 * n * n * M * passes, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
+        put("K4q-A + K3b (u, b, fit, LRT)", M * (n256 * 2.0) * s, "GB/s", acc["ms_fit"], hbm, "hbm")
+        put("K4q-B perm contraction (6 planes)", 6.0 * 2 * n * P * M * s, "TFLOP/s", acc["ms_perm"], i8_peak()[0], "tensor(i8)")
     else:
         put("K1 decode_2bit_tile", M * (raw + 8.0 * n128 * s), "GB/s", acc["ms_decode"], hbm, "hbm")
         put("K2 whiten_tile (DMMA)", float(s) * n * n * M, "TFLOP/s", acc["ms_whiten"], fp64_peak()[0], "tensor(f64)")
@@ -338,8 +339,9 @@ def main():
         if int8_path:
             # K2q: Q = 6 digit planes x n(n+1)/2 int8 MACs per SNP (2 ops per MAC), on the i8 tensor pipe
             peak, peak_src = i8_peak()
-            work = 6.0 * n * n * w["M"] * a.steps
-            kname = "qf_i8_kernel (K2q: x'V^-1x, tcgen05.mma kind::i8, 6 exact digit planes)"
+            passes = max(1, int(round(acc.get("int8_passes", a.steps) / a.steps)))
+            work = 6.0 * n * n * w["M"] * a.steps * passes
+            kname = "qf_i8_kernel (K2q: g'C V^-1 C g, tcgen05.mma kind::i8, 6 exact digit planes, %d pass%s per batch)" % (passes, "" if passes == 1 else "es")
             tfile = "qf_traffic.json"
         else:
             peak, peak_src = fp64_peak()

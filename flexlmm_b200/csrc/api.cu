@@ -1150,6 +1150,7 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
     if (M > 0) {
         const bool fast = h->fast;
         h->stats.int8_path = fast ? 1 : 0;
+        h->stats.int8_passes = fast ? (int64_t)h->plan.passes.size() : 0;
         FLX_TRY(run_batches(h, var_idx, M, out != nullptr, do_perm, nullptr, nullptr, fast, false, nullptr, M));
         if (fast) {
             // SNPs whose x is (nearly) in the span of the constant columns lose digits in A = x'V^-1x - |u|^2: re-fit them in FP64

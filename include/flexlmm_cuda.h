@@ -33,7 +33,7 @@ extern "C" {
 #define FLX_ERR_NO_DEVICE        -8   /* no CUDA device: there is NO CPU fallback */
 
 /* flx_config.flags */
-#define FLX_FLAG_NO_INT8   1  /* never use the exact int8 tensor-core path for x' V^-1 x (K2q); always whiten in FP64 (K2) */
+#define FLX_FLAG_NO_INT8   1  /* never use the exact int8 tensor-core route (K2q/K4q); always whiten in FP64 (K2) */
 #define FLX_FLAG_PLANES_5   4  /* int8 route with 5 digit planes (40 bits, ~1e-12 relative in x'V^-1x) instead of 6 (48 bits, ~4e-15)        */
 
 
@@ -81,6 +81,7 @@ typedef struct {
     int64_t cols_per_tile;     /* design columns actually used per 128-wide tile                       */
     int64_t int8_path;         /* 1: the batches ran K2q (int8 tensor cores), 0: K2 (FP64 DMMA)        */
     int64_t refit_snps;        /* SNPs re-fitted on the FP64 path (near-collinear with constant columns)*/
+    int64_t int8_passes;       /* K2q launches per batch: 1 for one SNP term, 6 for x + I(x==1) + x:cov   */
 } flx_stats;
 
 const char* flx_last_error(void);
