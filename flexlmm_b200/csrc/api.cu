@@ -51,6 +51,7 @@ struct DevBuf {
     size_t cap = 0;
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void swap(DevBuf& o) { std::swap(p, o.p); std::swap(cap, o.cap); }
     int ensure(size_t count) {
         if (count <= cap && p) return 0;
         release();
@@ -237,24 +238,41 @@ extern "C" void flx_destroy(flx_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// L (or L^-1) dense on the device, n x n column-major with leading dimension n: build every whitening operand from it
-static int whitening_from_device(flx_handle* h, double* Ld, int64_t n, int is_inverse) {
+// src: L (or L^-1) dense on the device, n x n column-major with leading dimension n.  The buffer is CONSUMED: it becomes
+// h->Zdense and is inverted in place (cusolverDnXtrtri), so that the setup of n = 10^5 holds one dense matrix (80 GB), not two.
+static int whitening_from_device(flx_handle* h, DevBuf<double>& src, int64_t n, int is_inverse) {
     h->n = n;
     h->n_pad = (n + TJ - 1) / TJ * TJ;
     h->KC = (int)(h->n_pad / KCH);
     h->T = (int)(h->n_pad / TJ);
     h->dirty = true;
-    // dense L and L^-1 live on the device during setup (n <= ~45000 in this round)
-    FLX_TRY(h->Zdense.ensure((size_t)n * n));
+    h->Zdense.release();
+    h->Zdense.swap(src);
     if (!is_inverse) {
-        // Z = L^-1 by a triangular solve against the identity (setup only; library call outside the hot loop)
-        FLX_TRY(launch_set_identity(h->Zdense.p, n, n, h->stream));
-        const double one = 1.0;
-        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, (int)n, &one, Ld, (int)n, h->Zdense.p, (int)n));
-    } else {
-        FLX_CUDA_TRY(cudaMemcpyAsync(h->Zdense.p, Ld, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        FLX_TRY(launch_zero_upper(h->Zdense.p, n, n, h->stream));
+        // Z = L^-1 in place (setup only; library call outside the hot loop)
+        cusolverDnHandle_t cs = nullptr;
+        if (cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); return FLX_ERR_CUDA; }
+        cusolverDnSetStream(cs, h->stream);
+        size_t wdev = 0, whost = 0;
+        cusolverStatus_t st = cusolverDnXtrtri_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, n, CUDA_R_64F, h->Zdense.p, n, &wdev, &whost);
+        DevBuf<char> wbuf;
+        DevBuf<int> info_d;
+        std::vector<char> hbuf(whost + 1);
+        int rc = 0, info = 0;
+        if (st == CUSOLVER_STATUS_SUCCESS) rc = wbuf.ensure(wdev + 1);
+        if (st == CUSOLVER_STATUS_SUCCESS && rc == 0) rc = info_d.ensure(1);
+        if (st == CUSOLVER_STATUS_SUCCESS && rc == 0)
+            st = cusolverDnXtrtri(cs, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, n, CUDA_R_64F, h->Zdense.p, n, wbuf.p, wdev, hbuf.data(), whost, info_d.p);
+        if (st == CUSOLVER_STATUS_SUCCESS && rc == 0) {
+            cudaMemcpyAsync(&info, info_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+            cudaStreamSynchronize(h->stream);
+        }
+        cusolverDnDestroy(cs);
+        if (rc) return rc;
+        if (st != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnXtrtri failed: cusolver status %d", (int)st); return FLX_ERR_CUDA; }
+        if (info != 0) { set_error("flx_set_whitening: L is singular (zero on the diagonal at %d)", info); return FLX_ERR_BAD_ARG; }
     }
+    FLX_TRY(launch_zero_upper(h->Zdense.p, n, n, h->stream));      // the strict upper triangle of the caller's matrix may carry anything
     h->have_Z = true;
     FLX_TRY(h->linv.ensure((size_t)tri_chunks_before(h->T) * CHUNK));
     FLX_TRY(launch_pack_tri(h->Zdense.p, n, n, h->T, h->linv.p, h->stream));
@@ -265,10 +283,11 @@ static int whitening_from_device(flx_handle* h, double* Ld, int64_t n, int is_in
 extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse) {
     if (!h || !L || n <= 0 || ld < n) { set_error("flx_set_whitening: bad arguments"); return FLX_ERR_BAD_ARG; }
     FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->Zdense.release(); h->have_Z = false;
     DevBuf<double> Ld;
     FLX_TRY(Ld.ensure((size_t)n * n));
     FLX_CUDA_TRY(cudaMemcpy2DAsync(Ld.p, n * sizeof(double), L, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
-    return whitening_from_device(h, Ld.p, n, is_inverse);
+    return whitening_from_device(h, Ld, n, is_inverse);
 }
 
 #define FLX_CUSOLVER_TRY(expr)                                                             \
@@ -328,9 +347,9 @@ extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double
         FLX_CUDA_TRY(cudaMemcpyAsync(lam.p, lh.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         // V <- U diag(|lambda|) U'
         FLX_CUDA_TRY(cudaMemcpyAsync(U.p, V.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        FLX_CUBLAS_TRY(cublasDdgmm(h->cublas, CUBLAS_SIDE_RIGHT, (int)n, (int)n, U.p, (int)n, lam.p, 1, T2.p, (int)n));
+        FLX_CUBLAS_TRY(cublasDdgmm_64(h->cublas, CUBLAS_SIDE_RIGHT, (int)n, (int)n, U.p, (int)n, lam.p, 1, T2.p, (int)n));
         const double one = 1.0, zero = 0.0;
-        FLX_CUBLAS_TRY(cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)n, (int)n, &one, T2.p, (int)n, U.p, (int)n, &zero, V.p, (int)n));
+        FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)n, (int)n, &one, T2.p, (int)n, U.p, (int)n, &zero, V.p, (int)n));
         FLX_CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, &lwork));
         FLX_TRY(work.ensure((size_t)lwork));
         FLX_CUSOLVER_TRY(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, work.p, lwork, info_d.p));
@@ -350,13 +369,13 @@ extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double
         if (y) FLX_CUDA_TRY(cudaMemcpyAsync(B.p, y, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         if (c > 0) FLX_CUDA_TRY(cudaMemcpyAsync(B.p + (y ? n : 0), X, (size_t)n * c * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         const double one = 1.0;
-        FLX_CUBLAS_TRY(cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, nrhs, &one, V.p, (int)n, B.p, (int)n));
+        FLX_CUBLAS_TRY(cublasDtrsm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)n, nrhs, &one, V.p, (int)n, B.p, (int)n));
         if (y && y_mm_out) FLX_CUDA_TRY(cudaMemcpyAsync(y_mm_out, B.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (c > 0 && X_mm_out) FLX_CUDA_TRY(cudaMemcpyAsync(X_mm_out, B.p + (y ? n : 0), (size_t)n * c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     if (L_out) FLX_CUDA_TRY(cudaMemcpyAsync(L_out, V.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return whitening_from_device(h, V.p, n, 0);
+    return whitening_from_device(h, V, n, 0);
 }
 
 extern "C" int flx_set_null(flx_handle* h, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null) {
@@ -709,17 +728,6 @@ static int finalize_setup(flx_handle* h) {
         FLX_TRY(h->cvec_d.ensure(cpad.size()));
         FLX_CUDA_TRY(cudaMemcpy(h->cvec_d.p, cpad.data(), cpad.size() * sizeof(double), cudaMemcpyHostToDevice));
         auto cptr = [&](int gq) -> const double* { return pl.ones[gq] ? nullptr : h->cvec_d.p + (size_t)gq * n_pad; };
-        // V^-1 = L^-T L^-1 (lower), digit planes of the lower triangle of C_a V^-1 C_b
-        DevBuf<double> V;
-        FLX_TRY(V.ensure((size_t)n * n));
-        FLX_CUBLAS_TRY(cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, (int)n, (int)n, &one, h->Zdense.p, (int)n, &zero, V.p, (int)n));
-        for (int a = 0; a < pl.NG; a++)
-            for (int b = 0; b < pl.NG; b++) {
-                const int mi = a * pl.NG + b;
-                FLX_TRY(h->rowscale[mi].ensure((size_t)h->T256 * 256));
-                FLX_TRY(h->T8[mi].ensure((size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384));
-                FLX_TRY(launch_qf_slice(V.p, n, n, h->T256, h->Q, cptr(a), cptr(b), h->rowscale[mi].p, h->T8[mi].p, h->stream));
-            }
         // H = L^-T [Qc | r]  (n x (cr+1)), stored row-major padded like Qc
         std::vector<double> Hc((size_t)n * (cr + 1));
         memcpy(Hc.data(), Qc.data(), (size_t)n * cr * sizeof(double));
@@ -727,7 +735,7 @@ static int finalize_setup(flx_handle* h) {
         DevBuf<double> Hd;
         FLX_TRY(Hd.ensure(Hc.size()));
         FLX_CUDA_TRY(cudaMemcpyAsync(Hd.p, Hc.data(), Hc.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, cr + 1, &one, h->Zdense.p, (int)n, Hd.p, (int)n, Hd.p, (int)n));
+        FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, cr + 1, &one, h->Zdense.p, (int)n, Hd.p, (int)n, Hd.p, (int)n));
         // digit planes of C_g H for K4q pass A (u = Qc' w, b = r' w), one set per scale group
         h->NB_A = ((cr + 1 + 15) / 16) * 16;
         for (int gq = 0; gq < pl.NG; gq++) {
@@ -783,7 +791,7 @@ static int finalize_setup(flx_handle* h) {
         } else {
             FLX_TRY(launch_gather_ep(ep_d.p, idx_d.p, m, P, E.p, h->stream));
             // U1 %*% sample(e.p) for every seed: one plain library GEMM (setup, outside the hot loop)
-            FLX_CUBLAS_TRY(cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, U1d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
+            FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, U1d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
         }
         PermPrepArgs pa{};
         pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.crp = gram_padded_width(cr); pa.Qn = h->Qn.p; pa.cn = h->cn; pa.cnp = gram_padded_width(h->cn);
@@ -794,7 +802,7 @@ static int finalize_setup(flx_handle* h) {
         int64_t inv_len = h->P_pad;
         if (h->fast) {
             // int8 path: the contraction runs against the raw genotypes, b* = x' (L^-T r*): digit planes of L^-T R_f
-            FLX_CUBLAS_TRY(cublasDtrmm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, P, &one, h->Zdense.p, (int)n, UE.p, (int)n_pad, UE.p, (int)n_pad));
+            FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, P, &one, h->Zdense.p, (int)n, UE.p, (int)n_pad, UE.p, (int)n_pad));
             h->ntilesB = (P + 79) / 80;
             h->NB_B = (((P + h->ntilesB - 1) / h->ntilesB + 15) / 16) * 16;
             inv_len = std::max<int64_t>(inv_len, (int64_t)h->ntilesB * h->NB_B);
@@ -821,6 +829,31 @@ static int finalize_setup(flx_handle* h) {
         FLX_CUDA_TRY(cudaMemcpy(h->inv_rss.p, inv.data(), inv_len * sizeof(double), cudaMemcpyHostToDevice));
         FLX_CUDA_TRY(cudaMemcpy(h->lrs0p.p, lr.data(), P * sizeof(double), cudaMemcpyHostToDevice));
         std::vector<double>().swap(h->U1_copy);
+    }
+    if (h->fast) {
+        // V^-1 = L^-T L^-1 one 256-row tile at a time (a plain library GEMM over the non-zero k range of the triangular
+        // factor), each tile cut into the digit planes of tril(C_a V^-1 C_b): no second dense n x n matrix at any n
+        const flx_handle::FastPlan& pl = h->plan;
+        const double one = 1.0, zero = 0.0;
+        DevBuf<double> Vt;
+        FLX_TRY(Vt.ensure((size_t)256 * n));
+        for (int mi = 0; mi < pl.NG * pl.NG; mi++) {
+            FLX_TRY(h->rowscale[mi].ensure((size_t)h->T256 * 256));
+            FLX_TRY(h->T8[mi].ensure((size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384));
+        }
+        for (int I = 0; I < h->T256; I++) {
+            const int64_t r0 = (int64_t)I * 256;
+            const int64_t m = std::min<int64_t>(256, n - r0), ncols = r0 + m, K = n - r0;
+            FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, m, ncols, K, &one, h->Zdense.p + r0 + r0 * n, n, h->Zdense.p + r0, n, &zero, Vt.p, 256));
+            for (int a = 0; a < pl.NG; a++)
+                for (int b = 0; b < pl.NG; b++) {
+                    const int mi = a * pl.NG + b;
+                    const double* ca = pl.ones[a] ? nullptr : h->cvec_d.p + (size_t)a * n_pad;
+                    const double* cb = pl.ones[b] ? nullptr : h->cvec_d.p + (size_t)b * n_pad;
+                    FLX_TRY(launch_qf_slice(Vt.p, n, 256, I, h->Q, ca, cb, h->rowscale[mi].p, h->T8[mi].p, h->stream));
+                }
+        }
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
     FLX_TRY(h->df_count.ensure(16));
     FLX_TRY(h->missing.ensure(1));

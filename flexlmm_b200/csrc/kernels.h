@@ -63,8 +63,9 @@ struct XgArgs {
 int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st);
 // rowmul (optional, [n]): the planes are those of diag(rowmul) G
 int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul, double* colscale, int8_t* G8, cudaStream_t st);
-// ca, cb (optional, [n]): the planes are those of tril(diag(ca) V diag(cb)) with half diagonal
-int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st);
+// Vtile: rows 256 I .. 256 I + 255 of V^-1 (column-major, ld), columns 0 .. row.  ca, cb (optional, [n]): the planes are those
+// of tril(diag(ca) V^-1 diag(cb)) with half diagonal
+int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st);
 int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 
 // ---------------------------------------------------------------- K1 (decode.cu)

@@ -336,23 +336,26 @@ __device__ __forceinline__ double digit_scale(double m) {
     return sc;
 }
 
-__global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int64_t ld, int64_t n_pad, const double* __restrict__ ca,
+// V: rows row0 .. row0+255 of V^-1 (column-major, leading dimension ld), columns 0 .. row
+__global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int64_t ld, int64_t row0, const double* __restrict__ ca,
                                    const double* __restrict__ cb, double* __restrict__ rowscale) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // grid covers n_pad exactly (multiple of 256)
+    const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // 256 threads in all: one per row of the tile
+    const int64_t i = row0 + il;
     double m = 0.0;
     if (i < n) {
         const double ai = ca ? ca[i] : 1.0;
-        for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(ai * V[i + j * ld] * (cb ? cb[j] : 1.0)));
-        m = fmax(m, 0.5 * fabs(ai * V[i + i * ld] * (cb ? cb[i] : 1.0)));
+        for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(ai * V[il + j * ld] * (cb ? cb[j] : 1.0)));
+        m = fmax(m, 0.5 * fabs(ai * V[il + i * ld] * (cb ? cb[i] : 1.0)));
     }
     // one scale per 16 consecutive rows (= one tcgen05.ld chunk of the K2q epilogue, which then reduces the chunk in int64)
     for (int off = 8; off >= 1; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (i < n_pad) rowscale[i] = digit_scale(m);
+    rowscale[i] = digit_scale(m);
 }
 
 __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __restrict__ V, int64_t n, int64_t ld, const double* __restrict__ ca,
-                                                           const double* __restrict__ cb, const double* __restrict__ rowscale, int Q, int8_t* __restrict__ T8) {
-    const int I = blockIdx.y, kb = blockIdx.x;
+                                                           const double* __restrict__ cb, const double* __restrict__ rowscale, int Q, int I,
+                                                           int8_t* __restrict__ T8) {
+    const int kb = blockIdx.x;
     if (kb >= 4 * (I + 1)) return;
     const int rl = threadIdx.x;                         // row within the 256-row tile
     const int64_t i = (int64_t)I * 256 + rl;
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __rest
         for (int b = 0; b < 16; b++) {
             const int64_t j = (int64_t)kb * QF_KB + ch * 16 + b;
             double t = 0.0;
-            if (i < n && j <= i) t = ((j == i) ? 0.5 : 1.0) * (ai * V[i + j * ld] * (cb ? cb[j] : 1.0));
+            if (i < n && j <= i) t = ((j == i) ? 0.5 : 1.0) * (ai * V[rl + j * ld] * (cb ? cb[j] : 1.0));
             long long ri = __double2ll_rn(t * inv * up);
             for (int q = Q - 1; q >= 0; q--) {
                 const long long d = ((ri + 128) & 255) - 128;
@@ -381,10 +384,9 @@ __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __rest
     }
 }
 
-int launch_qf_slice(const double* V, int64_t n, int64_t ld, int T256, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st) {
-    const int64_t n_pad = (int64_t)T256 * 256;
-    qf_rowscale_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(V, n, ld, n_pad, ca, cb, rowscale);
-    qf_slice_pack_kernel<<<dim3((unsigned)(4 * T256), (unsigned)T256), 256, 0, st>>>(V, n, ld, ca, cb, rowscale, Q, T8);
+int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st) {
+    qf_rowscale_kernel<<<2, 128, 0, st>>>(Vtile, n, ld, (int64_t)I * 256, ca, cb, rowscale);
+    qf_slice_pack_kernel<<<(unsigned)(4 * (I + 1)), 256, 0, st>>>(Vtile, n, ld, ca, cb, rowscale, Q, I, T8);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("qf_slice launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
