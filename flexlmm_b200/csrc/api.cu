@@ -249,28 +249,31 @@ static int whitening_from_device(flx_handle* h, DevBuf<double>& src, int64_t n, 
     h->Zdense.release();
     h->Zdense.swap(src);
     if (!is_inverse) {
-        // Z = L^-1 in place (setup only; library call outside the hot loop)
-        cusolverDnHandle_t cs = nullptr;
-        if (cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); return FLX_ERR_CUDA; }
-        cusolverDnSetStream(cs, h->stream);
-        size_t wdev = 0, whost = 0;
-        cusolverStatus_t st = cusolverDnXtrtri_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, n, CUDA_R_64F, h->Zdense.p, n, &wdev, &whost);
-        DevBuf<char> wbuf;
-        DevBuf<int> info_d;
-        std::vector<char> hbuf(whost + 1);
-        int rc = 0, info = 0;
-        if (st == CUSOLVER_STATUS_SUCCESS) rc = wbuf.ensure(wdev + 1);
-        if (st == CUSOLVER_STATUS_SUCCESS && rc == 0) rc = info_d.ensure(1);
-        if (st == CUSOLVER_STATUS_SUCCESS && rc == 0)
-            st = cusolverDnXtrtri(cs, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, n, CUDA_R_64F, h->Zdense.p, n, wbuf.p, wdev, hbuf.data(), whost, info_d.p);
-        if (st == CUSOLVER_STATUS_SUCCESS && rc == 0) {
-            cudaMemcpyAsync(&info, info_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-            cudaStreamSynchronize(h->stream);
+        // Z = L^-1 in place: LAPACK dtrtri's blocked lower-triangular sweep (last block column first) on plain library
+        // trmm / trsm calls — setup only, outside the hot loop.  (cusolverDnXtrtri refuses n = 10^5.)
+        std::vector<double> dg(n);
+        FLX_CUDA_TRY(cudaMemcpy2DAsync(dg.data(), sizeof(double), h->Zdense.p, (n + 1) * sizeof(double), sizeof(double), n, cudaMemcpyDeviceToHost, h->stream));
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int64_t i = 0; i < n; i++)
+            if (!(dg[i] != 0.0) || !std::isfinite(dg[i])) { set_error("flx_set_whitening: L is singular or not finite (diagonal entry %lld)", (long long)i + 1); return FLX_ERR_BAD_ARG; }
+        const int64_t nb = 1024;
+        const double one = 1.0, mone = -1.0;
+        DevBuf<double> Tb;
+        FLX_TRY(Tb.ensure((size_t)nb * nb));
+        double* A = h->Zdense.p;
+        for (int64_t j = ((n - 1) / nb) * nb; j >= 0; j -= nb) {
+            const int64_t jb = std::min(nb, n - j), rest = n - j - jb;
+            if (rest > 0) {
+                FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, rest, jb, &one,
+                                              A + (j + jb) + (j + jb) * n, n, A + (j + jb) + j * n, n, A + (j + jb) + j * n, n));
+                FLX_CUBLAS_TRY(cublasDtrsm_64(h->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, rest, jb, &mone,
+                                              A + j + j * n, n, A + (j + jb) + j * n, n));
+            }
+            // diagonal block: solve against the identity, copy the lower triangle back
+            FLX_TRY(launch_set_identity(Tb.p, jb, jb, h->stream));
+            FLX_CUBLAS_TRY(cublasDtrsm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, jb, jb, &one, A + j + j * n, n, Tb.p, jb));
+            FLX_CUDA_TRY(cudaMemcpy2DAsync(A + j + j * n, n * sizeof(double), Tb.p, jb * sizeof(double), jb * sizeof(double), jb, cudaMemcpyDeviceToDevice, h->stream));
         }
-        cusolverDnDestroy(cs);
-        if (rc) return rc;
-        if (st != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnXtrtri failed: cusolver status %d", (int)st); return FLX_ERR_CUDA; }
-        if (info != 0) { set_error("flx_set_whitening: L is singular (zero on the diagonal at %d)", info); return FLX_ERR_BAD_ARG; }
     }
     FLX_TRY(launch_zero_upper(h->Zdense.p, n, n, h->stream));      // the strict upper triangle of the caller's matrix may carry anything
     h->have_Z = true;
