@@ -84,6 +84,8 @@ struct flx_handle {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t d2h_stream = nullptr;   // per-batch result copies into pinned staging, overlapped with the next batch
+    cudaEvent_t ev_res = nullptr;
     cublasHandle_t cublas = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1;
@@ -166,6 +168,8 @@ struct flx_handle {
     // run-wide results
     DevBuf<double> chisq, pval, coef;
     DevBuf<int32_t> df, rank, pivot;
+    PinBuf<double> chisq_h, pval_h, coef_h;       // pinned staging of the per-SNP results
+    PinBuf<int32_t> df_h, rank_h, pivot_h;
 
     flx_stats stats{};
 
@@ -180,6 +184,8 @@ struct flx_handle {
         if (cublas) cublasDestroy(cublas);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (d2h_stream) cudaStreamDestroy(d2h_stream);
+        if (ev_res) cudaEventDestroy(ev_res);
     }
 };
 
@@ -215,7 +221,9 @@ extern "C" int flx_create(const flx_config* cfg, flx_handle** out) {
     }
     h->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_res, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete h;
         return FLX_ERR_CUDA;
@@ -911,6 +919,10 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         FLX_TRY(h->snp_df.ensure((size_t)snps_per_batch));
         FLX_TRY(h->chisq.ensure(M_total)); FLX_TRY(h->pval.ensure(M_total)); FLX_TRY(h->df.ensure(M_total)); FLX_TRY(h->rank.ensure(M_total));
         FLX_TRY(h->pivot.ensure((size_t)M_total * h->k)); FLX_TRY(h->coef.ensure((size_t)M_total * h->k));
+        if (want_results) {
+            FLX_TRY(h->chisq_h.ensure(M_total)); FLX_TRY(h->pval_h.ensure(M_total)); FLX_TRY(h->df_h.ensure(M_total)); FLX_TRY(h->rank_h.ensure(M_total));
+            FLX_TRY(h->pivot_h.ensure((size_t)M_total * h->k)); FLX_TRY(h->coef_h.ensure((size_t)M_total * h->k));
+        }
         if (out_map_host) {
             FLX_TRY(h->out_map_d.ensure(M));
             FLX_CUDA_TRY(cudaMemcpyAsync(h->out_map_d.p, out_map_host, M * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -1117,6 +1129,18 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         sa.refit_flag = use_fast ? h->refit_flag.p + s0 : nullptr;
         FLX_TRY(launch_snp_solve(sa, h->stream));
         h->stats.launches += 1;
+        if (want_results && !out_map_host) {
+            // this batch's per-SNP results go to pinned staging while the permutation pass and the next batch run
+            FLX_CUDA_TRY(cudaEventRecord(h->ev_res, h->stream));
+            FLX_CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_res, 0));
+            const size_t k = (size_t)h->k;
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->chisq_h.p + s0, h->chisq.p + s0, nsnp * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->pval_h.p + s0, h->pval.p + s0, nsnp * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->df_h.p + s0, h->df.p + s0, nsnp * sizeof(int32_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->rank_h.p + s0, h->rank.p + s0, nsnp * sizeof(int32_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->pivot_h.p + s0 * k, h->pivot.p + s0 * k, nsnp * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->coef_h.p + s0 * k, h->coef.p + s0 * k, nsnp * k * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+        }
         mark();  // [4] perm start
         if (do_perm && use_fast) {
             // K4q pass B: b*_t = g_t' (C_t L^-T r*) for every seed on the i8 pipe; one term: fused max-ratio epilogue,
@@ -1169,7 +1193,6 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         set_error("missing genotype (NA hard call) in tested variant var_idx[%d]=%d: the reference aborts on it (no imputation anywhere in the pipeline)", miss, var_idx[miss]);
         return FLX_ERR_MISSING_GENOTYPE;
     }
-    (void)want_results;
     return FLX_OK;
 }
 
@@ -1208,18 +1231,38 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, h->stream);
     if (out && M > 0) {
-        auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
-            if (!dst) return 0;
-            FLX_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
-            h->stats.d2h_bytes += (int64_t)bytes;
-            return 0;
+        const size_t k = (size_t)h->k;
+        if (h->stats.refit_snps > 0) {
+            // the FP64 refit pass rewrote scattered slots: fetch the arrays again
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->chisq_h.p, h->chisq.p, M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->pval_h.p, h->pval.p, M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->df_h.p, h->df.p, M * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->rank_h.p, h->rank.p, M * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->pivot_h.p, h->pivot.p, M * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaMemcpyAsync(h->coef_h.p, h->coef.p, M * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
+        // pinned staging -> the caller's arrays, a slice per host thread
+        struct Cp { void* dst; const void* src; size_t bytes; };
+        const Cp cps[6] = {{out->lrt_chisq, h->chisq_h.p, M * sizeof(double)}, {out->pval, h->pval_h.p, M * sizeof(double)},
+                           {out->lrt_df, h->df_h.p, M * sizeof(int32_t)},    {out->rank, h->rank_h.p, M * sizeof(int32_t)},
+                           {out->pivot, h->pivot_h.p, M * k * sizeof(int32_t)}, {out->coef, h->coef_h.p, M * k * sizeof(double)}};
+        const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 8u), M / 65536));
+        auto work = [&](unsigned ti) {
+            for (const Cp& c : cps) {
+                if (!c.dst) continue;
+                const size_t lo = c.bytes * ti / nt, hi = c.bytes * (ti + 1) / nt;
+                memcpy((char*)c.dst + lo, (const char*)c.src + lo, hi - lo);
+            }
         };
-        FLX_TRY(d2h(out->lrt_chisq, h->chisq.p, M * sizeof(double)));
-        FLX_TRY(d2h(out->pval, h->pval.p, M * sizeof(double)));
-        FLX_TRY(d2h(out->lrt_df, h->df.p, M * sizeof(int32_t)));
-        FLX_TRY(d2h(out->rank, h->rank.p, M * sizeof(int32_t)));
-        FLX_TRY(d2h(out->pivot, h->pivot.p, (size_t)M * h->k * sizeof(int32_t)));
-        FLX_TRY(d2h(out->coef, h->coef.p, (size_t)M * h->k * sizeof(double)));
+        if (nt == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned ti = 0; ti < nt; ti++) th.emplace_back(work, ti);
+            for (auto& x : th) x.join();
+        }
+        for (const Cp& c : cps) if (c.dst) h->stats.d2h_bytes += (int64_t)c.bytes;
     }
     int64_t nv = M;
     if (do_perm) {
