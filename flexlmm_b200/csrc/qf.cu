@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
 
-    // item -> (row tile I, digit plane q, SNP tile pair JP); long row tiles first
+    // item -> (row tile I, SNP tile pair JP, digit plane q), planes innermost: the Q CTAs that work on one tile pair at the same
+    // time stream the same A blocks, so a pair's genotype tiles come from HBM once per row tile, not once per plane (at
+    // n = 20,000 a batch's tiles, 383 MB, no longer fit L2); long row tiles first
     const int NJ2 = (g.NJ + 1) >> 1;
     const int per_I = NJ2 * g.Q;
     if (warp == 0) {
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
                 const int rem = (int)(item % per_I);
-                const int q = rem / NJ2, JP = rem % NJ2;
+                const int JP = rem / g.Q, q = rem % g.Q;
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;      // an odd tile count leaves the last pair a single tile
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             const long long t_begin = g.prof ? clock64() : 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
-                const int JP = (int)(item % per_I) % NJ2;
+                const int JP = (int)(item % per_I) / g.Q;
                 const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;
                 int nkb = 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             const int I = g.T256 - 1 - (int)(item / per_I);
             const int rem = (int)(item % per_I);
-            const int q = rem / NJ2, JP = rem % NJ2;
+            const int JP = rem / g.Q, q = rem % g.Q;
             const int J = 2 * JP + t;
             const bool live = J < g.NJ;
             // the left vectors at the rows of the tile (for a plain quadratic form the SNP's own genotypes):
