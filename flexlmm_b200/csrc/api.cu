@@ -845,6 +845,19 @@ static int finalize_setup(flx_handle* h) {
         // V^-1 = L^-T L^-1 one 256-row tile at a time (a plain library GEMM over the non-zero k range of the triangular
         // factor), each tile cut into the digit planes of tril(C_a V^-1 C_b): no second dense n x n matrix at any n
         const flx_handle::FastPlan& pl = h->plan;
+        // the plane sets must fit next to the dense inverse and the batch buffers; if they do not (two-scale models at
+        // n ~ 10^5), the task runs on the FP64 route instead of failing
+        size_t free_b = 0, total_b = 0;
+        FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t planes_b = (size_t)pl.NG * pl.NG * 2 * h->T256 * (h->T256 + 1) * h->Q * 16384;
+        const size_t batch_b = (size_t)h->num_sms * h->NKB * 8192 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);
+        if (planes_b + batch_b + (size_t)256 * n * 8 > free_b) {
+            if (h->cfg.verbose) fprintf(stderr, "[flx] int8 route needs %.1f GB of digit planes, %.1f GB free: using the FP64 route\n", planes_b / 1e9, free_b / 1e9);
+            h->fast = false;
+        }
+    }
+    if (h->fast) {
+        const flx_handle::FastPlan& pl = h->plan;
         const double one = 1.0, zero = 0.0;
         DevBuf<double> Vt;
         FLX_TRY(Vt.ensure((size_t)256 * n));
