@@ -850,7 +850,7 @@ static int finalize_setup(flx_handle* h) {
         size_t free_b = 0, total_b = 0;
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t planes_b = (size_t)pl.NG * pl.NG * 2 * h->T256 * (h->T256 + 1) * h->Q * 16384;
-        const size_t batch_b = (size_t)h->num_sms * h->NKB * 8192 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);
+        const size_t batch_b = (size_t)h->num_sms * h->NKB * 8192 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);   // one tile per SM at least
         if (planes_b + batch_b + (size_t)256 * n * 8 > free_b) {
             if (h->cfg.verbose) fprintf(stderr, "[flx] int8 route needs %.1f GB of digit planes, %.1f GB free: using the FP64 route\n", planes_b / 1e9, free_b / 1e9);
             h->fast = false;
@@ -896,7 +896,20 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     if (M_total < M) M_total = M;
     TileShape ts = make_tile_shape(h->s);
     if (use_fast) ts.snps = 128;          // int8 tiles hold 128 SNPs whatever the number of terms
-    const int tiles_per_batch = h->cfg.batch_tiles > 0 ? h->cfg.batch_tiles : h->num_sms;
+    // default batch: one column tile per SM on the FP64 route (the X / W tiles are 8 n_pad bytes per column); four on the int8
+    // route, where a tile is 128 n bytes and K1q / K3b / K4q want more SNPs in flight than one tile per SM (K2q is indifferent),
+    // capped so that the batch buffers stay below a quarter of the free memory
+    int tiles_per_batch = h->cfg.batch_tiles > 0 ? h->cfg.batch_tiles : h->num_sms;
+    if (h->cfg.batch_tiles <= 0 && use_fast) {
+        size_t free_b = 0, total_b = 0;
+        FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_tile = (size_t)h->plan.NA * h->NKB * 8192 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 +
+                                ((do_perm && h->s > 1) ? (size_t)h->s * 128 * h->ntilesB * h->NB_B * 8 : 0) + (size_t)128 * 40 * 8 * (h->s + 2);
+        const size_t have = free_b + h->X8.cap + h->qf_part.cap * 8 + h->bst.cap * 8;     // what this handle already holds is reusable
+        int mult = 4;
+        while (mult > 1 && (size_t)mult * h->num_sms * per_tile > have / 4) mult--;
+        tiles_per_batch = mult * h->num_sms;
+    }
     const int64_t snps_per_batch = (int64_t)tiles_per_batch * ts.snps;
     const int64_t nbatch = (M + snps_per_batch - 1) / snps_per_batch;
     const int64_t bpv = h->bpv;
