@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/flexlmm_cuda.h"
@@ -160,6 +161,8 @@ struct flx_handle {
     // batch buffers
     DevBuf<uint8_t> packed_d[2];
     PinBuf<uint8_t> staging[2];
+    DevBuf<uint8_t> blob_d[2], px_scratch[2];   // K0: compressed .pgen records of a batch + descriptors; rows of out-of-batch LD bases
+    DevBuf<int> px_err;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     cudaEvent_t ev_used[2] = {nullptr, nullptr};
     DevBuf<int32_t> vmap_d;
@@ -971,6 +974,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             FLX_TRY(h->staging[i].ensure((size_t)snps_per_batch * bpv));
         }
     const int int_max = INT_MAX;
+    FLX_TRY(h->px_err.ensure(1));
+    FLX_CUDA_TRY(cudaMemsetAsync(h->px_err.p, 0, sizeof(int), h->stream));
     if (!accumulate) {
         FLX_CUDA_TRY(cudaMemcpyAsync(h->missing.p, &int_max, sizeof(int), cudaMemcpyHostToDevice, h->stream));
         FLX_CUDA_TRY(cudaMemsetAsync(h->df_count.p, 0, 16 * sizeof(int), h->stream));
@@ -996,7 +1001,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         } else {
             // H2D on the copy stream so that the transfer of batch b+1 overlaps the kernels of batch b
             FLX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[buf], 0));   // the decode of batch b-2 has read this buffer
-            const uint8_t* src_ptr;
+            const uint8_t* src_ptr = nullptr;
+            bool expanded_on_device = false;
             if (h->src == 2 && contiguous && h->host_registered) {
                 src_ptr = h->packed_host + (size_t)(var_idx[s0] - 1) * bpv;          // pinned in place: no staging copy
             } else {
@@ -1005,34 +1011,86 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 if (h->src == 2) {
                     if (contiguous) memcpy(st, h->packed_host + (size_t)(var_idx[s0] - 1) * bpv, (size_t)nsnp * bpv);
                     else for (int64_t i = 0; i < nsnp; i++) memcpy(st + i * bpv, h->packed_host + (size_t)(var_idx[s0 + i] - 1) * bpv, bpv);
+                } else if (h->src == 1 && h->pgen->mode() == 0x02) {
+                    for (int64_t i = 0; i < nsnp; i++) memcpy(st + i * bpv, h->pgen->fixed_record((uint32_t)(var_idx[s0 + i] - 1)), bpv);
                 } else if (h->src == 1) {
-                    // host expansion of LD / difflist / 1-bit records to packed 2-bit, one slice of the batch per host thread
-                    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 32u), nsnp / 256));
-                    std::vector<std::string> errs(nt);
-                    std::vector<int64_t> err_at(nt, -1);
-                    auto work = [&](unsigned ti) {
-                        PgenFile::LdCache cache;
-                        const int64_t lo = nsnp * ti / nt, hi = nsnp * (ti + 1) / nt;
-                        for (int64_t i = lo; i < hi; i++) {
-                            std::string e = h->pgen->read_packed((uint32_t)(var_idx[s0 + i] - 1), st + i * bpv, cache);
-                            if (!e.empty()) { errs[ti] = e; err_at[ti] = i; return; }
-                        }
-                    };
-                    if (nt == 1) work(0);
-                    else {
-                        std::vector<std::thread> th;
-                        for (unsigned ti = 0; ti < nt; ti++) th.emplace_back(work, ti);
-                        for (auto& x : th) x.join();
+                    // K0: ship the COMPRESSED records (plus LD bases that are not part of the batch) and expand on the device
+                    struct Ent { uint64_t off; uint32_t len; uint8_t vt; int32_t base_row, out_row; };
+                    std::vector<Ent> ents((size_t)nsnp);
+                    std::unordered_map<uint32_t, int32_t> row_of;
+                    bool any_ld = false;
+                    for (int64_t i = 0; i < nsnp; i++) {
+                        const uint32_t v = (uint32_t)(var_idx[s0 + i] - 1);
+                        const PgenFile::RecInfo ri = h->pgen->rec_info(v);
+                        if (ri.vrtype & 0x08) { set_error("pgen variant %d: multiallelic record (the pipeline converts with --max-alleles 2)", var_idx[s0 + i]); return FLX_ERR_PGEN; }
+                        ents[i] = Ent{ri.off, ri.len, ri.vrtype, 0, (int32_t)i};
+                        if ((ri.vrtype & 6) != 2) row_of.emplace(v, (int32_t)i); else any_ld = true;
                     }
-                    for (unsigned ti = 0; ti < nt; ti++)
-                        if (err_at[ti] >= 0) { set_error("pgen variant %d: %s", var_idx[s0 + err_at[ti]], errs[ti].c_str()); return FLX_ERR_PGEN; }
+                    int32_t nbase = 0;
+                    if (any_ld)
+                        for (int64_t i = 0; i < nsnp; i++) {
+                            if ((ents[i].vt & 6) != 2) continue;
+                            const uint32_t b = h->pgen->rec_info((uint32_t)(var_idx[s0 + i] - 1)).ldbase;
+                            auto it = row_of.find(b);
+                            if (it == row_of.end()) {
+                                const PgenFile::RecInfo rb = h->pgen->rec_info(b);
+                                nbase++;
+                                ents.push_back(Ent{rb.off, rb.len, rb.vrtype, 0, -nbase});
+                                it = row_of.emplace(b, -nbase).first;
+                            }
+                            ents[i].base_row = it->second;
+                        }
+                    const size_t E = ents.size();
+                    std::vector<uint32_t> roff(E);
+                    size_t blob_bytes = 0;
+                    for (size_t e = 0; e < E; e++) { roff[e] = (uint32_t)blob_bytes; blob_bytes += ents[e].len; }
+                    if (blob_bytes >= ((size_t)1 << 32)) { set_error("pgen batch of %lld records exceeds 4 GB of compressed bytes: lower batch_tiles", (long long)nsnp); return FLX_ERR_BAD_ARG; }
+                    const size_t o_off = (blob_bytes + 15) / 16 * 16, o_len = o_off + 4 * E, o_base = o_len + 4 * E, o_out = o_base + 4 * E, o_vt = o_out + 4 * E;
+                    const size_t total = (o_vt + E + 15) / 16 * 16;
+                    FLX_TRY(h->staging[buf].ensure(total));
+                    st = h->staging[buf].p;
+                    {
+                        const uint8_t* file = h->pgen->data();
+                        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min(std::thread::hardware_concurrency(), 16u), E / 1024));
+                        auto work = [&](unsigned ti) {
+                            for (size_t e = E * ti / nt; e < E * (ti + 1) / nt; e++) memcpy(st + roff[e], file + ents[e].off, ents[e].len);
+                        };
+                        if (nt == 1) work(0);
+                        else {
+                            std::vector<std::thread> th;
+                            for (unsigned ti = 0; ti < nt; ti++) th.emplace_back(work, ti);
+                            for (auto& x : th) x.join();
+                        }
+                    }
+                    for (size_t e = 0; e < E; e++) {
+                        memcpy(st + o_off + 4 * e, &roff[e], 4); memcpy(st + o_len + 4 * e, &ents[e].len, 4);
+                        memcpy(st + o_base + 4 * e, &ents[e].base_row, 4); memcpy(st + o_out + 4 * e, &ents[e].out_row, 4);
+                        st[o_vt + e] = ents[e].vt;
+                    }
+                    FLX_TRY(h->blob_d[buf].ensure(total));
+                    FLX_TRY(h->px_scratch[buf].ensure((size_t)std::max(nbase, 1) * bpv));
+                    FLX_CUDA_TRY(cudaMemcpyAsync(h->blob_d[buf].p, st, total, cudaMemcpyHostToDevice, h->copy_stream));
+                    FLX_CUDA_TRY(cudaEventRecord(h->ev_h2d[buf], h->copy_stream));
+                    FLX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[buf], 0));
+                    h->stats.h2d_bytes += (int64_t)total;
+                    PgenExpandArgs px{};
+                    const uint8_t* bd = h->blob_d[buf].p;
+                    px.blob = bd; px.rec_off = reinterpret_cast<const uint32_t*>(bd + o_off); px.rec_len = reinterpret_cast<const uint32_t*>(bd + o_len);
+                    px.base_row = reinterpret_cast<const int32_t*>(bd + o_base); px.out_row = reinterpret_cast<const int32_t*>(bd + o_out); px.vrtype = bd + o_vt;
+                    px.E = (int)E; px.sample_ct = (uint32_t)h->raw_n; px.bpv = bpv; px.out = h->packed_d[buf].p; px.scratch = h->px_scratch[buf].p;
+                    px.err = h->px_err.p; px.any_ld = any_ld ? 1 : 0;
+                    FLX_TRY(launch_pgen_expand(px, h->stream));
+                    h->stats.launches += any_ld ? 2 : 1;
+                    expanded_on_device = true;
                 } else { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
                 src_ptr = st;
             }
-            FLX_CUDA_TRY(cudaMemcpyAsync(h->packed_d[buf].p, src_ptr, (size_t)nsnp * bpv, cudaMemcpyHostToDevice, h->copy_stream));
-            FLX_CUDA_TRY(cudaEventRecord(h->ev_h2d[buf], h->copy_stream));
-            FLX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[buf], 0));
-            h->stats.h2d_bytes += nsnp * bpv;
+            if (!expanded_on_device) {
+                FLX_CUDA_TRY(cudaMemcpyAsync(h->packed_d[buf].p, src_ptr, (size_t)nsnp * bpv, cudaMemcpyHostToDevice, h->copy_stream));
+                FLX_CUDA_TRY(cudaEventRecord(h->ev_h2d[buf], h->copy_stream));
+                FLX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[buf], 0));
+                h->stats.h2d_bytes += nsnp * bpv;
+            }
             packed_dev = h->packed_d[buf].p;
         }
         mark();  // [1] decode start
@@ -1213,6 +1271,13 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     }
     if (!evs.empty()) { float ms; cudaEventElapsedTime(&ms, evs.front(), evs.back()); h->stats.ms_total += ms; }
     for (auto e : evs) cudaEventDestroy(e);
+    int pxe = 0;
+    FLX_CUDA_TRY(cudaMemcpy(&pxe, h->px_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (pxe != 0) {
+        static const char* what[] = {"", "short raw record", "short 1-bit record", "bad difflist length", "truncated difflist", "bad difflist entry"};
+        set_error("pgen: malformed variant record (%s; record %d of its batch)", what[std::min(pxe & 15, 5)], pxe >> 4);
+        return FLX_ERR_PGEN;
+    }
     int miss = INT_MAX;
     FLX_CUDA_TRY(cudaMemcpy(&miss, h->missing.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (miss != INT_MAX && !decode_only) {

@@ -51,6 +51,10 @@ public:
     struct LdCache { int64_t base = -1; std::vector<uint8_t> geno; };
     std::string read_packed(uint32_t v, uint8_t* out, LdCache& cache) const;
     std::string read_packed(uint32_t v, uint8_t* out) { return read_packed(v, out, own_cache_); }
+    // mode 0x10: where variant v's record lives in the file, its type byte and the variant its LD compression refers to
+    struct RecInfo { uint64_t off; uint32_t len; uint8_t vrtype; uint32_t ldbase; };
+    RecInfo rec_info(uint32_t v) const { return RecInfo{recs_[v].off, recs_[v].len, recs_[v].vrtype, ldbase_[v]}; }
+    const uint8_t* data() const { return data_; }
 private:
     struct Rec { uint64_t off; uint32_t len; uint8_t vrtype; };
     std::string parse();

@@ -68,6 +68,21 @@ int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int 
 int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st);
 int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 
+// ---------------------------------------------------------------- K0 (pgen_expand.cu)
+// .pgen mode-0x10 records -> packed 2-bit rows.  Entry e: record bytes blob[rec_off[e] .. +rec_len[e]), vrtype[e]; row codes:
+// r >= 0 -> out + r * bpv, r < 0 -> scratch + (-r - 1) * bpv (LD bases that are not themselves part of the batch).
+struct PgenExpandArgs {
+    const uint8_t* blob; const uint32_t* rec_off; const uint32_t* rec_len; const uint8_t* vrtype;
+    const int32_t* base_row;  // row of the LD base (vrtype & 7 in {2, 3}), unused otherwise
+    const int32_t* out_row;
+    int E; uint32_t sample_ct; int64_t bpv;
+    uint8_t* out; uint8_t* scratch;
+    int* err;                 // 0, or (entry << 4) | code of the first malformed record
+    int any_ld;               // host hint: skip the second launch when no record is LD-compressed
+    int pass, row_words;      // set by the launcher
+};
+int launch_pgen_expand(const PgenExpandArgs& a, cudaStream_t st);
+
 // ---------------------------------------------------------------- K1 (decode.cu)
 struct DecodeArgs {
     const uint8_t* packed;    // device: 2-bit records of the batch's variants, record v at packed + v*bpv

@@ -636,8 +636,59 @@ def test_implicit_complement_permutations(fx, orc, model, int8):
     assert_logp_close(r_imp["min_pval"], want)
 
 
+def test_pgen_device_expansion_long_difflists_and_foreign_ld_bases(fx, tmp_path):
+    """K0 on records whose difflists span more than 32 groups of 64 entries (two rounds of the warp scan over the group byte
+    counts), requested as a shuffled subset so that most LD records refer to a base variant that is not part of the batch."""
+    from flexlmm_b200 import synth
+    from pgen_writer import write_pgen
+    rng = np.random.default_rng(31)
+    n_raw, M = 4100, 240
+    c = rng.integers(0, 3, size=(M, n_raw)).astype(np.uint8)
+    for v in range(1, M):
+        if v % 5:
+            c[v] = c[v - 1]
+            flip = rng.choice(n_raw, size=int(rng.integers(1, 200)), replace=False)
+            c[v, flip] = rng.integers(0, 4, size=flip.size)         # includes missing calls (code 3)
+    vt = [0] + [int(x) for x in rng.choice([1, 2, 2, 3, 3, 4, 6, 7, 0], size=M - 1)]
+    path = tmp_path / "long.pgen"
+    path.write_bytes(write_pgen(c, vt))
+    n = 1500
+    t = synth.task(n, 8, model="simple", seed=3)
+    order = (rng.permutation(n_raw)[:n] + 1).astype(np.int32)
+    with fx.FitModel() as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.open_pgen(path, order)
+        vi = (rng.permutation(M)[:150] + 1).astype(np.int32)
+        _, cd = fm.decode_tile(vi, want_X=False)
+        assert np.array_equal(cd, c[vi - 1][:, order - 1])
+        _, cd_all = fm.decode_tile(np.arange(1, M + 1, dtype=np.int32), want_X=False)
+        assert np.array_equal(cd_all, c[:, order - 1])
+
+
+def test_pgen_malformed_record_is_reported(fx, tmp_path):
+    """A difflist whose sample ids run past the sample count must surface as FLX_ERR_PGEN, not as silent garbage."""
+    from flexlmm_b200 import synth
+    from pgen_writer import write_pgen
+    rng = np.random.default_rng(4)
+    n, M = 300, 12
+    c = rng.integers(0, 3, size=(M, n)).astype(np.uint8)
+    buf = bytearray(write_pgen(c, [0] + [4] * (M - 1)))
+    t = synth.task(n, 8, model="simple", seed=1)
+    # the last record is a vrtype-4 difflist: blow up one of its first-sample-id bytes (2 bytes per group at n = 300)
+    body = bytes(buf)
+    bad = bytearray(body)
+    bad[-(len(body) // (4 * M)) - 40:] = b"\xff" * len(bad[-(len(body) // (4 * M)) - 40:])
+    path = tmp_path / "bad.pgen"
+    path.write_bytes(bytes(bad))
+    with fx.FitModel() as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.open_pgen(path, None)
+        with pytest.raises(fx.FlxError, match="pgen"):
+            fm.decode_tile(np.arange(1, M + 1, dtype=np.int32), want_X=False)
+
+
 def test_pgen_mode10_threaded_expansion(fx, tmp_path):
-    """Enough variants that the host expansion of LD / difflist records is split over threads, each with its own LD-base cache."""
+    """Enough variants that the compressed records of a batch are gathered by several host threads; LD chains throughout."""
     from flexlmm_b200 import synth
     from pgen_writer import write_pgen
     rng = np.random.default_rng(9)
