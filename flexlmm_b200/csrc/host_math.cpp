@@ -204,7 +204,8 @@ void null_fit_householder(const double* X, int64_t n, int c, const double* y, Nu
 }
 
 // ------------------------------------------------------------------------------------------------
-// .pgen (plink-ng pgenlib on-disk format), hard calls only.
+// .pgen (plink-ng pgenlib on-disk format): header and record index only — the records themselves are expanded on the
+// device (pgen_expand.cu).
 // ------------------------------------------------------------------------------------------------
 PgenFile::~PgenFile() {
     if (mapped_ && data_) munmap(const_cast<uint8_t*>(data_), static_cast<size_t>(len_));
@@ -283,109 +284,6 @@ std::string PgenFile::parse() {
             else if (!have_base) return "LD-compressed record without a base variant";
             ldbase_[first + i] = base;
         }
-    }
-    return "";
-}
-
-static inline void set2(uint8_t* g, uint32_t i, uint8_t v) {
-    const int sh = 2 * (i & 3);
-    g[i >> 2] = static_cast<uint8_t>((g[i >> 2] & ~(3u << sh)) | (static_cast<uint32_t>(v) << sh));
-}
-
-std::string PgenFile::apply_difflist(const uint8_t*& p, const uint8_t* end, uint8_t* geno) const {
-    auto varint = [&](uint32_t& out) -> bool {
-        out = 0;
-        for (int sh = 0; sh <= 28 && p < end; sh += 7) {
-            const uint8_t b = *p++;
-            out |= static_cast<uint32_t>(b & 127) << sh;
-            if (!(b & 128)) return true;
-        }
-        return false;
-    };
-    uint32_t dl;
-    if (!varint(dl)) return "bad difflist length";
-    if (dl == 0) return "";
-    if (dl > sample_ct_) return "difflist longer than the sample count";
-    const uint32_t ngroups = (dl + 63) / 64;
-    const int idb = sample_ct_ <= 256u ? 1 : sample_ct_ <= 65536u ? 2 : sample_ct_ <= 16777216u ? 3 : 4;
-    const uint8_t* first_ids = p;
-    p += static_cast<uint64_t>(ngroups) * idb;
-    p += ngroups - 1;  // group byte counts: used only for random access
-    const uint8_t* rare = p;
-    p += (dl + 3) / 4;
-    if (p > end) return "truncated difflist";
-    uint32_t sid = 0;
-    for (uint32_t e = 0; e < dl; ++e) {
-        if ((e & 63) == 0) sid = static_cast<uint32_t>(le_bytes(first_ids + static_cast<uint64_t>(e >> 6) * idb, idb));
-        else {
-            uint32_t d;
-            if (!varint(d)) return "bad difflist delta";
-            sid += d;
-        }
-        if (sid >= sample_ct_) return "difflist sample id out of range";
-        set2(geno, sid, (rare[e >> 2] >> (2 * (e & 3))) & 3);
-    }
-    return "";
-}
-
-std::string PgenFile::decode_main(const Rec& r, uint8_t* out) const {
-    const uint8_t* p = data_ + r.off;
-    const uint8_t* end = p + r.len;
-    const int64_t bpv = bytes_per_variant();
-    const int t = r.vrtype & 7;
-    if (t == 0) {
-        if (r.len < bpv) return "short raw record";
-        std::memcpy(out, p, static_cast<size_t>(bpv));
-    } else if (t == 1) {
-        const uint8_t c2 = *p++;
-        const uint8_t lo = c2 >> 2, hi = static_cast<uint8_t>((c2 >> 2) + (c2 & 3));
-        if (p + (sample_ct_ + 7) / 8 > end) return "short 1-bit record";
-        std::memset(out, 0, static_cast<size_t>(bpv));
-        for (uint32_t i = 0; i < sample_ct_; ++i) set2(out, i, ((p[i >> 3] >> (i & 7)) & 1) ? hi : lo);
-        p += (sample_ct_ + 7) / 8;
-        std::string e = apply_difflist(p, end, out);
-        if (!e.empty()) return e;
-    } else if (t >= 4) {
-        std::memset(out, (t & 3) * 0x55, static_cast<size_t>(bpv));
-        std::string e = apply_difflist(p, end, out);
-        if (!e.empty()) return e;
-    } else {
-        return "internal: LD record passed to decode_main";
-    }
-    // clear pad bits
-    if (sample_ct_ & 3) out[bpv - 1] &= static_cast<uint8_t>((1u << (2 * (sample_ct_ & 3))) - 1);
-    return "";
-}
-
-std::string PgenFile::read_packed(uint32_t v, uint8_t* out, LdCache& cache) const {
-    if (v >= variant_ct_) return "variant index out of range";
-    const int64_t bpv = bytes_per_variant();
-    if (mode_ == 0x02) {
-        std::memcpy(out, fixed_record(v), static_cast<size_t>(bpv));
-        return "";
-    }
-    const Rec& r = recs_[v];
-    if (r.vrtype & 0x08) return "multiallelic record (the pipeline converts with --max-alleles 2)";
-    if ((r.vrtype & 6) != 2) return decode_main(r, out);
-    // LD-compressed against the nearest earlier non-LD variant
-    const uint32_t b = ldbase_[v];
-    if (cache.base != b) {
-        cache.geno.resize(static_cast<size_t>(bpv));
-        std::string e = decode_main(recs_[b], cache.geno.data());
-        if (!e.empty()) return e;
-        cache.base = b;
-    }
-    std::memcpy(out, cache.geno.data(), static_cast<size_t>(bpv));
-    const uint8_t* p = data_ + r.off;
-    std::string e = apply_difflist(p, p + r.len, out);
-    if (!e.empty()) return e;
-    if ((r.vrtype & 7) == 3) {
-        // inverted: 0 <-> 2, het and missing unchanged. On 2-bit codes: flip the high bit where the low bit is 0.
-        for (int64_t i = 0; i < bpv; ++i) {
-            const uint8_t g = out[i];
-            out[i] = static_cast<uint8_t>(g ^ ((~g & 0x55) << 1));
-        }
-        if (sample_ct_ & 3) out[bpv - 1] &= static_cast<uint8_t>((1u << (2 * (sample_ct_ & 3))) - 1);
     }
     return "";
 }

@@ -32,7 +32,8 @@ struct NullFit {
 };
 void null_fit_householder(const double* X, int64_t n, int c, const double* y, NullFit& out);
 
-// .pgen access for hard calls (pgenlibr::NewPgen / ReadHardcalls, fit_model.nf:39-40,123).
+// .pgen access (pgenlibr::NewPgen, fit_model.nf:39-40): header, record index, raw record bytes.  ReadHardcalls (:123) is
+// K0 (pgen_expand.cu) + K1 on the device.
 class PgenFile {
 public:
     ~PgenFile();
@@ -46,11 +47,6 @@ public:
     bool has_dosage() const { return has_dosage_; }
     // If the file is mode 0x02 the records are already packed 2-bit: pointer to record v (0-based).
     const uint8_t* fixed_record(uint32_t v) const { return data_ + 12 + (int64_t)v * bytes_per_variant(); }
-    // Expand variant v (0-based) to packed 2-bit (bytes_per_variant() bytes, pad bits 0). Any mode.
-    // The decoded LD base lives in the caller's cache, so several threads can expand disjoint variant ranges concurrently.
-    struct LdCache { int64_t base = -1; std::vector<uint8_t> geno; };
-    std::string read_packed(uint32_t v, uint8_t* out, LdCache& cache) const;
-    std::string read_packed(uint32_t v, uint8_t* out) { return read_packed(v, out, own_cache_); }
     // mode 0x10: where variant v's record lives in the file, its type byte and the variant its LD compression refers to
     struct RecInfo { uint64_t off; uint32_t len; uint8_t vrtype; uint32_t ldbase; };
     RecInfo rec_info(uint32_t v) const { return RecInfo{recs_[v].off, recs_[v].len, recs_[v].vrtype, ldbase_[v]}; }
@@ -58,8 +54,6 @@ public:
 private:
     struct Rec { uint64_t off; uint32_t len; uint8_t vrtype; };
     std::string parse();
-    std::string decode_main(const Rec& r, uint8_t* out) const;
-    std::string apply_difflist(const uint8_t*& p, const uint8_t* end, uint8_t* geno) const;
     const uint8_t* data_ = nullptr;
     int64_t len_ = 0;
     bool mapped_ = false;
@@ -69,7 +63,6 @@ private:
     bool has_dosage_ = false;
     std::vector<Rec> recs_;           // mode 0x10
     std::vector<uint32_t> ldbase_;    // mode 0x10: index of the LD base record for LD-compressed variants
-    LdCache own_cache_;
 };
 
 }  // namespace flx
