@@ -240,7 +240,7 @@ def main():
     tests_per_step_rank = w["M"] * (1 + w["P"])
     config = {"workload": f"{a.workload}: {w['desc']}", "n": w["n"], "snps_per_gpu": w["M"], "permutations": w["P"],
               "design": {"k": w["k"], "c": w["c"], "s": w["s"]}, "sharding": "SNP blocks per GPU, NCCL min-allreduce of min-p" if world > 1 else "single GPU",
-              "l2_policy": "no flush needed: each step streams 1.25 GB of packed genotypes and, per batch, 97 MB of int8 tiles + 79 MB of digit planes (FP64 route: 2 x 775 MB tiles + 107 MB L^-1), all above the 126 MB L2"}
+              "l2_policy": "no flush needed: each step streams 1.25 GB of packed genotypes and, per batch of 75,776 SNPs, 388 MB of int8 tiles + 79 MB of digit planes (FP64 route: 2 x 775 MB tiles + 107 MB L^-1 per 18,944 SNPs), all above the 126 MB L2"}
 
     if a.impl == "reference":
         if rank != 0:
