@@ -914,7 +914,16 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         tiles_per_batch = mult * h->num_sms;
     }
     const int64_t snps_per_batch = (int64_t)tiles_per_batch * ts.snps;
-    const int64_t nbatch = (M + snps_per_batch - 1) / snps_per_batch;
+    // batch boundaries; when the genotypes come from the host, the first batches ramp up (1/4, 1/2, then full size) so that the
+    // first H2D, which nothing can overlap, is short
+    std::vector<int64_t> bstart;
+    {
+        const int64_t unit = (int64_t)h->num_sms * ts.snps;
+        int64_t pos = 0, step = (!h->is_resident && snps_per_batch >= 4 * unit) ? snps_per_batch / 4 : snps_per_batch;
+        while (pos < M) { bstart.push_back(pos); pos += step; step = std::min(snps_per_batch, 2 * step); }
+        bstart.push_back(M);
+    }
+    const int64_t nbatch = (int64_t)bstart.size() - 1;
     const int64_t bpv = h->bpv;
     const int nsym = h->s * (h->s + 1) / 2;
     const int cr = h->cr;
@@ -988,8 +997,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     std::vector<uint8_t> xhost;
 
     for (int64_t bi = 0; bi < nbatch; bi++) {
-        const int64_t s0 = bi * snps_per_batch;
-        const int64_t nsnp = std::min(snps_per_batch, M - s0);
+        const int64_t s0 = bstart[bi];
+        const int64_t nsnp = bstart[bi + 1] - s0;
         const int NJ = (int)((nsnp + ts.snps - 1) / ts.snps);
         const int buf = (int)(bi & 1);
         const uint8_t* packed_dev;
