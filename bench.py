@@ -209,7 +209,7 @@ def stage_roofline(w, acc, steps, int8_path):
     if int8_path:
         put("K1q decode_i8", M * (raw + n256), "GB/s", acc["ms_decode"], hbm, "hbm")
         passes = max(1, int(round(acc.get("int8_passes", steps) / steps)))
-        put("K2q qf_i8 (g'C V^-1 C g, 6 planes x %d passes)" % passes, 6.0 * n * n * M * passes, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
+        put("K2q qf_i8 (g'C V^-1 C g, 6 planes x %d pass units)" % passes, 6.0 * n * n * M * passes, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
         put("K4q-A + K3b (u, b, fit, LRT)", M * (n256 * 2.0) * s, "GB/s", acc["ms_fit"], hbm, "hbm")
         put("K4q-B perm contraction (6 planes)", 6.0 * 2 * n * P * M * s, "TFLOP/s", acc["ms_perm"], i8_peak()[0], "tensor(i8)")
     else:
@@ -341,7 +341,7 @@ def main():
             peak, peak_src = i8_peak()
             passes = max(1, int(round(acc.get("int8_passes", a.steps) / a.steps)))
             work = 6.0 * n * n * w["M"] * a.steps * passes
-            kname = "qf_i8_kernel (K2q: g'C V^-1 C g, tcgen05.mma kind::i8, 6 exact digit planes, %d pass%s per batch)" % (passes, "" if passes == 1 else "es")
+            kname = "qf_i8_kernel (K2q: g'C V^-1 C g, tcgen05.mma kind::i8, 6 exact digit planes, %d triangular-pass unit%s per batch)" % (passes, "" if passes == 1 else "s")
             tfile = "qf_traffic.json"
         else:
             peak, peak_src = fp64_peak()

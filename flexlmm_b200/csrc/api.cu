@@ -712,14 +712,17 @@ static int finalize_setup(flx_handle* h) {
         h->fast = ok;
     }
     if (h->fast) {
-        // passes: for every ordered group pair (a, b) and every triple used on the right (group b), one K2q launch whose
-        // epilogue dots with every triple used on the left (group a)
+        // passes: one K2q launch per (matrix, triple on the right), its epilogue dots with every triple used on the left.
+        //   same scale a:      T^(a,a) = tril(C_a V^-1 C_a), half diagonal: A_raw[t][v] = g_t' T g_v + g_v' T g_t
+        //   scales a < b:      the FULL matrix F^(a,b) = C_a V^-1 C_b:        A_raw[t][v] = g_t' F g_v  (t in a, v in b)
+        // (a full pass costs two triangular ones, but one full pass with two left vectors replaces three triangular passes
+        //  of the x + I(x==1) + x:cov model: 5 pass units instead of 6)
         int slot_of[2][2][2][2];
         memset(slot_of, -1, sizeof(slot_of));
         bool used[2][2] = {{false, false}, {false, false}};
         for (int t = 0; t < h->s; t++) used[pl.grp[t]][pl.alp[t]] = true;
         for (int a = 0; a < pl.NG; a++)
-            for (int b = 0; b < pl.NG; b++)
+            for (int b = a; b < pl.NG; b++)
                 for (int ar = 0; ar < pl.NA; ar++) {
                     if (!used[b][ar]) continue;
                     flx_handle::QfPass ps{};
@@ -730,8 +733,14 @@ static int finalize_setup(flx_handle* h) {
                 }
         for (int t = 0; t < h->s; t++)
             for (int v = 0; v < h->s; v++) {
-                pl.slot_a[t][v] = (int8_t)slot_of[pl.grp[t]][pl.grp[v]][pl.alp[t]][pl.alp[v]];
-                pl.slot_b[t][v] = (int8_t)slot_of[pl.grp[v]][pl.grp[t]][pl.alp[v]][pl.alp[t]];
+                const int a = pl.grp[t], b = pl.grp[v];
+                if (a == b) {
+                    pl.slot_a[t][v] = (int8_t)slot_of[a][a][pl.alp[t]][pl.alp[v]];
+                    pl.slot_b[t][v] = (int8_t)slot_of[a][a][pl.alp[v]][pl.alp[t]];
+                } else {
+                    pl.slot_a[t][v] = (int8_t)(a < b ? slot_of[a][b][pl.alp[t]][pl.alp[v]] : slot_of[b][a][pl.alp[v]][pl.alp[t]]);
+                    pl.slot_b[t][v] = -1;
+                }
             }
         const double one = 1.0, zero = 0.0;
         h->T256 = (int)((n + 255) / 256);
@@ -852,7 +861,7 @@ static int finalize_setup(flx_handle* h) {
         // n ~ 10^5), the task runs on the FP64 route instead of failing
         size_t free_b = 0, total_b = 0;
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t planes_b = (size_t)pl.NG * pl.NG * 2 * h->T256 * (h->T256 + 1) * h->Q * 16384;
+        const size_t planes_b = (size_t)pl.NG * pl.NG * 2 * h->T256 * (h->T256 + 1) * h->Q * 16384;   // a full set = two triangular ones
         const size_t batch_b = (size_t)h->num_sms * h->NKB * 8192 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);   // one tile per SM at least
         if (planes_b + batch_b + (size_t)256 * n * 8 > free_b) {
             if (h->cfg.verbose) fprintf(stderr, "[flx] int8 route needs %.1f GB of digit planes, %.1f GB free: using the FP64 route\n", planes_b / 1e9, free_b / 1e9);
@@ -864,20 +873,22 @@ static int finalize_setup(flx_handle* h) {
         const double one = 1.0, zero = 0.0;
         DevBuf<double> Vt;
         FLX_TRY(Vt.ensure((size_t)256 * n));
-        for (int mi = 0; mi < pl.NG * pl.NG; mi++) {
-            FLX_TRY(h->rowscale[mi].ensure((size_t)h->T256 * 256));
-            FLX_TRY(h->T8[mi].ensure((size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384));
-        }
+        const size_t tri_b = (size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384, full_b = (size_t)h->T256 * h->NKB * h->Q * 16384;
+        for (int a = 0; a < pl.NG; a++)
+            for (int b = a; b < pl.NG; b++) {
+                FLX_TRY(h->rowscale[a * pl.NG + b].ensure((size_t)h->T256 * 256));
+                FLX_TRY(h->T8[a * pl.NG + b].ensure(a == b ? tri_b : full_b));
+            }
         for (int I = 0; I < h->T256; I++) {
             const int64_t r0 = (int64_t)I * 256;
-            const int64_t m = std::min<int64_t>(256, n - r0), ncols = r0 + m, K = n - r0;
+            const int64_t m = std::min<int64_t>(256, n - r0), ncols = (pl.NG > 1) ? n : r0 + m, K = n - r0;
             FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, m, ncols, K, &one, h->Zdense.p + r0 + r0 * n, n, h->Zdense.p + r0, n, &zero, Vt.p, 256));
             for (int a = 0; a < pl.NG; a++)
-                for (int b = 0; b < pl.NG; b++) {
+                for (int b = a; b < pl.NG; b++) {
                     const int mi = a * pl.NG + b;
                     const double* ca = pl.ones[a] ? nullptr : h->cvec_d.p + (size_t)a * n_pad;
                     const double* cb = pl.ones[b] ? nullptr : h->cvec_d.p + (size_t)b * n_pad;
-                    FLX_TRY(launch_qf_slice(Vt.p, n, 256, I, h->Q, ca, cb, h->rowscale[mi].p, h->T8[mi].p, h->stream));
+                    FLX_TRY(launch_qf_slice(Vt.p, n, 256, I, h->T256, h->Q, ca, cb, a == b ? 0 : 1, h->rowscale[mi].p, h->T8[mi].p, h->stream));
                 }
         }
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1161,6 +1172,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 const flx_handle::QfPass& ps = h->plan.passes[pi];
                 QfArgs q{};
                 q.X8 = h->X8.p + ps.amma * x8_stride; q.T8 = h->T8[ps.mat].p; q.rowscale = h->rowscale[ps.mat].p;
+                q.full = (ps.mat / h->plan.NG != ps.mat % h->plan.NG) ? 1 : 0;
                 q.ndot = ps.ndot;
                 for (int d = 0; d < ps.ndot; d++) { q.Xd[d] = h->X8.p + ps.adot[d] * x8_stride; q.part[d] = h->qf_part.p + (int64_t)ps.slot[d] * nparts * nsnp; }
                 for (int i = 0; i < 8; i++) q.plane_scale[i] = std::ldexp(1.0, -8 * (i + 1));
@@ -1309,7 +1321,8 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
     if (M > 0) {
         const bool fast = h->fast;
         h->stats.int8_path = fast ? 1 : 0;
-        h->stats.int8_passes = fast ? (int64_t)h->plan.passes.size() : 0;
+        h->stats.int8_passes = 0;      // in units of one triangular pass (6 n^2 int8 ops per SNP); a full-matrix pass counts two
+        if (fast) for (const auto& ps : h->plan.passes) h->stats.int8_passes += (ps.mat / h->plan.NG != ps.mat % h->plan.NG) ? 2 : 1;
         FLX_TRY(run_batches(h, var_idx, M, out != nullptr, do_perm, nullptr, nullptr, fast, false, nullptr, M));
         if (fast) {
             // SNPs whose x is (nearly) in the span of the constant columns lose digits in A = x'V^-1x - |u|^2: re-fit them in FP64

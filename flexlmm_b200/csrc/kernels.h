@@ -32,7 +32,9 @@ struct QfArgs {
     const int8_t* X8;         // [NJ][NKB][8 KB]  int8 genotype tiles (128 SNPs x 64 samples per block, UMMA canonical K-major): MMA operand g'
     const int8_t* Xd[2];      // tiles of the left vectors g of the forms g' T g' (same layout; Xd[0] == X8 for a plain quadratic form)
     int ndot;                 // 1 or 2 left vectors per pass
-    const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(V^-1) (half diagonal)
+    const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(C_a V^-1 C_a) (half diagonal), or,
+                              // full != 0, [row tile I][kb < NKB][Q planes][16 KB] planes of the full matrix C_a V^-1 C_b
+    int full;
     const double* rowscale;   // [n_pad256] power-of-two scale of each row of T (one value per 16 consecutive rows)
     double plane_scale[8];    // 2^-8(q+1)
     double* part[2];          // per left vector: [T256][Q][nsnp] partial forms
@@ -63,9 +65,10 @@ struct XgArgs {
 int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st);
 // rowmul (optional, [n]): the planes are those of diag(rowmul) G
 int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul, double* colscale, int8_t* G8, cudaStream_t st);
-// Vtile: rows 256 I .. 256 I + 255 of V^-1 (column-major, ld), columns 0 .. row.  ca, cb (optional, [n]): the planes are those
-// of tril(diag(ca) V^-1 diag(cb)) with half diagonal
-int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st);
+// Vtile: rows 256 I .. 256 I + 255 of V^-1 (column-major, ld), columns 0 .. row (full: all n columns).  ca, cb (optional, [n]):
+// the planes are those of tril(diag(ca) V^-1 diag(cb)) with half diagonal, or of the full matrix diag(ca) V^-1 diag(cb)
+int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int T256, int Q, const double* ca, const double* cb, int full, double* rowscale, int8_t* T8,
+                    cudaStream_t st);
 int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 
 // ---------------------------------------------------------------- K0 (pgen_expand.cu)
@@ -152,7 +155,7 @@ struct SolveArgs {
     int fast;
     double refit_thr;         // re-fit in FP64 when a Cholesky pivot <= refit_thr * A_raw[t][t]
     const double* qf_part; int qf_nparts;
-    int8_t slot_a[8][8], slot_b[8][8];
+    int8_t slot_a[8][8], slot_b[8][8];   // slot_b < 0: single term
     int32_t* refit_flag;      // [nsnp] set to 1 when the SNP must be re-fitted on the FP64 path (near-collinear with the constant columns)
 };
 int upload_fit_const(const FitConst& c);

@@ -119,11 +119,12 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
                 const int rem = (int)(item % per_I);
                 const int JP = rem / g.Q, q = rem % g.Q;
-                int nkb = 4 * (I + 1);
+                int nkb = g.full ? g.NKB_live : 4 * (I + 1);      // lower-triangular matrices: k runs to the diagonal block
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;      // an odd tile count leaves the last pair a single tile
                 const int8_t* a_src = g.X8 + (int64_t)(2 * JP) * g.NKB * QF_A_BYTES;
-                const int8_t* b_src = g.T8 + ((int64_t)2 * I * (I + 1) * g.Q + q) * QF_B_BYTES;   // 4*I*(I+1)/2 blocks precede tile I
+                // triangular: 4*I*(I+1)/2 blocks precede tile I; full: NKB blocks per tile
+                const int8_t* b_src = g.T8 + ((g.full ? (int64_t)I * g.NKB : (int64_t)2 * I * (I + 1)) * g.Q + q) * QF_B_BYTES;
                 for (int kb = 0; kb < nkb; kb++) {
                     qbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                 const int I = g.T256 - 1 - (int)(item / per_I);
                 const int JP = (int)(item % per_I) / g.Q;
                 const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;
-                int nkb = 4 * (I + 1);
+                int nkb = g.full ? g.NKB_live : 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 if (g.prof) t0 = clock64();
                 qbar_wait(acc_empty, aphase ^ 1);           // epilogue has drained the accumulators of the previous item
@@ -340,14 +341,18 @@ __device__ __forceinline__ double digit_scale(double m) {
 
 // V: rows row0 .. row0+255 of V^-1 (column-major, leading dimension ld), columns 0 .. row
 __global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int64_t ld, int64_t row0, const double* __restrict__ ca,
-                                   const double* __restrict__ cb, double* __restrict__ rowscale) {
+                                   const double* __restrict__ cb, int full, double* __restrict__ rowscale) {
     const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // 256 threads in all: one per row of the tile
     const int64_t i = row0 + il;
     double m = 0.0;
     if (i < n) {
         const double ai = ca ? ca[i] : 1.0;
-        for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(ai * V[il + j * ld] * (cb ? cb[j] : 1.0)));
-        m = fmax(m, 0.5 * fabs(ai * V[il + i * ld] * (cb ? cb[i] : 1.0)));
+        if (full) {
+            for (int64_t j = 0; j < n; j++) m = fmax(m, fabs(ai * V[il + j * ld] * (cb ? cb[j] : 1.0)));
+        } else {
+            for (int64_t j = 0; j < i; j++) m = fmax(m, fabs(ai * V[il + j * ld] * (cb ? cb[j] : 1.0)));
+            m = fmax(m, 0.5 * fabs(ai * V[il + i * ld] * (cb ? cb[i] : 1.0)));
+        }
     }
     // one scale per 16 consecutive rows (= one tcgen05.ld chunk of the K2q epilogue, which then reduces the chunk in int64)
     for (int off = 8; off >= 1; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
@@ -356,22 +361,22 @@ __global__ void qf_rowscale_kernel(const double* __restrict__ V, int64_t n, int6
 
 __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __restrict__ V, int64_t n, int64_t ld, const double* __restrict__ ca,
                                                            const double* __restrict__ cb, const double* __restrict__ rowscale, int Q, int I,
-                                                           int8_t* __restrict__ T8) {
+                                                           int full, int NKB, int8_t* __restrict__ T8) {
     const int kb = blockIdx.x;
-    if (kb >= 4 * (I + 1)) return;
     const int rl = threadIdx.x;                         // row within the 256-row tile
     const int64_t i = (int64_t)I * 256 + rl;
     const double inv = (i < n) ? 1.0 / rowscale[i] : 0.0;
     const double ai = (ca && i < n) ? ca[i] : 1.0;
     const double up = ldexp(1.0, 8 * Q);
-    int8_t* blk = T8 + ((int64_t)2 * I * (I + 1) + kb) * Q * QF_B_BYTES;
+    int8_t* blk = T8 + ((full ? (int64_t)I * NKB : (int64_t)2 * I * (I + 1)) + kb) * Q * QF_B_BYTES;
     for (int ch = 0; ch < 4; ch++) {
         uint32_t w[7][4];
         for (int q = 0; q < Q; q++) w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
         for (int b = 0; b < 16; b++) {
             const int64_t j = (int64_t)kb * QF_KB + ch * 16 + b;
             double t = 0.0;
-            if (i < n && j <= i) t = ((j == i) ? 0.5 : 1.0) * (ai * V[rl + j * ld] * (cb ? cb[j] : 1.0));
+            if (full) { if (i < n && j < n) t = ai * V[rl + j * ld] * (cb ? cb[j] : 1.0); }
+            else if (i < n && j <= i) t = ((j == i) ? 0.5 : 1.0) * (ai * V[rl + j * ld] * (cb ? cb[j] : 1.0));
             long long ri = __double2ll_rn(t * inv * up);
             for (int q = Q - 1; q >= 0; q--) {
                 const long long d = ((ri + 128) & 255) - 128;
@@ -386,9 +391,10 @@ __global__ void __launch_bounds__(256) qf_slice_pack_kernel(const double* __rest
     }
 }
 
-int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int Q, const double* ca, const double* cb, double* rowscale, int8_t* T8, cudaStream_t st) {
-    qf_rowscale_kernel<<<2, 128, 0, st>>>(Vtile, n, ld, (int64_t)I * 256, ca, cb, rowscale);
-    qf_slice_pack_kernel<<<(unsigned)(4 * (I + 1)), 256, 0, st>>>(Vtile, n, ld, ca, cb, rowscale, Q, I, T8);
+int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int T256, int Q, const double* ca, const double* cb, int full, double* rowscale, int8_t* T8,
+                    cudaStream_t st) {
+    qf_rowscale_kernel<<<2, 128, 0, st>>>(Vtile, n, ld, (int64_t)I * 256, ca, cb, full, rowscale);
+    qf_slice_pack_kernel<<<(unsigned)(full ? 4 * T256 : 4 * (I + 1)), 256, 0, st>>>(Vtile, n, ld, ca, cb, rowscale, Q, I, full, 4 * T256, T8);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("qf_slice launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             for (int v = t; v < s; v++) {
                 double uu = 0.0;
                 for (int j = 0; j < cr; j++) uu += __ldg(ub + t * a.crp + j) * __ldg(ub + v * a.crp + j);
-                const double araw = S[a.slot_a[t][v]] + S[a.slot_b[t][v]];
+                const double araw = S[a.slot_a[t][v]] + (a.slot_b[t][v] >= 0 ? S[a.slot_b[t][v]] : 0.0);
                 if (v == t) nrm2[t] = araw;
                 A[t][v] = A[v][t] = araw - uu;
             }

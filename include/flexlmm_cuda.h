@@ -81,7 +81,7 @@ typedef struct {
     int64_t cols_per_tile;     /* design columns actually used per 128-wide tile                       */
     int64_t int8_path;         /* 1: the batches ran K2q (int8 tensor cores), 0: K2 (FP64 DMMA)        */
     int64_t refit_snps;        /* SNPs re-fitted on the FP64 path (near-collinear with constant columns)*/
-    int64_t int8_passes;       /* K2q launches per batch: 1 for one SNP term, 6 for x + I(x==1) + x:cov   */
+    int64_t int8_passes;       /* K2q work per batch in triangular-pass units (6 n^2 int8 ops per SNP): 1 for one SNP term, 5 for x + I(x==1) + x:cov */
 } flx_stats;
 
 const char* flx_last_error(void);
