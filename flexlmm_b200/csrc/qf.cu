@@ -31,7 +31,7 @@ constexpr int QF_B_BYTES = 256 * QF_KB;       // 16 KB (one digit plane block)
 constexpr int QF_STAGE_BYTES = 2 * QF_A_BYTES + QF_B_BYTES;   // two SNP tiles share one digit-plane block
 constexpr int QF_STAGES = 7;
 constexpr int QF_SMEM = QF_STAGES * QF_STAGE_BYTES + 256;
-constexpr int QF_THREADS = 320;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int QF_THREADS = 384;                // warpgroup 0: warp 0 TMA, warp 1 MMA (56 registers); warps 4-11 epilogue (224): 128*56 + 256*224 = 384*168, the CTA's pool
 constexpr int XG_THREADS = 192;
 
 __device__ __forceinline__ uint32_t qsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     // n = 20,000 a batch's tiles, 383 MB, no longer fit L2); long row tiles first
     const int NJ2 = (g.NJ + 1) >> 1;
     const int per_I = NJ2 * g.Q;
-    if (warp == 0) {
+    // the register file is partitioned per SM sub-partition, so the split must be explicit: the producer warpgroup gives its
+    // registers to the eight epilogue warps, whose sixteen 16-byte genotype words per left vector then stay in registers
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 0) {
         // ---------------- TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -179,10 +183,12 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             }
             if (g.prof) { g.prof[4 * blockIdx.x] = clock64() - t_begin; g.prof[4 * blockIdx.x + 1] = t_acc; g.prof[4 * blockIdx.x + 2] = t_full; g.prof[4 * blockIdx.x + 3] = t_head; }
         }
+      }
     } else {
-        // ---------------- epilogue: thread = TMEM lane = SNP; warps 2-5 own the first SNP tile of the pair, warps 6-9 the second
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ---------------- epilogue: thread = TMEM lane = SNP; warps 4-7 own the first SNP tile of the pair, warps 8-11 the second
         const int quad = warp & 3;
-        const int t = (warp - 2) >> 2;
+        const int t = (warp - 4) >> 2;
         const int snp_l = quad * 32 + lane;
         uint32_t aphase = 0;
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
