@@ -129,7 +129,7 @@ struct flx_handle {
     DevBuf<double> Rpk, inv_rss, lrs0p, maxratio, minp_d;
     // int8 quadratic-form path (K2q)
     bool fast = false;
-    int Q = 6, T256 = 0, NKB = 0, crpH = 4;
+    int Q = 6, T256 = 0, NKB = 0;
     // every SNP term is g_t(x) * c_t[sample] with an integer triple g_t (|g| <= 2, "alpha") and a per-sample scale c_t ("group")
     struct QfPass { int mat, amma, ndot, adot[2], slot[2]; };
     struct FastPlan {
@@ -745,7 +745,6 @@ static int finalize_setup(flx_handle* h) {
         const double one = 1.0, zero = 0.0;
         h->T256 = (int)((n + 255) / 256);
         h->NKB = h->T256 * 4;
-        h->crpH = gram_padded_width(cr + 1);
         std::vector<double> cpad((size_t)pl.NG * n_pad, 0.0);
         for (int gq = 0; gq < pl.NG; gq++) memcpy(cpad.data() + (size_t)gq * n_pad, cvecs[gq].data(), n * sizeof(double));
         FLX_TRY(h->cvec_d.ensure(cpad.size()));

@@ -137,7 +137,6 @@ struct GramArgs {
 };
 int gram_padded_width(int cr);
 int launch_snp_gram(const GramArgs& a, cudaStream_t st);
-int launch_snp_gram_sweep1(const GramArgs& a, cudaStream_t st);   // only u = Qc' w and ||w||^2 (fast mode: against H = L^-T [Qc | r])
 
 struct SolveArgs {
     const double* n_part; const double* u_part; const double* a_part; const double* b_part;

@@ -1,25 +1,29 @@
-// qf.cu — K2q: the whitened quadratic form x' V^-1 x on the int8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators).
+// qf.cu — the int8 tensor-core route (tcgen05.mma kind::i8, TMEM accumulators): K2q (quadratic forms), K4q (x against
+// whitened matrices), K1q (2-bit -> int8 tiles) and the once-per-task digit-plane packers.
 //
-// For a design whose SNP-dependent column is the hard call itself (x in {0,1,2}; additive models, BASELINE configs C2/C4/C5)
-// the only O(n^2)-per-SNP quantity of the fit is  ||L^-1 x||^2 = x' V^-1 x = 2 x' T x,  T = strict lower triangle of V^-1
-// plus half its diagonal (everything else — Qc' L^-1 x, r' L^-1 x, R_f' L^-1 x — is x against n x (c+1+P) matrices that
-// are whitened once).  x is an exact small integer, so T is split ONCE into Q = 6 balanced base-256 digit planes
-// ("Ozaki slices", 48 bits below each row's power-of-two scale): every int8 x int8 product and every s32 accumulation is
-// exact, and the result differs from the FP64 value only by the 2^-48 truncation of T — measured 4e-15 relative in
-// x' V^-1 x at n = 2000, better than the rounding a length-n FP64 dot product accumulates.  Throughput of the i8 pipe
-// (4.5 POP/s nominal, 4.17 POP/s measured by tools/qf_probe.cu) over 6 slices is ~19x the FP64 DMMA pipe.
+// For a design whose SNP terms are integer genotype codes g(x) (x, I(x==1): values in {-2..2}) times a per-sample scale c
+// (1, or the covariate of an x:cov interaction) the only O(n^2)-per-SNP quantities of the fit are the forms
+//   g' C_a V^-1 C_b g'  =  g' T g' + g'' T' g      (same scale: T = strict lower triangle of C V^-1 C plus half its diagonal)
+//                       =  g' F g'                 (two scales: the full matrix F = C_a V^-1 C_b)
+// (everything else — Qc' L^-1 x, r' L^-1 x, R_f' L^-1 x — is g against n x (c+1+P) matrices that are whitened once: K4q).
+// g is an exact small integer vector, so T / F are split ONCE into Q = 6 balanced base-256 digit planes ("Ozaki slices",
+// 48 bits below a power-of-two scale per 16 rows): every int8 x int8 product and every s32 accumulation is exact, and the
+// result differs from the FP64 value only by the 2^-48 truncation of the matrix — measured 4e-15 relative in x' V^-1 x at
+// n = 2000, better than the rounding a length-n FP64 dot product accumulates.  Throughput of the i8 pipe (4.5 POP/s
+// nominal, 4.17 POP/s measured by tools/qf_probe.cu) over 6 slices is ~19x the FP64 DMMA pipe.
 //
-// Kernel: persistent, warp-specialised, one CTA per SM.
-//   warp 0  : TMA producer — 1-D bulk copies of pre-packed operand blocks (UMMA canonical K-major, no swizzle: 8 x 16 B
-//             core matrices) into a 7-stage x 32 KB ring.  The kernel runs at the L2 -> SM throughput cap, so the work
-//             item is shaped for operand reuse: TWO SNP tiles (2 x 8 KB) against ONE digit-plane block (16 KB).
-//   warp 1  : allocates 512 TMEM columns; one lane issues tcgen05.mma.cta_group::1.kind::i8, M = 128 SNPs (A = X8 tile),
-//             N = 256 rows of T (B = one digit plane), K = 32 per instruction, one 128 x 256 s32 accumulator per SNP tile;
-//             tcgen05.commit frees stages.
-//   warps 2-9: epilogue — tcgen05.ld an accumulator 16 rows at a time, multiply by the SNP's own genotype at that row,
-//             reduce the 16 rows exactly in int64 (they share one power-of-two scale), scale and sum over the 256 rows
-//             IN THE THREAD (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane, SNP).
-// Work item = (row tile I of 256 rows, digit plane q, pair of SNP tiles); k runs over the lower-triangular range.
+// K2q kernel: persistent, warp-specialised, one CTA of 12 warps per SM.
+//   warp 0   : TMA producer — 1-D bulk copies of pre-packed operand blocks (UMMA canonical K-major, no swizzle: 8 x 16 B
+//              core matrices) into a 7-stage x 32 KB ring.  The operand stream L2 -> SM bounds the kernel, so the work
+//              item is shaped for operand reuse: TWO SNP tiles (2 x 8 KB) against ONE digit-plane block (16 KB).
+//   warp 1   : allocates 512 TMEM columns; one lane issues tcgen05.mma.cta_group::1.kind::i8, M = 128 SNPs (A = X8 tile),
+//              N = 256 rows of T (B = one digit plane), K = 32 per instruction, one 128 x 256 s32 accumulator per SNP tile;
+//              tcgen05.commit frees stages.  (warps 2-3 idle: setmaxnreg works on whole warpgroups.)
+//   warps 4-11: epilogue — tcgen05.ld an accumulator 16 rows at a time, multiply by the left vector(s) at those rows,
+//              reduce the 16 rows exactly in s32 (they share one power-of-two scale), scale and sum over the 256 rows
+//              IN THE THREAD (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane, SNP).
+// Work item = (row tile I of 256 rows, pair of SNP tiles, digit plane q); k runs over the lower-triangular range (all k
+// for a full matrix).
 #include "common.cuh"
 #include "kernels.h"
 

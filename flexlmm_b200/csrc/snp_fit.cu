@@ -235,28 +235,6 @@ static int launch_gram_s(const GramArgs& a, cudaStream_t st) {
     return -1;
 }
 
-template <int CRP>
-static int launch_sweep1_c(const GramArgs& a, cudaStream_t st) {
-    using C = GramCfg<1, CRP>;
-    const int64_t NJ = (a.nsnp + 8 * C::GROUPS - 1) / (8 * C::GROUPS);
-    snp_gram1_kernel<1, CRP><<<dim3((unsigned)NJ, (unsigned)a.KS), C::THREADS, 0, st>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("snp_gram sweep1 launch: %s", cudaGetErrorString(e)); return -3; }
-    return 0;
-}
-int launch_snp_gram_sweep1(const GramArgs& a, cudaStream_t st) {
-    if (a.nsnp <= 0) return 0;
-    if (a.s != 1) { set_error("snp_gram sweep1: s must be 1"); return -1; }
-    switch (a.crp) {
-        case 4: return launch_sweep1_c<4>(a, st);
-        case 8: return launch_sweep1_c<8>(a, st);
-        case 16: return launch_sweep1_c<16>(a, st);
-        case 24: return launch_sweep1_c<24>(a, st);
-    }
-    set_error("snp_gram sweep1: unsupported padded width %d", a.crp);
-    return -1;
-}
-
 int gram_padded_width(int cr) { return cr <= 4 ? 4 : cr <= 8 ? 8 : cr <= 16 ? 16 : 24; }
 
 int launch_snp_gram(const GramArgs& a, cudaStream_t st) {
