@@ -153,15 +153,19 @@ class FitModel:
         check(self._lib.flx_comm_attach(self._h, ptr(uid), int(rank), int(nranks)))
 
     # ---- the hot loop
-    def run(self, var_idx, per_snp=True, minp=None):
-        """var_idx: 1-based variant numbers (get_var_idx.nf:34-35).  Returns a dict."""
+    def run(self, var_idx, per_snp=True, minp=None, out=None):
+        """var_idx: 1-based variant numbers (get_var_idx.nf:34-35).  Returns a dict.  `out`: the dict of an earlier call with
+        the same number of variants, whose per-SNP arrays are overwritten instead of allocating (and page-faulting) new ones."""
         var_idx = np.ascontiguousarray(var_idx, dtype=np.int32)
         M = var_idx.size
         res = {}
-        out = None
+        prev, out = out, None
         if per_snp:
-            res = dict(lrt_chisq=np.empty(M), pval=np.empty(M), lrt_df=np.empty(M, dtype=np.int32), rank=np.empty(M, dtype=np.int32),
-                       pivot=np.empty((M, self.k), dtype=np.int32), coef=np.empty((M, self.k)))
+            shapes = dict(lrt_chisq=((M,), np.float64), pval=((M,), np.float64), lrt_df=((M,), np.int32), rank=((M,), np.int32),
+                          pivot=((M, self.k), np.int32), coef=((M, self.k), np.float64))
+            reuse = prev is not None and all(f in prev and prev[f].shape == sh and prev[f].dtype == dt and prev[f].flags.c_contiguous
+                                             for f, (sh, dt) in shapes.items())
+            res = {f: (prev[f] if reuse else np.empty(sh, dtype=dt)) for f, (sh, dt) in shapes.items()}
             out = FlxSnpOut(*(res[f].ctypes.data for f in ("lrt_chisq", "pval", "lrt_df", "rank", "pivot", "coef")))
         want_minp = (self.P > 0) if minp is None else bool(minp)
         mp = np.empty(self.P) if want_minp else None

@@ -361,6 +361,22 @@ def test_empty_and_single_variant(fx, big):
         fm.run(np.array([6001], dtype=np.int32))
 
 
+def test_run_reuses_result_arrays(fx, big):
+    """run(out=previous result) overwrites the caller's arrays in place (no new allocations on a streaming caller's path)."""
+    t, fm, r = big
+    vi = np.arange(1, 501, dtype=np.int32)
+    a = fm.run(vi)
+    keep = {k2: a[k2].copy() for k2 in ("lrt_chisq", "pval", "lrt_df", "rank", "pivot", "coef")}
+    ids = {k2: a[k2].ctypes.data for k2 in keep}
+    a["lrt_chisq"][:] = -1.0
+    b = fm.run(vi, out=a)
+    for k2 in keep:
+        assert b[k2].ctypes.data == ids[k2]
+        assert np.array_equal(b[k2], keep[k2], equal_nan=True)
+    c = fm.run(vi[:100], out=b)                     # other size: fresh arrays
+    assert c["lrt_chisq"].shape == (100,) and np.array_equal(c["lrt_chisq"], keep["lrt_chisq"][:100])
+
+
 # ------------------------------------------------------------------------------------------------ K2q: exact int8 tensor-core path
 def _run(fx, t, int8, M, perm=True):
     fm = fx.FitModel(int8=int8)
