@@ -731,6 +731,7 @@ static int finalize_setup(flx_handle* h) {
                         if (used[a][al]) { ps.adot[ps.ndot] = al; ps.slot[ps.ndot] = pl.nslots; slot_of[a][b][al][ar] = pl.nslots++; ps.ndot++; }
                     pl.passes.push_back(ps);
                 }
+        if (pl.nslots > 16) { set_error("internal: %d int8 forms exceed the K3b slot table", pl.nslots); return FLX_ERR_BAD_ARG; }
         for (int t = 0; t < h->s; t++)
             for (int v = 0; v < h->s; v++) {
                 const int a = pl.grp[t], b = pl.grp[v];

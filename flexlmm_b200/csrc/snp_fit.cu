@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     bool refit = false;
     if (a.fast) {
         // A_raw[t][v] = g_t' V^-1 g_v from the int8 passes (K2q), u_t = (L^-T Qc)' g_t and b_t = (L^-T r)' g_t from K4q-A
-        double S[8];
+        double S[16];    // at most 12 forms: two scales x two triples on either side
         int nslots = 0;
         for (int t = 0; t < s; t++)
             for (int v = t; v < s; v++) { nslots = max(nslots, (int)a.slot_a[t][v] + 1); nslots = max(nslots, (int)a.slot_b[t][v] + 1); }

@@ -469,6 +469,23 @@ def test_int8_path_multi_term_model(fx, orc, n, M):
         assert_logp_close(r8["min_pval"], want)
 
 
+def test_int8_path_four_terms_two_scales_two_codes(fx, orc):
+    """y ~ x + I(x==1) + x:cov + I(x==1):cov + cov: every (scale, genotype code) combination in use — 12 int8 forms."""
+    from flexlmm_b200 import synth
+    n, M = 380, 150
+    t = synth.task(n, M, model="additive", P=3, seed=23, effect=0.1)
+    cov = t["M0"][:, 2]
+    one = np.ones(n)
+    t["M0"], t["M1"], t["M2"] = (np.column_stack([one, np.full(n, float(v)), np.full(n, float(v == 1)), cov, v * cov, (v == 1) * cov]) for v in (0, 1, 2))
+    r8, st8 = _run(fx, t, True, M)
+    r64, st64 = _run(fx, t, False, M)
+    assert st8["int8_path"] == 1 and st64["int8_path"] == 0 and st8["int8_passes"] == 8
+    assert np.array_equal(r8["lrt_df"], r64["lrt_df"]) and np.array_equal(r8["pivot"], r64["pivot"])
+    np.testing.assert_allclose(r8["lrt_chisq"], r64["lrt_chisq"], rtol=1e-8, atol=1e-9)
+    assert_logp_close(r8["min_pval"], r64["min_pval"])
+    compare(r8, oracle_run(orc, t, t["codes_raw"]))
+
+
 def test_int8_path_factor_interaction_and_rare_variants(fx, orc):
     """The reference's test formula shape, y ~ x + I(x==1) + x:group + group with a two-level factor (indicator scale), on
     SNPs many of which have no hom-alt call: there I(x==1) duplicates x exactly and is dropped by the rank rule WITHOUT a
