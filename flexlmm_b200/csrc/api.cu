@@ -1345,6 +1345,7 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
     cudaEventRecord(e0, h->stream);
     if (out && M > 0) {
         const size_t k = (size_t)h->k;
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));       // the per-batch copies have landed (and cannot overtake what follows)
         if (h->stats.refit_snps > 0) {
             // the FP64 refit pass rewrote scattered slots: fetch the arrays again
             FLX_CUDA_TRY(cudaMemcpyAsync(h->chisq_h.p, h->chisq.p, M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1355,7 +1356,6 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
             FLX_CUDA_TRY(cudaMemcpyAsync(h->coef_h.p, h->coef.p, M * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
         }
-        FLX_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
         // pinned staging -> the caller's arrays, a slice per host thread
         struct Cp { void* dst; const void* src; size_t bytes; };
         const Cp cps[6] = {{out->lrt_chisq, h->chisq_h.p, M * sizeof(double)}, {out->pval, h->pval_h.p, M * sizeof(double)},
