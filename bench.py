@@ -210,8 +210,8 @@ def stage_roofline(w, acc, steps, int8_path):
         put("K1q decode_i8", M * (raw + n256), "GB/s", acc["ms_decode"], hbm, "hbm")
         passes = max(1, int(round(acc.get("int8_passes", steps) / steps)))
         put("K2q qf_i8 (g'C V^-1 C g, 6 planes x %d pass units)" % passes, 6.0 * n * n * M * passes, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
-        put("K4q-A + K3b (u, b, fit, LRT)", M * (n256 * 2.0) * s, "GB/s", acc["ms_fit"], hbm, "hbm")
-        put("K4q-B perm contraction (6 planes)", 6.0 * 2 * n * P * M * s, "TFLOP/s", acc["ms_perm"], i8_peak()[0], "tensor(i8)")
+        put("K4q (u, b, b* for all seeds, 6 planes) + K3b", 6.0 * 2 * n * (c + 1 + P) * M * s, "TFLOP/s", acc["ms_fit"], i8_peak()[0], "tensor(i8)")
+        put("perm_reduce (b*' Sm b* / RSS_f*, max per seed)", 8.0 * M * s * P, "GB/s", acc["ms_perm"], hbm, "hbm")
     else:
         put("K1 decode_2bit_tile", M * (raw + 8.0 * n128 * s), "GB/s", acc["ms_decode"], hbm, "hbm")
         put("K2 whiten_tile (DMMA)", float(s) * n * n * M, "TFLOP/s", acc["ms_whiten"], fp64_peak()[0], "tensor(f64)")

@@ -140,9 +140,9 @@ struct flx_handle {
         std::vector<QfPass> passes;     // one K2q launch each
         int8_t slot_a[8][8]{}, slot_b[8][8]{};
     } plan;
-    DevBuf<int8_t> T8[4], X8, GA8[2], GB8[2];      // T8[a * NG + b]: digit planes of tril(C_a V^-1 C_b)
-    DevBuf<double> rowscale[4], qf_part, GA_scale[2], GB_scale[2], cvec_d, bst;
-    int NB_A = 16, NB_B = 16, ntilesB = 0;
+    DevBuf<int8_t> T8[4], X8, G8[2];               // T8[a * NG + b]: digit planes of tril(C_a V^-1 C_b) / of C_a V^-1 C_b; G8[a]: of C_a L^-T [Qc | r | R_f]
+    DevBuf<double> rowscale[4], qf_part, G_scale[2], cvec_d, ub, Hd;
+    int NB_G = 16, ntilesG = 1;                    // column blocks of G: ntilesG x NB_G >= cr + 1 + P
     DevBuf<int32_t> refit_flag, out_map_d;
     DevBuf<int> df_count, missing;
 
@@ -751,23 +751,29 @@ static int finalize_setup(flx_handle* h) {
         FLX_TRY(h->cvec_d.ensure(cpad.size()));
         FLX_CUDA_TRY(cudaMemcpy(h->cvec_d.p, cpad.data(), cpad.size() * sizeof(double), cudaMemcpyHostToDevice));
         auto cptr = [&](int gq) -> const double* { return pl.ones[gq] ? nullptr : h->cvec_d.p + (size_t)gq * n_pad; };
-        // H = L^-T [Qc | r]  (n x (cr+1)), stored row-major padded like Qc
+        // H = L^-T [Qc | r]  (n x (cr+1))
         std::vector<double> Hc((size_t)n * (cr + 1));
         memcpy(Hc.data(), Qc.data(), (size_t)n * cr * sizeof(double));
         memcpy(Hc.data() + (size_t)n * cr, r.data(), (size_t)n * sizeof(double));
-        DevBuf<double> Hd;
-        FLX_TRY(Hd.ensure(Hc.size()));
-        FLX_CUDA_TRY(cudaMemcpyAsync(Hd.p, Hc.data(), Hc.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, cr + 1, &one, h->Zdense.p, (int)n, Hd.p, (int)n, Hd.p, (int)n));
-        // digit planes of C_g H for K4q pass A (u = Qc' w, b = r' w), one set per scale group
-        h->NB_A = ((cr + 1 + 15) / 16) * 16;
-        for (int gq = 0; gq < pl.NG; gq++) {
-            FLX_TRY(h->GA_scale[gq].ensure(h->NB_A));
-            FLX_TRY(h->GA8[gq].ensure((size_t)h->NKB * h->Q * h->NB_A * 64));
-            FLX_TRY(launch_xg_slice(Hd.p, n, n, cr + 1, h->NB_A, 1, h->Q, h->NKB, cptr(gq), h->GA_scale[gq].p, h->GA8[gq].p, h->stream));
-        }
+        FLX_TRY(h->Hd.ensure(Hc.size()));
+        FLX_CUDA_TRY(cudaMemcpyAsync(h->Hd.p, Hc.data(), Hc.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, cr + 1, &one, h->Zdense.p, (int)n, h->Hd.p, (int)n, h->Hd.p, (int)n));
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
+    // digit planes of G = C_g [H | L^-T R_f] for K4q, one set per scale group; without permutations G = C_g H
+    auto slice_G = [&](const double* G2, int64_t ld2, int P) -> int {
+        const flx_handle::FastPlan& pl = h->plan;
+        const int NC = cr + 1 + P;
+        h->ntilesG = (NC + 79) / 80;
+        h->NB_G = (((NC + h->ntilesG - 1) / h->ntilesG + 15) / 16) * 16;
+        for (int gq = 0; gq < pl.NG; gq++) {
+            FLX_TRY(h->G_scale[gq].ensure((size_t)h->ntilesG * h->NB_G));
+            FLX_TRY(h->G8[gq].ensure((size_t)h->ntilesG * h->NKB * h->Q * h->NB_G * 64));
+            FLX_TRY(launch_xg_slice(h->Hd.p, n, cr + 1, G2, ld2, n, NC, h->NB_G, h->ntilesG, h->Q, h->NKB, pl.ones[gq] ? nullptr : h->cvec_d.p + (size_t)gq * n_pad,
+                                    h->G_scale[gq].p, h->G8[gq].p, h->stream));
+        }
+        return 0;
+    };
 
     // ---- permutation prologue (fit_model.nf:96-101) for all seeds at once
     h->P_pad = 0; h->NP = 0;
@@ -826,15 +832,7 @@ static int finalize_setup(flx_handle* h) {
         if (h->fast) {
             // int8 path: the contraction runs against the raw genotypes, b* = x' (L^-T r*): digit planes of L^-T R_f
             FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)n, P, &one, h->Zdense.p, (int)n, UE.p, (int)n_pad, UE.p, (int)n_pad));
-            h->ntilesB = (P + 79) / 80;
-            h->NB_B = (((P + h->ntilesB - 1) / h->ntilesB + 15) / 16) * 16;
-            inv_len = std::max<int64_t>(inv_len, (int64_t)h->ntilesB * h->NB_B);
-            for (int gq = 0; gq < h->plan.NG; gq++) {
-                FLX_TRY(h->GB_scale[gq].ensure((size_t)h->ntilesB * h->NB_B));
-                FLX_TRY(h->GB8[gq].ensure((size_t)h->ntilesB * h->NKB * h->Q * h->NB_B * 64));
-                FLX_TRY(launch_xg_slice(UE.p, n, n_pad, P, h->NB_B, h->ntilesB, h->Q, h->NKB, h->plan.ones[gq] ? nullptr : h->cvec_d.p + (size_t)gq * n_pad,
-                                        h->GB_scale[gq].p, h->GB8[gq].p, h->stream));
-            }
+            FLX_TRY(slice_G(UE.p, n_pad, P));
         }
         std::vector<double> rssf(P), rss0(P);
         FLX_CUDA_TRY(cudaMemcpyAsync(rssf.data(), rssf_d.p, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -853,6 +851,7 @@ static int finalize_setup(flx_handle* h) {
         FLX_CUDA_TRY(cudaMemcpy(h->lrs0p.p, lr.data(), P * sizeof(double), cudaMemcpyHostToDevice));
         std::vector<double>().swap(h->U1_copy);
     }
+    if (h->fast && !(h->have_perm && h->P > 0)) FLX_TRY(slice_G(nullptr, 0, 0));
     if (h->fast) {
         // V^-1 = L^-T L^-1 one 256-row tile at a time (a plain library GEMM over the non-zero k range of the triangular
         // factor), each tile cut into the digit planes of tril(C_a V^-1 C_b): no second dense n x n matrix at any n
@@ -918,8 +917,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         size_t free_b = 0, total_b = 0;
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_tile = (size_t)h->plan.NA * h->NKB * 8192 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 +
-                                ((do_perm && h->s > 1) ? (size_t)h->s * 128 * h->ntilesB * h->NB_B * 8 : 0) + (size_t)128 * 40 * 8 * (h->s + 2);
-        const size_t have = free_b + h->X8.cap + h->qf_part.cap * 8 + h->bst.cap * 8;     // what this handle already holds is reusable
+                                (size_t)h->s * 128 * h->ntilesG * h->NB_G * 8 + (size_t)128 * 40 * 8 * (h->s + 2);
+        const size_t have = free_b + h->X8.cap + h->qf_part.cap * 8 + h->ub.cap * 8;     // what this handle already holds is reusable
         int mult = 4;
         while (mult > 1 && (size_t)mult * h->num_sms * per_tile > have / 4) mult--;
         tiles_per_batch = mult * h->num_sms;
@@ -938,7 +937,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const int64_t bpv = h->bpv;
     const int nsym = h->s * (h->s + 1) / 2;
     const int cr = h->cr;
-    const int crp = use_fast ? h->NB_A : gram_padded_width(cr);
+    const int crp = gram_padded_width(cr);
     constexpr int KS_MAX = 32;
     const bool decode_only = (X_out_dense != nullptr) || (codes_out != nullptr);
 
@@ -951,13 +950,13 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     const size_t tile_elems = (size_t)h->KC * CHUNK;
     if (!use_fast || decode_only) FLX_TRY(h->X.ensure((size_t)tiles_per_batch * tile_elems));
     const size_t x8_stride = (size_t)tiles_per_batch * h->NKB * 8192;
-    const int64_t ldp = (int64_t)h->ntilesB * h->NB_B;
+    const int64_t ldg = (int64_t)h->ntilesG * h->NB_G;     // row length of the K4q output: u (cr), b, b* (P), padding
     if (!decode_only) {
         if (!use_fast) FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
         if (use_fast) {
             FLX_TRY(h->X8.ensure(x8_stride * h->plan.NA));
             FLX_TRY(h->qf_part.ensure((size_t)h->plan.nslots * h->T256 * h->Q * snps_per_batch));
-            if (do_perm && h->s > 1) FLX_TRY(h->bst.ensure((size_t)h->s * snps_per_batch * ldp));
+            FLX_TRY(h->ub.ensure((size_t)h->s * snps_per_batch * ldg));
             FLX_TRY(h->refit_flag.ensure(M_total));
         }
         FLX_TRY(h->n_part.ensure((size_t)KS_MAX * snps_per_batch * h->s));
@@ -1194,14 +1193,16 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 h->stats.launches += 1; h->stats.launches_whiten++;
             }
             mark();  // [3] fit start
-            // K4q pass A per term: u_t = (C_t L^-T Qc)' g_t, b_t = (C_t L^-T r)' g_t against the digit planes of C_t H
+            // K4q per term: u_t = (C_t L^-T Qc)' g_t, b_t = (C_t L^-T r)' g_t and, for every seed, b*_t = (C_t L^-T r*)' g_t in one
+            // launch against the digit planes of C_t [H | L^-T R_f]
             for (int t = 0; t < h->s; t++) {
                 XgArgs xa{};
-                xa.X8 = h->X8.p + h->plan.alp[t] * x8_stride; xa.G8 = h->GA8[h->plan.grp[t]].p; xa.colscale = h->GA_scale[h->plan.grp[t]].p;
+                xa.X8 = h->X8.p + h->plan.alp[t] * x8_stride; xa.G8 = h->G8[h->plan.grp[t]].p; xa.colscale = h->G_scale[h->plan.grp[t]].p;
                 for (int i = 0; i < 3; i++) xa.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-                xa.n_items = NJ; xa.NCT = 1; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_A; xa.NC = cr + 1; xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = nkb_live;
-                xa.out = h->u_part.p + (int64_t)t * h->NB_A; xa.ld_out = (int64_t)h->s * h->NB_A;
-                FLX_TRY(launch_xg(xa, 0, h->num_sms, h->stream));
+                xa.n_items = (int64_t)h->ntilesG * NJ; xa.NCT = h->ntilesG; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_G; xa.NC = cr + 1 + (do_perm ? h->P : 0);
+                xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = nkb_live;
+                xa.out = h->ub.p + (int64_t)t * nsnp * ldg; xa.ld_out = ldg;
+                FLX_TRY(launch_xg(xa, h->num_sms, h->stream));
                 h->stats.launches += 1;
             }
             ga.KS = 1;
@@ -1222,7 +1223,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             FLX_CUDA_TRY(cudaMemsetAsync(h->snp_sm.p, 0, (size_t)snps_per_batch * nsym * sizeof(double), h->stream));
         }
         SolveArgs sa{};
-        sa.n_part = h->n_part.p; sa.u_part = h->u_part.p; sa.a_part = h->a_part.p; sa.b_part = h->b_part.p; sa.KS = ga.KS; sa.crp = crp;
+        sa.n_part = h->n_part.p; sa.u_part = use_fast ? h->ub.p : h->u_part.p; sa.a_part = h->a_part.p; sa.b_part = h->b_part.p; sa.KS = ga.KS; sa.crp = crp;
+        sa.u_term_stride = nsnp * ldg; sa.u_ld = ldg;
         sa.nsnp = nsnp; sa.out_offset = s0;
         sa.out_map = out_map_host ? h->out_map_d.p + s0 : nullptr;
         sa.chisq = h->chisq.p; sa.pval = h->pval.p; sa.df = h->df.p; sa.rank = h->rank.p; sa.pivot = h->pivot.p; sa.coef = h->coef.p;
@@ -1248,27 +1250,13 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         }
         mark();  // [4] perm start
         if (do_perm && use_fast) {
-            // K4q pass B: b*_t = g_t' (C_t L^-T r*) for every seed on the i8 pipe; one term: fused max-ratio epilogue,
-            // several terms: store b* per term, then one reduction pass forms b*' Sm b* / RSS_f
-            for (int t = 0; t < h->s; t++) {
-                XgArgs xb{};
-                xb.X8 = h->X8.p + h->plan.alp[t] * x8_stride; xb.G8 = h->GB8[h->plan.grp[t]].p; xb.colscale = h->GB_scale[h->plan.grp[t]].p;
-                for (int i = 0; i < 3; i++) xb.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-                xb.n_items = (int64_t)h->ntilesB * NJ; xb.NCT = h->ntilesB; xb.nsnp = nsnp; xb.NJ = NJ; xb.NB = h->NB_B; xb.NC = h->P; xb.Q = h->Q; xb.NKB = h->NKB;
-                xb.NKB_live = (int)((h->n + 63) / 64);
-                xb.snp_df = h->snp_df.p; xb.snp_sm = h->snp_sm.p; xb.perm_inv_rss = h->inv_rss.p; xb.perm_maxratio = h->maxratio.p;
-                xb.out = h->bst.p + (int64_t)t * nsnp * ldp; xb.ld_out = ldp;
-                FLX_TRY(launch_xg(xb, h->s == 1 ? 1 : 0, h->num_sms, h->stream));
-                h->stats.launches++;
-            }
-            if (h->s > 1) {
-                PermReduceArgs pr{};
-                pr.bst = h->bst.p; pr.term_stride = nsnp * ldp; pr.ldp = ldp;
-                pr.snp_df = h->snp_df.p; pr.snp_sm = h->snp_sm.p; pr.perm_inv_rss = h->inv_rss.p; pr.perm_maxratio = h->maxratio.p;
-                pr.nsnp = nsnp; pr.P = h->P; pr.P_pad = h->P_pad; pr.s = h->s;
-                FLX_TRY(launch_perm_reduce(pr, h->stream));
-                h->stats.launches++;
-            }
+            // b*' Sm b* / RSS_f* per (SNP, seed) from the stored b*_t, running max per (seed, df)
+            PermReduceArgs pr{};
+            pr.bst = h->ub.p + (cr + 1); pr.term_stride = nsnp * ldg; pr.ldp = ldg;
+            pr.snp_df = h->snp_df.p; pr.snp_sm = h->snp_sm.p; pr.perm_inv_rss = h->inv_rss.p; pr.perm_maxratio = h->maxratio.p;
+            pr.nsnp = nsnp; pr.P = h->P; pr.P_pad = h->P_pad; pr.s = h->s;
+            FLX_TRY(launch_perm_reduce(pr, h->stream));
+            h->stats.launches++;
         } else if (do_perm) {
             GemmArgs gp{};
             gp.A = h->W.p; gp.B = h->Rpk.p; gp.NJ = NJ; gp.NP = h->NP; gp.KC = h->KC; gp.n_items = (int64_t)NJ * h->NP;

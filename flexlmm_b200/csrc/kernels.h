@@ -57,14 +57,13 @@ struct XgArgs {
     int64_t nsnp;
     int NJ, NB, NC, Q, NKB, NKB_live;
     int NCT;                  // column blocks (n_items = NJ * NCT)
-    // MODE 0
-    double* out; int64_t ld_out;
-    // MODE 1
-    const int32_t* snp_df; const double* snp_sm; const double* perm_inv_rss; double* perm_maxratio;
+    double* out; int64_t ld_out;   // out[snp * ld_out + col]
 };
-int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st);
-// rowmul (optional, [n]): the planes are those of diag(rowmul) G
-int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul, double* colscale, int8_t* G8, cudaStream_t st);
+int launch_xg(const XgArgs& g, int num_sms, cudaStream_t st);
+// columns 0..c1-1 come from G (ld), columns c1..NC-1 from G2 (ld2) — [Qc | r] and R_f live in different buffers.
+// rowmul (optional, [n]): the planes are those of diag(rowmul) [G | G2]
+int launch_xg_slice(const double* G, int64_t ld, int c1, const double* G2, int64_t ld2, int64_t n, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul,
+                    double* colscale, int8_t* G8, cudaStream_t st);
 // Vtile: rows 256 I .. 256 I + 255 of V^-1 (column-major, ld), columns 0 .. row (full: all n columns).  ca, cb (optional, [n]):
 // the planes are those of tril(diag(ca) V^-1 diag(cb)) with half diagonal, or of the full matrix diag(ca) V^-1 diag(cb)
 int launch_qf_slice(const double* Vtile, int64_t n, int64_t ld, int I, int T256, int Q, const double* ca, const double* cb, int full, double* rowscale, int8_t* T8,
@@ -150,7 +149,8 @@ struct SolveArgs {
     int* df_count;            // [9] run-wide count of SNPs per lrt_df (1..8)
     const int32_t* out_map;   // optional: run-wide output slot of batch SNP q (refit pass), else out_offset + q
     // fast (int8 quadratic form) mode: A_raw[t][v] = S[slot_a[t][v]] + S[slot_b[t][v]], S[slot] = sum of the qf_nparts partials
-    // of K2q pass `slot` (qf_part: [slot][qf_nparts][nsnp]); u, b from the K4q-A sweeps (u_part: [snp][s][crp], KS = 1)
+    // of K2q pass `slot` (qf_part: [slot][qf_nparts][nsnp]); u_t (cr values) and b_t from K4q: u_part[t * u_term_stride + snp * u_ld + j]
+    int64_t u_term_stride, u_ld;
     int fast;
     double refit_thr;         // re-fit in FP64 when a Cholesky pivot <= refit_thr * A_raw[t][t]
     const double* qf_part; int qf_nparts;

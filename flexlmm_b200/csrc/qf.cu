@@ -424,10 +424,9 @@ int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st) {
 }
 
 // ================================================================================================
-// K4q: X8 (128 SNPs x n, int8) against a column block of G = L^-T [Qc | r | R_f] split into Q digit planes:
-//      out[snp][col] = x_snp' g_col  exactly (up to the 2^-48 truncation of G below each column's power-of-two scale).
-//   MODE 0: store the values (u = Qc' w and b = r' w for K3b).
-//   MODE 1: permutation epilogue — ratio = val^2 * Sm[snp] / RSS_f[col], running max over SNPs per permutation.
+// K4q: X8 (128 SNPs x n, int8) against a column block of G = C L^-T [Qc | r | R_f] split into Q digit planes:
+//      out[snp][col] = g_snp' G_col  exactly (up to the 2^-48 truncation of G below each column's power-of-two scale):
+//      u = Qc' w (cr columns), b = r' w, and b* for every permutation seed in ONE pass over the genotype tile per column block.
 // Same pipeline as K2q; the Q planes of a column block are accumulated side by side in TMEM (Q * NB <= 512 columns).
 // ================================================================================================
 constexpr int XG_MAX_NB = 80;
@@ -435,7 +434,6 @@ constexpr int XG_STAGES = 5;
 constexpr int XG_STAGE_MAX = QF_A_BYTES + 6 * XG_MAX_NB * QF_KB;     // 8 KB + 30 KB
 constexpr int XG_SMEM = XG_STAGES * XG_STAGE_MAX + 256;
 
-template <int MODE>
 __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XG_STAGES * XG_STAGE_MAX);
@@ -520,8 +518,6 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             const int J = (int)(item / g.NCT), ct = (int)(item % g.NCT);
             const int64_t snp = (int64_t)J * 128 + snp_l;
-            double sm = 0.0;
-            if (MODE == 1 && snp < g.nsnp && g.snp_df[snp] > 0) sm = g.snp_sm[snp];
             qbar_wait(acc_full, aphase);
             aphase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
@@ -541,23 +537,12 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
                     for (int qq = 2; qq >= 0; qq--) {
                         if (2 * qq < Q) {
                             const long long comb = (long long)(int)v[2 * qq][j] * 256 + ((2 * qq + 1 < Q) ? (long long)(int)v[2 * qq + 1][j] : 0);
-                            val += (double)comb * g.pair_scale[qq];
+                            // |comb| < 2^40: bias trick instead of I2F (16/clk/SM)
+                            val += (__longlong_as_double(0x4330000000000000LL + (comb + (1LL << 51))) - 6755399441055744.0) * g.pair_scale[qq];
                         }
                     }
                     val *= g.colscale[col];
-                    if (MODE == 0) {
-                        if (snp < g.nsnp && col < g.NC) g.out[snp * g.ld_out + col] = val;
-                    } else {
-                        // ratio of this (SNP, permutation); max over the 32 SNPs of the warp, one atomic per column
-                        double ratio = fmax(val * val * sm * g.perm_inv_rss[col], 0.0);
-                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 16));
-                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 8));
-                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 4));
-                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 2));
-                        ratio = fmax(ratio, __shfl_xor_sync(0xffffffffu, ratio, 1));
-                        if (lane == 0 && ratio > 0.0)
-                            atomicMax(reinterpret_cast<unsigned long long*>(&g.perm_maxratio[col]), (unsigned long long)__double_as_longlong(ratio));
-                    }
+                    if (snp < g.nsnp && col < g.NC) g.out[snp * g.ld_out + col] = val;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -569,19 +554,17 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st) {
+int launch_xg(const XgArgs& g, int num_sms, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(xg_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, XG_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(xg_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, XG_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(xg_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XG_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(xg): %s", cudaGetErrorString(e)); return -3; }
         configured = true;
     }
     if (g.NB % 16 != 0 || g.NB < 16 || g.NB > XG_MAX_NB || g.Q < 1 || g.Q > 6) { set_error("xg: bad column block %d / planes %d", g.NB, g.Q); return -1; }
     const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
     if (grid <= 0) return 0;
-    if (mode == 0) xg_i8_kernel<0><<<(unsigned)grid, XG_THREADS, XG_SMEM, st>>>(g);
-    else xg_i8_kernel<1><<<(unsigned)grid, XG_THREADS, XG_SMEM, st>>>(g);
+    xg_i8_kernel<<<(unsigned)grid, XG_THREADS, XG_SMEM, st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("xg launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
@@ -589,13 +572,15 @@ int launch_xg(const XgArgs& g, int mode, int num_sms, cudaStream_t st) {
 
 // ---- setup: G (n x NC dense, column-major) -> per-column power-of-two scale + Q digit planes, packed per column block:
 //      G8[col block ct][kb][plane q][k16 chunk 4][col group NB/8][8 cols][16 B]
-__global__ void xg_colscale_kernel(const double* __restrict__ G, int64_t n, int64_t ld, int NC, int NC_pad, const double* __restrict__ rowmul,
-                                   double* __restrict__ colscale) {
+__global__ void xg_colscale_kernel(const double* __restrict__ G, int64_t ld, int c1, const double* __restrict__ G2, int64_t ld2, int64_t n, int NC,
+                                   const double* __restrict__ rowmul, double* __restrict__ colscale) {
     const int col = blockIdx.x;
     __shared__ double sh[8];
     double m = 0.0;
-    if (col < NC)
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(G[i + (int64_t)col * ld] * (rowmul ? rowmul[i] : 1.0)));
+    if (col < NC) {
+        const double* src = (col < c1) ? G + (int64_t)col * ld : G2 + (int64_t)(col - c1) * ld2;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(src[i] * (rowmul ? rowmul[i] : 1.0)));
+    }
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
     __syncthreads();
@@ -603,11 +588,11 @@ __global__ void xg_colscale_kernel(const double* __restrict__ G, int64_t n, int6
         for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmax(m, sh[w]);
         colscale[col] = digit_scale(m);
     }
-    (void)NC_pad;
 }
 
-__global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __restrict__ G, int64_t n, int64_t ld, int NC, int NB, int Q, int NKB,
-                                                           const double* __restrict__ rowmul, const double* __restrict__ colscale, int8_t* __restrict__ G8) {
+__global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __restrict__ G, int64_t ld, int c1, const double* __restrict__ G2, int64_t ld2, int64_t n,
+                                                           int NC, int NB, int Q, int NKB, const double* __restrict__ rowmul,
+                                                           const double* __restrict__ colscale, int8_t* __restrict__ G8) {
     const int ct = blockIdx.y, kb = blockIdx.x;
     const int plane_bytes = NB * QF_KB;
     int8_t* blk = G8 + ((int64_t)ct * NKB + kb) * Q * plane_bytes;
@@ -617,11 +602,12 @@ __global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __rest
         const int cl = e % NB, ch = e / NB;
         const int col = ct * NB + cl;
         const double inv = (col < NC) ? 1.0 / colscale[col] : 0.0;
+        const double* src = (col < c1) ? G + (int64_t)col * ld : G2 + (int64_t)(col - c1) * ld2;
         uint32_t w[6][4];
         for (int q = 0; q < 6; q++) w[q][0] = w[q][1] = w[q][2] = w[q][3] = 0;
         for (int b = 0; b < 16; b++) {
             const int64_t k = (int64_t)kb * QF_KB + ch * 16 + b;
-            const double t = (col < NC && k < n) ? G[k + (int64_t)col * ld] * (rowmul ? rowmul[k] : 1.0) : 0.0;
+            const double t = (col < NC && k < n) ? src[k] * (rowmul ? rowmul[k] : 1.0) : 0.0;
             long long ri = __double2ll_rn(t * inv * up);
             for (int q = Q - 1; q >= 0; q--) {
                 const long long d = ((ri + 128) & 255) - 128;
@@ -637,10 +623,10 @@ __global__ void __launch_bounds__(256) xg_slice_pack_kernel(const double* __rest
     }
 }
 
-int launch_xg_slice(const double* G, int64_t n, int64_t ld, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul, double* colscale, int8_t* G8,
-                    cudaStream_t st) {
-    xg_colscale_kernel<<<(unsigned)(NB * ntiles), 256, 0, st>>>(G, n, ld, NC, NB * ntiles, rowmul, colscale);
-    xg_slice_pack_kernel<<<dim3((unsigned)NKB, (unsigned)ntiles), 256, 0, st>>>(G, n, ld, NC, NB, Q, NKB, rowmul, colscale, G8);
+int launch_xg_slice(const double* G, int64_t ld, int c1, const double* G2, int64_t ld2, int64_t n, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul,
+                    double* colscale, int8_t* G8, cudaStream_t st) {
+    xg_colscale_kernel<<<(unsigned)(NB * ntiles), 256, 0, st>>>(G, ld, c1, G2, ld2, n, NC, rowmul, colscale);
+    xg_slice_pack_kernel<<<dim3((unsigned)NKB, (unsigned)ntiles), 256, 0, st>>>(G, ld, c1, G2, ld2, n, NC, NB, Q, NKB, rowmul, colscale, G8);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("xg_slice launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;

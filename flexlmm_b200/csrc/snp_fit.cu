@@ -325,12 +325,12 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             for (; p < a.qf_nparts; p++) acc += __ldg(qp + (int64_t)p * a.nsnp);
             S[sl] = acc;
         }
-        const double* __restrict__ ub = a.u_part + snp * s * a.crp;     // [t][crp]: u_t (cr values) then b_t
+        const double* __restrict__ ub = a.u_part + snp * a.u_ld;        // term t at + t * u_term_stride: u_t (cr values) then b_t
         for (int t = 0; t < s; t++) {
-            bq[t] = __ldg(ub + t * a.crp + cr);
+            bq[t] = __ldg(ub + t * a.u_term_stride + cr);
             for (int v = t; v < s; v++) {
                 double uu = 0.0;
-                for (int j = 0; j < cr; j++) uu += __ldg(ub + t * a.crp + j) * __ldg(ub + v * a.crp + j);
+                for (int j = 0; j < cr; j++) uu += __ldg(ub + t * a.u_term_stride + j) * __ldg(ub + v * a.u_term_stride + j);
                 const double araw = S[a.slot_a[t][v]] + (a.slot_b[t][v] >= 0 ? S[a.slot_b[t][v]] : 0.0);
                 if (v == t) nrm2[t] = araw;
                 A[t][v] = A[v][t] = araw - uu;
@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
             const int t = -kind - 1;
             for (int i = 0; i < cr; i++) {
                 double acc = 0.0;
-                for (int p = 0; p < a.KS; p++) acc += a.u_part[(((int64_t)p * a.nsnp + snp) * s + t) * a.crp + i];
+                if (a.fast) acc = a.u_part[t * a.u_term_stride + snp * a.u_ld + i];
+                else for (int p = 0; p < a.KS; p++) acc += a.u_part[(((int64_t)p * a.nsnp + snp) * s + t) * a.crp + i];
                 col[i] = acc;
             }
             for (int i = 0; i <= t; i++) col[cr + i] = Rs[i][t];
@@ -573,42 +574,65 @@ int launch_snp_solve(const SolveArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // int8 route with s > 1 terms: K4q stores b*_t = g_t' (L^-T r*_p) per term; this pass forms b*' Sm b* / RSS_f per (SNP, permutation)
 // and keeps the running max over SNPs per (df, permutation).  HBM bound: one read of s * nsnp * P doubles.
-__global__ void __launch_bounds__(128) perm_reduce_kernel(const PermReduceArgs a) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t q0 = (int64_t)blockIdx.y * 64;
-    const int64_t q1 = min(q0 + 64, a.nsnp);
-    const int s = a.s, nsym = s * (s + 1) / 2;
-    __shared__ double sm_s[64][MAXS * (MAXS + 1) / 2];
-    __shared__ int df_s[64];
-    for (int e = threadIdx.x; e < 64; e += blockDim.x) df_s[e] = (q0 + e < q1) ? a.snp_df[q0 + e] : 0;
-    for (int e = threadIdx.x; e < 64 * nsym; e += blockDim.x) {
-        const int qi = e / nsym, c = e % nsym;
-        sm_s[qi][c] = (q0 + qi < q1) ? a.snp_sm[(q0 + qi) * nsym + c] : 0.0;
-    }
-    __syncthreads();
-    if (p >= a.P) return;
-    const double inv = a.perm_inv_rss[p];
-    double mx[MAXS];
+constexpr int PR_LANES = 8;        // SNP lanes per block (x 128 permutation lanes)
+constexpr int PR_SNPS = 512;       // SNPs per block
+template <int S>
+__global__ void __launch_bounds__(128 * PR_LANES) perm_reduce_kernel(const PermReduceArgs a) {
+    const int pl = threadIdx.x & 127, y = threadIdx.x >> 7;
+    const int p = blockIdx.x * 128 + pl;
+    const int64_t q0 = (int64_t)blockIdx.y * PR_SNPS;
+    const int64_t q1 = min(q0 + PR_SNPS, a.nsnp);
+    constexpr int s = S, nsym = S * (S + 1) / 2;      // compile-time: z, mx and the quadratic form stay in registers
+    __shared__ double red[PR_LANES][128];
+    const bool live = p < a.P;
+    const double inv = live ? a.perm_inv_rss[p] : 0.0;
+    double mx[S];
+#pragma unroll
     for (int t = 0; t < s; t++) mx[t] = 0.0;
-    for (int64_t q = q0; q < q1; q++) {
-        const int df = df_s[q - q0];
-        if (df <= 0) continue;
-        double z[MAXS];
-        for (int t = 0; t < s; t++) z[t] = a.bst[(int64_t)t * a.term_stride + q * a.ldp + p];
-        double quad = 0.0;
-        int c = 0;
-        for (int t = 0; t < s; t++)
-            for (int u = t; u < s; u++) { quad += ((u == t) ? 1.0 : 2.0) * sm_s[q - q0][c] * z[t] * z[u]; c++; }
-        const double ratio = fmax(quad * inv, 0.0);
-        mx[df - 1] = fmax(mx[df - 1], ratio);
+    // a warp reads one contiguous run of permutations of one SNP; Sm and df are warp-uniform (broadcast loads); no
+    // data-dependent branch, so the loads of several SNPs are in flight at once
+    if (live) {
+#pragma unroll 4
+        for (int64_t q = q0 + y; q < q1; q += PR_LANES) {
+            const int df = __ldg(a.snp_df + q);
+            double z[S];
+#pragma unroll
+            for (int t = 0; t < s; t++) z[t] = __ldg(a.bst + (int64_t)t * a.term_stride + q * a.ldp + p);
+            double quad = 0.0;
+            int c = 0;
+#pragma unroll
+            for (int t = 0; t < s; t++)
+#pragma unroll
+                for (int u = t; u < s; u++) { quad += ((u == t) ? 1.0 : 2.0) * __ldg(a.snp_sm + q * nsym + c) * z[t] * z[u]; c++; }
+            const double ratio = fmax(quad * inv, 0.0);      // Sm is zero for df = 0 and for SNPs handed to the FP64 refit
+#pragma unroll
+            for (int t = 0; t < s; t++) mx[t] = (df == t + 1) ? fmax(mx[t], ratio) : mx[t];
+        }
     }
-    for (int t = 0; t < s; t++)
-        if (mx[t] > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&a.perm_maxratio[(int64_t)t * a.P_pad + p]), (unsigned long long)__double_as_longlong(mx[t]));
+    // one atomic per (permutation, df) per block: with 148 blocks per batch the hot addresses see little contention
+#pragma unroll
+    for (int t = 0; t < s; t++) {
+        red[y][pl] = mx[t];
+        __syncthreads();
+        if (y == 0 && live) {
+            double v = red[0][pl];
+            for (int l = 1; l < PR_LANES; l++) v = fmax(v, red[l][pl]);
+            if (v > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&a.perm_maxratio[(int64_t)t * a.P_pad + p]), (unsigned long long)__double_as_longlong(v));
+        }
+        __syncthreads();
+    }
 }
 
 int launch_perm_reduce(const PermReduceArgs& a, cudaStream_t st) {
     if (a.P <= 0 || a.nsnp <= 0) return 0;
-    perm_reduce_kernel<<<dim3((unsigned)((a.P + 127) / 128), (unsigned)((a.nsnp + 63) / 64)), 128, 0, st>>>(a);
+    const dim3 grid((unsigned)((a.P + 127) / 128), (unsigned)((a.nsnp + PR_SNPS - 1) / PR_SNPS));
+    switch (a.s) {
+        case 1: perm_reduce_kernel<1><<<grid, 128 * PR_LANES, 0, st>>>(a); break;
+        case 2: perm_reduce_kernel<2><<<grid, 128 * PR_LANES, 0, st>>>(a); break;
+        case 3: perm_reduce_kernel<3><<<grid, 128 * PR_LANES, 0, st>>>(a); break;
+        case 4: perm_reduce_kernel<4><<<grid, 128 * PR_LANES, 0, st>>>(a); break;
+        default: set_error("perm_reduce: s = %d terms not supported on the int8 route", a.s); return -1;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("perm_reduce launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
