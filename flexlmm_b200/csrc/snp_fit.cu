@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     bool alive[MAXS];
     bool refit = false;
     if (a.fast) {
-        // A_raw[t][v] = g_t' V^-1 g_v from the int8 passes (K2q), u_t = (L^-T Qc)' g_t and b_t = (L^-T r)' g_t from K4q-A
+        // A_raw[t][v] = g_t' V^-1 g_v from the int8 passes (K2q), u_t = (L^-T Qc)' g_t and b_t = (L^-T r)' g_t from K4q
         double S[16];    // at most 12 forms: two scales x two triples on either side
         int nslots = 0;
         for (int t = 0; t < s; t++)
