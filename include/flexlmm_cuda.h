@@ -66,10 +66,10 @@ typedef struct {
 /* Timings and counters of the last flx_run*, for bench.py (device times from CUDA events, ms). */
 typedef struct {
     double ms_total;           /* whole flx_run* call on the device stream                             */
-    double ms_decode;          /* K1  decode_2bit_tile                                                 */
+    double ms_decode;          /* K0/K1 pgen_expand + decode_2bit_tile / decode_i8_tile                */
     double ms_whiten;          /* K2  whiten_tile (L^-1 . X)  or  K2q int8 quadratic form                      */
-    double ms_fit;             /* K3  snp_gram + snp_solve                                             */
-    double ms_perm;            /* K4  perm_contract_minp                                               */
+    double ms_fit;             /* K3  snp_gram + snp_solve; int8 route: K4q (u, b, b*) + snp_solve     */
+    double ms_perm;            /* K4  perm_contract_minp; int8 route: perm_reduce                      */
     double ms_h2d;             /* host->device copies inside the call                                  */
     double ms_d2h;             /* device->host copies inside the call                                  */
     int64_t launches;          /* kernels launched by this library inside the call                     */

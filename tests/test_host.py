@@ -26,6 +26,29 @@ def test_library_exports_every_declared_symbol(fx):
     assert sorted(fx._capi.EXPORTS) == names
 
 
+def test_ctypes_structs_mirror_the_header():
+    """The Python mirror of the C ABI structs must list the header's fields in the header's order (a drifted flx_stats would
+    silently shift every counter bench.py reads)."""
+    import re
+    from flexlmm_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "flexlmm_cuda.h")).read()
+
+    def fields(struct_name):
+        end = re.search(r"\}\s*" + struct_name + r"\s*;", hdr).start()
+        body = hdr[hdr.rindex("typedef struct", 0, end):end].split("{", 1)[1]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                out.append(re.sub(r"[\*\s]", " ", decl).split()[-1])
+        return out
+
+    assert fields("flx_config") == [f for f, _ in _capi.FlxConfig._fields_]
+    assert fields("flx_snp_out") == [f for f, _ in _capi.FlxSnpOut._fields_]
+    assert fields("flx_stats") == [f for f, _ in _capi.FlxStats._fields_]
+
+
 def test_version_and_error_string(fx):
     L = fx.load()
     assert b"sm_100a" in L.flx_version()
