@@ -361,6 +361,33 @@ def test_empty_and_single_variant(fx, big):
         fm.run(np.array([6001], dtype=np.int32))
 
 
+def test_default_batching_ramp_refit_and_staged_results(fx):
+    """80,000 SNPs through the default int8 batching (ramp 18,944 / 37,888 / 75,776-SNP batches from host memory, per-batch
+    result copies into pinned staging, FP64 refit of the monomorphic SNPs scattered over the batches) must reproduce, bit for
+    bit, the run with one tile per SM and the run from HBM-resident genotypes."""
+    from flexlmm_b200 import synth
+    n, M = 200, 80000
+    t = synth.task(n, M, model="additive", P=4, seed=41)
+    c = t["codes_raw"]
+    c[::997] = 0                                   # monomorphic: refit in every batch
+    c[5::1499] = 2
+    t["packed"] = synth.pack_2bit(c)
+    vi = np.arange(1, M + 1, dtype=np.int32)
+    res = []
+    for bt, resident in ((0, False), (148, False), (0, True)):
+        with make(fx, t, perm=True, batch_tiles=bt) as fm:
+            if resident:
+                fm.make_resident()
+            r = fm.run(vi)
+            st = fm.stats()
+            assert st["int8_path"] == 1 and st["refit_snps"] >= M // 997
+            res.append(r)
+    for r in res[1:]:
+        for k2 in ("lrt_chisq", "pval", "lrt_df", "rank", "pivot", "coef", "min_pval"):
+            assert np.array_equal(res[0][k2], r[k2], equal_nan=True), k2
+    assert (res[0]["lrt_df"][::997] == 0).all() and np.isnan(res[0]["pval"][::997]).all()
+
+
 def test_run_reuses_result_arrays(fx, big):
     """run(out=previous result) overwrites the caller's arrays in place (no new allocations on a streaming caller's path)."""
     t, fm, r = big
