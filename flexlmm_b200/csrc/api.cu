@@ -6,6 +6,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -111,8 +112,7 @@ struct flx_handle {
     bool perm_implicit = false;   // U1 is the implicit Householder complement of the null design
     NullFit nullfit;
     std::vector<double> y_pred, e_p;
-    const double* U1_host = nullptr;  // caller-owned until finalise
-    std::vector<double> U1_copy;
+    DevBuf<double> U1_d;              // explicit U1 (n x m), device copy made by flx_set_perm, freed after finalisation
     int64_t m = 0;
     std::vector<int32_t> seeds;
     int P = 0;
@@ -419,7 +419,10 @@ extern "C" int flx_set_perm(flx_handle* h, const double* y_pred, const double* U
     if (h->n <= 0) { set_error("flx_set_perm: call flx_set_whitening first"); return FLX_ERR_STATE; }
     h->y_pred.assign(y_pred, y_pred + h->n);
     h->e_p.assign(e_p, e_p + m);
-    h->U1_copy.assign(U1, U1 + (size_t)h->n * m);  // R owns U1 only for the duration of the call
+    // R owns U1 only for the duration of the call: it goes straight to the device (no host copy of an n x m matrix)
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    FLX_TRY(h->U1_d.ensure((size_t)h->n * m));
+    FLX_CUDA_TRY(cudaMemcpy(h->U1_d.p, U1, (size_t)h->n * m * sizeof(double), cudaMemcpyHostToDevice));
     h->m = m;
     h->seeds.assign(seeds, seeds + P);
     h->P = P; h->have_perm = true; h->perm_implicit = false; h->dirty = true;
@@ -434,7 +437,7 @@ extern "C" int flx_set_perm_implicit(flx_handle* h, const int32_t* seeds, int32_
     h->y_pred = h->nullfit.fitted;
     h->e_p = h->nullfit.e_p;
     h->m = (int64_t)h->e_p.size();
-    h->U1_copy.clear();
+    h->U1_d.release();
     h->seeds.assign(seeds, seeds + P);
     h->P = P; h->have_perm = true; h->perm_implicit = true; h->dirty = true;
     return FLX_OK;
@@ -572,6 +575,14 @@ static int finalize_setup(flx_handle* h) {
     FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int64_t n = h->n, n_pad = h->n_pad;
     const int k = h->k;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (h->cfg.verbose < 1) return;
+        cudaStreamSynchronize(h->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[flx] setup: %-34s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     // ---- split the design into SNP-independent columns and SNP-dependent terms (fit_model.nf:124-127)
     std::vector<int> const_cols, snp_cols;
     for (int j = 0; j < k; j++) {
@@ -605,6 +616,7 @@ static int finalize_setup(flx_handle* h) {
     }
     FLX_TRY(h->lut.ensure(lut.size()));
     FLX_CUDA_TRY(cudaMemcpy(h->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    lap("design split, lookup tables");
     // ---- whiten the constant columns of the real model, orthonormal basis Qc
     std::vector<double> Cw((size_t)n * std::max(h->ncf, 1));
     if (h->ncf > 0) {
@@ -658,6 +670,7 @@ static int finalize_setup(flx_handle* h) {
     FLX_TRY(h->Qn.ensure(tmp.size()));
     FLX_CUDA_TRY(cudaMemcpy(h->Qn.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
 
+    lap("constant columns, Qc, null basis");
     // ---- int8 quadratic-form path (K2q / K4q): every SNP term must factor as g_t(x) * c_t[sample] with an integer triple
     // |g_t| <= 2 (x itself, I(x==1), ...) and a per-sample scale c_t (1 for main effects, the covariate for x:cov).  Then
     //   A_raw[t][v] = g_t' C_t V^-1 C_v g_v = g_t' T^(t,v) g_v + g_v' T^(v,t) g_t,   T^(a,b) = tril(C_a V^-1 C_b), half diagonal,
@@ -775,6 +788,7 @@ static int finalize_setup(flx_handle* h) {
         return 0;
     };
 
+    lap("int8 plan, H = L^-T [Qc | r]");
     // ---- permutation prologue (fit_model.nf:96-101) for all seeds at once
     h->P_pad = 0; h->NP = 0;
     if (h->have_perm && h->P > 0) {
@@ -792,18 +806,17 @@ static int finalize_setup(flx_handle* h) {
             for (auto& x : th) x.join();
         }
         DevBuf<int32_t> idx_d;
-        DevBuf<double> ep_d, E, U1d, UE, ypred_d, rssf_d, rss0_d;
+        DevBuf<double> ep_d, E, UE, ypred_d, rssf_d, rss0_d;
         FLX_TRY(idx_d.ensure(idx.size()));
         FLX_TRY(ep_d.ensure(m));
         FLX_TRY(E.ensure((size_t)m * P));
-        if (!h->perm_implicit) FLX_TRY(U1d.ensure((size_t)n * m));
         FLX_TRY(UE.ensure((size_t)n_pad * h->P_pad));
         FLX_TRY(ypred_d.ensure(n));
         FLX_TRY(rssf_d.ensure(P));
         FLX_TRY(rss0_d.ensure(P));
         FLX_CUDA_TRY(cudaMemcpyAsync(idx_d.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         FLX_CUDA_TRY(cudaMemcpyAsync(ep_d.p, h->e_p.data(), m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        if (!h->perm_implicit) FLX_CUDA_TRY(cudaMemcpyAsync(U1d.p, h->U1_copy.data(), (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (!h->perm_implicit && !h->U1_d.p) { set_error("flx_run: the permutation inputs were consumed by an earlier setup; call flx_set_perm again"); return FLX_ERR_STATE; }
         FLX_CUDA_TRY(cudaMemcpyAsync(ypred_d.p, h->y_pred.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         FLX_CUDA_TRY(cudaMemsetAsync(UE.p, 0, (size_t)n_pad * h->P_pad * sizeof(double), h->stream));
         const double one = 1.0, zero = 0.0;
@@ -820,7 +833,7 @@ static int finalize_setup(flx_handle* h) {
         } else {
             FLX_TRY(launch_gather_ep(ep_d.p, idx_d.p, m, P, E.p, h->stream));
             // U1 %*% sample(e.p) for every seed: one plain library GEMM (setup, outside the hot loop)
-            FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, U1d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
+            FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, P, (int)m, &one, h->U1_d.p, (int)n, E.p, (int)m, &zero, UE.p, (int)n_pad));
         }
         PermPrepArgs pa{};
         pa.UE = UE.p; pa.y_pred = ypred_d.p; pa.Qc = h->Qc.p; pa.cr = cr; pa.crp = gram_padded_width(cr); pa.Qn = h->Qn.p; pa.cn = h->cn; pa.cnp = gram_padded_width(h->cn);
@@ -849,8 +862,10 @@ static int finalize_setup(flx_handle* h) {
         FLX_TRY(h->minp_d.ensure(P));
         FLX_CUDA_TRY(cudaMemcpy(h->inv_rss.p, inv.data(), inv_len * sizeof(double), cudaMemcpyHostToDevice));
         FLX_CUDA_TRY(cudaMemcpy(h->lrs0p.p, lr.data(), P * sizeof(double), cudaMemcpyHostToDevice));
-        std::vector<double>().swap(h->U1_copy);
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->U1_d.release();
     }
+    lap("permutation prologue, G planes");
     if (h->fast && !(h->have_perm && h->P > 0)) FLX_TRY(slice_G(nullptr, 0, 0));
     if (h->fast) {
         // V^-1 = L^-T L^-1 one 256-row tile at a time (a plain library GEMM over the non-zero k range of the triangular
@@ -892,6 +907,7 @@ static int finalize_setup(flx_handle* h) {
         }
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
+    lap("V^-1 row tiles -> digit planes");
     FLX_TRY(h->df_count.ensure(16));
     FLX_TRY(h->missing.ensure(1));
     // the dense inverse is only needed again if the null model / design / permutations are re-set: keep it while it is small
@@ -923,6 +939,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         while (mult > 1 && (size_t)mult * h->num_sms * per_tile > have / 4) mult--;
         tiles_per_batch = mult * h->num_sms;
     }
+    // a run smaller than one batch sizes every batch buffer for itself, not for the default batch
+    tiles_per_batch = (int)std::max<int64_t>(1, std::min<int64_t>(tiles_per_batch, (M + ts.snps - 1) / ts.snps));
     const int64_t snps_per_batch = (int64_t)tiles_per_batch * ts.snps;
     // batch boundaries; when the genotypes come from the host, the first batches ramp up (1/4, 1/2, then full size) so that the
     // first H2D, which nothing can overlap, is short
@@ -990,7 +1008,6 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     if (!use_resident)
         for (int i = 0; i < 2; i++) {
             FLX_TRY(h->packed_d[i].ensure((size_t)snps_per_batch * bpv));
-            FLX_TRY(h->staging[i].ensure((size_t)snps_per_batch * bpv));
         }
     const int int_max = INT_MAX;
     FLX_TRY(h->px_err.ensure(1));
@@ -1026,6 +1043,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 src_ptr = h->packed_host + (size_t)(var_idx[s0] - 1) * bpv;          // pinned in place: no staging copy
             } else {
                 if (bi >= 2) FLX_CUDA_TRY(cudaEventSynchronize(h->ev_h2d[buf]));      // the staging buffer's previous H2D is done
+                if (h->src == 2 || h->pgen->mode() == 0x02) FLX_TRY(h->staging[buf].ensure((size_t)snps_per_batch * bpv));    // pinned, allocated only where used
                 uint8_t* st = h->staging[buf].p;
                 if (h->src == 2) {
                     if (contiguous) memcpy(st, h->packed_host + (size_t)(var_idx[s0] - 1) * bpv, (size_t)nsnp * bpv);
