@@ -566,6 +566,27 @@ def test_int8_digit_planes_when_the_leading_digit_would_be_128(fx, orc):
     assert_logp_close(r8["min_pval"], want)
 
 
+def test_five_plane_option_stays_within_the_parity_bar(fx):
+    """FLX_FLAG_PLANES_5 (40-bit digit planes, one sixth less K2q work): documented as ~1e-9 relative in lrt_chisq; the
+    parity bar of the path is 1e-8 in -log10 p."""
+    from flexlmm_b200 import synth
+    n, M = 1500, 600
+    for model in ("additive", "domgxe"):
+        t = synth.task(n, M, model=model, P=5, seed=77, effect=0.1)
+        r6, _ = _run(fx, t, True, M)
+        fm = fx.FitModel(planes=5)
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_perm(t["y_pred"], t["U1"], t["e_p"], t["seeds"]); fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r5 = fm.run(np.arange(1, M + 1, dtype=np.int32)); st5 = fm.stats(); fm.close()
+        assert st5["int8_path"] == 1
+        assert np.array_equal(r5["lrt_df"], r6["lrt_df"]) and np.array_equal(r5["pivot"], r6["pivot"])
+        np.testing.assert_allclose(r5["lrt_chisq"], r6["lrt_chisq"], rtol=2e-8, atol=1e-9)
+        with np.errstate(divide="ignore"):
+            a, b = -np.log10(r5["pval"]), -np.log10(r6["pval"])
+        ok = np.isfinite(a) & np.isfinite(b)
+        assert np.all(np.abs(a[ok] - b[ok]) <= 1e-8 * np.abs(b[ok]) + 1e-9)
+
+
 def test_int8_path_at_larger_n(fx, orc):
     """n = 12,000 (47 row tiles of 256, 188 k-blocks): int8 route vs FP64 route vs the oracle on a handful of SNPs."""
     from flexlmm_b200 import synth
