@@ -226,3 +226,29 @@ def test_fit_null_model_implicit_basis(fx, orc):
     np.testing.assert_allclose(U1.T @ X, 0, atol=1e-13)
     np.testing.assert_allclose(U1.T @ f["residuals"], r["e_p"], atol=1e-13)
     np.testing.assert_allclose(U1 @ r["e_p"], f["residuals"], atol=1e-13)     # e = U1 e.p: the decorrelation is lossless
+
+
+def test_pvar_psam_readers(fx, tmp_path):
+    """The text inputs next to the .pgen (fit_model.nf:34-52,70): header conventions, var_idx selection, match()."""
+    import gzip
+    pv = tmp_path / "a.pvar"
+    pv.write_text("##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\n"
+                  "1\t100\trs1\tA\tG\t.\n1\t250\trs2\tC\tT\t.\nX\t7\trs3\tG\tGA\t.\n")
+    assert fx.read_pvar(pv) == [("1", 100, "rs1", "A", "G"), ("1", 250, "rs2", "C", "T"), ("X", 7, "rs3", "G", "GA")]
+    assert fx.read_pvar(pv, var_idx=[3, 1]) == [("X", 7, "rs3", "G", "GA"), ("1", 100, "rs1", "A", "G")]
+    bim = tmp_path / "b.pvar.gz"
+    with gzip.open(bim, "wt") as f:
+        f.write("2\tv1\t0\t55\tT\tC\n")
+    assert fx.read_pvar(bim) == [("2", 55, "v1", "C", "T")]
+    ps = tmp_path / "a.psam"
+    ps.write_text("#FID\tIID\tSEX\nf1\ts1\t1\nf1\ts2\t2\nf2\ts3\tNA\n")
+    assert fx.read_psam(ps) == ["s1", "s2", "s3"]
+    ps2 = tmp_path / "b.psam"
+    ps2.write_text("#IID\tSEX\ns9\t1\ns8\t2\n")
+    assert fx.read_psam(ps2) == ["s9", "s8"]
+    fam = tmp_path / "c.psam"
+    fam.write_text("f1 s1 0 0 1 -9\nf1 s2 0 0 2 -9\n")
+    assert fx.read_psam(fam) == ["s1", "s2"]
+    assert fx.pgen_order(["s3", "s1"], ["s1", "s2", "s3", "s1"]).tolist() == [3, 1]
+    with pytest.raises(ValueError, match="not in the .psam"):
+        fx.pgen_order(["zz"], ["s1"])
