@@ -4,7 +4,7 @@ The product is the C-ABI library (include/flexlmm_cuda.h, flexlmm_b200/csrc); th
 mirror of the reference's process interface used by tests, bench.py and Python callers.
 """
 from ._capi import FlxError, load, lib_path  # noqa: F401
-from .fit_model import fit_null_model, FitModel, fit_model_task, perm_indices, minp_threshold, write_gwas_tsv, write_perm_tsv  # noqa: F401
+from .fit_model import fit_null_model, FitModel, fit_model_task, fit_model_files, perm_indices, minp_threshold, write_gwas_tsv, write_perm_tsv  # noqa: F401
 
 from .pfiles import read_pvar, read_psam, pgen_order  # noqa: F401
 from .postprocess import cat_perm, read_perm_table, summarise_by_chr, write_genome_wide_min_p, thresholds  # noqa: F401

@@ -247,3 +247,21 @@ def fit_model_task(L, y_mm, X_null, ll_null, df_null, M0, M1, M2, var_idx, pgen=
         else:
             fm.set_packed(packed, raw_sample_ct, pgen_order)
         return fm.run(var_idx, per_snp=per_snp)
+
+
+def fit_model_files(prefix, pgen, pvar, psam, samples, var_idx, colnames, L, y_mm, X_null, ll_null, df_null, M0, M1, M2,
+                    y_pred=None, U1=None, e_p=None, seeds=(), chrom=None, device=0):
+    """The FIT_MODEL process on its own files (fit_model.nf:7-16): reads `pvar` / `psam`, matches the model's `samples`
+    to the .psam (:70), tests the variants `var_idx` of `pgen`, and writes `<prefix>.tsv.gwas.gz` (ORIG, :112-116,145-169)
+    and, when seeds are given, `<prefix>.perm.tsv.gz` (one line per seed, :176-181).  Returns the result dict."""
+    from . import pfiles
+    rows = pfiles.read_pvar(pvar, var_idx)
+    order = pfiles.pgen_order(samples, pfiles.read_psam(psam))
+    res = fit_model_task(L, y_mm, X_null, ll_null, df_null, M0, M1, M2, var_idx, pgen=pgen, pgen_order=order,
+                         y_pred=y_pred, U1=U1, e_p=e_p, seeds=seeds, device=device)
+    write_gwas_tsv(f"{prefix}.tsv.gwas.gz", rows, colnames, res)
+    if len(seeds):
+        chroms = {r[0] for r in rows}
+        write_perm_tsv(f"{prefix}.perm.tsv.gz", seeds, chrom if chrom is not None else (chroms.pop() if len(chroms) == 1 else "NA"),
+                       res["min_pval"], res["nvars_tested"])
+    return res

@@ -794,3 +794,34 @@ def test_pgen_mode10_threaded_expansion(fx, tmp_path):
         assert np.array_equal(cd, c)
         r = fm.run(vi)
         assert r["nvars_tested"] == M and np.isfinite(r["lrt_chisq"]).all()
+
+
+def test_fit_model_from_process_files(fx, orc, tmp_path):
+    """The process interface on files: .pgen (compressed records) + .pvar + .psam in a shuffled sample order, a var_idx
+    subset, ORIG TSV and PERM TSV out; numbers against the oracle, text against the R formatting rules."""
+    import gzip
+    from flexlmm_b200 import synth
+    from pgen_writer import write_pgen
+    n, n_raw, Mtot = 150, 220, 90
+    t = synth.task(n, Mtot, model="domgxe", n_raw=n_raw, P=3, seed=19, effect=0.2)
+    rng = np.random.default_rng(6)
+    raw_ids = [f"id{q:04d}" for q in rng.permutation(n_raw)]
+    samples = [raw_ids[i - 1] for i in t["pgen_order"]]
+    (tmp_path / "g.pgen").write_bytes(write_pgen(t["codes_raw"], [0] + [int(x) for x in rng.choice([0, 1, 2, 4, 6], size=Mtot - 1)]))
+    (tmp_path / "g.psam").write_text("#FID\tIID\tSEX\n" + "".join(f"fam\t{s}\tNA\n" for s in raw_ids))
+    (tmp_path / "g.pvar").write_text("##source=test\n#CHROM\tPOS\tID\tREF\tALT\n" + "".join(f"7\t{1000 + 10 * v}\tsnp{v}\tA\tC\n" for v in range(Mtot)))
+    vi = np.arange(5, 65, dtype=np.int32)
+    res = fx.fit_model_files(str(tmp_path / "out"), tmp_path / "g.pgen", tmp_path / "g.pvar", tmp_path / "g.psam", samples, vi, t["names"],
+                             t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"], t["M0"], t["M1"], t["M2"],
+                             y_pred=t["y_pred"], U1=t["U1"], e_p=t["e_p"], seeds=t["seeds"])
+    codes = t["codes_raw"][vi - 1][:, t["pgen_order"] - 1]
+    compare(res, oracle_run(orc, t, codes))
+    lines = gzip.open(tmp_path / "out.tsv.gwas.gz", "rt").read().splitlines()
+    assert lines[0] == "chr\tpos\tid\tref\talt\tlrt_chisq\tlrt_df\tpval\tbeta" and len(lines) == 1 + vi.size
+    f = lines[1].split("\t")
+    assert f[:5] == ["7", "1040", "snp4", "A", "C"] and float(f[5]) == pytest.approx(res["lrt_chisq"][0], rel=1e-14)
+    assert f[8].startswith("(Intercept)~") and f[8].count(",") == len(t["names"]) - 1
+    perm = gzip.open(tmp_path / "out.perm.tsv.gz", "rt").read().splitlines()
+    assert len(perm) == 3 and perm[0].split("\t")[:2] == ["1", "7"] and perm[0].split("\t")[3] == str(vi.size)
+    want = np.array([oracle_run(orc, t, codes, seed=int(sd))["min_pval"] for sd in t["seeds"]])
+    assert_logp_close(res["min_pval"], want)
