@@ -296,18 +296,36 @@ __global__ void __launch_bounds__(512) decode_i8_tile_kernel(const DecodeArgs a,
     const bool live = snp < a.nsnp;
     const uint8_t* rec = a.packed + (live ? (a.vmap ? (int64_t)a.vmap[snp] : snp) : 0) * a.bpv;
     const int kend = min(kb0 + DEC8_KBS, NKB);
+    // identity sample order: the CTA's 128-byte segment of every record is staged in shared memory with coalesced loads
+    // (a warp reads one record's segment), then each thread picks its 4 packed bytes as one word; rows padded to 33 words
+    __shared__ uint32_t seg[128][33];
+    const bool staged = (a.order == nullptr);
+    if (staged) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int64_t b0 = (int64_t)kb0 * (QF_KB / 4) + 4 * lane;          // first of this lane's 4 bytes within a record
+        for (int rr = warp; rr < 128; rr += 16) {
+            const int64_t s2 = (int64_t)J * 128 + rr;
+            uint32_t word = 0;
+            if (s2 < a.nsnp) {
+                const uint8_t* rc = a.packed + (a.vmap ? (int64_t)a.vmap[s2] : s2) * a.bpv;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (b0 + b < a.bpv) word |= (uint32_t)__ldg(rc + b0 + b) << (8 * b);
+            }
+            seg[rr][lane] = word;
+        }
+        __syncthreads();
+    }
     for (int kb = kb0; kb < kend; kb++) {
         uint32_t w[4] = {0, 0, 0, 0};
         const int64_t k0 = (int64_t)kb * QF_KB + ch * 16;
         if (live && k0 < a.n) {
-            if (!a.order && k0 + 16 <= a.n) {
-                // identity sample order: 16 samples = 4 packed bytes
+            if (staged && k0 + 16 <= a.n) {
+                // 16 samples = 4 packed bytes = one staged word
+                const uint32_t word = seg[r][(kb - kb0) * 4 + ch];
+                if (word & (word >> 1) & 0x55555555u) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
 #pragma unroll
-                for (int b4 = 0; b4 < 4; b4++) {
-                    const uint32_t byte = __ldg(rec + (k0 >> 2) + b4);
-                    if (byte & (byte >> 1) & 0x55u) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
-                    w[b4] = lut[byte];
-                }
+                for (int b4 = 0; b4 < 4; b4++) w[b4] = lut[(word >> (8 * b4)) & 0xffu];
             } else {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
