@@ -41,7 +41,7 @@ class FlxStats(C.Structure):
                 ("ms_perm", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("launches", C.c_int64),
                 ("launches_whiten", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("snps", C.c_int64),
                 ("n_pad", C.c_int64), ("cols_per_tile", C.c_int64), ("int8_path", C.c_int64), ("refit_snps", C.c_int64),
-                ("int8_passes", C.c_int64)]
+                ("int8_passes", C.c_int64), ("fallback_reason", C.c_int64), ("ms_wall", C.c_double), ("ms_batches", C.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -87,7 +87,8 @@ struct flx_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t d2h_stream = nullptr;   // per-batch result copies into pinned staging, overlapped with the next batch
-    cudaEvent_t ev_res = nullptr;
+    cudaEvent_t ev_res = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;    // stage stopwatch events, created once and reused by every run
     cublasHandle_t cublas = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1;
@@ -143,8 +144,11 @@ struct flx_handle {
     DevBuf<int8_t> T8[4], X8, G8[2];               // T8[a * NG + b]: digit planes of tril(C_a V^-1 C_b) / of C_a V^-1 C_b; G8[a]: of C_a L^-T [Qc | r | R_f]
     DevBuf<double> rowscale[4], qf_part, G_scale[2], cvec_d, ub, Hd;
     int NB_G = 16, ntilesG = 1;                    // column blocks of G: ntilesG x NB_G >= cr + 1 + P
-    DevBuf<int32_t> refit_flag, out_map_d;
+    DevBuf<int32_t> refit_flag, refit_list, out_map_d;
     DevBuf<int> df_count, missing;
+    DevBuf<long long> coll_d;                      // [nvars, status] of the end-of-run collective
+    int fallback_reason = 0;                       // FLX_FALLBACK_*: why `fast` is false
+    int tiles_auto[2] = {0, 0};                    // cached default batch size per route (one cudaMemGetInfo per setup, not per run)
 
     // genotype source
     int src = 0;  // 0 none, 1 pgen file, 2 host packed
@@ -189,6 +193,9 @@ struct flx_handle {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (d2h_stream) cudaStreamDestroy(d2h_stream);
         if (ev_res) cudaEventDestroy(ev_res);
+        if (ev_t0) cudaEventDestroy(ev_t0);
+        if (ev_t1) cudaEventDestroy(ev_t1);
+        for (auto e : ev_pool) cudaEventDestroy(e);
     }
 };
 
@@ -226,7 +233,8 @@ extern "C" int flx_create(const flx_config* cfg, flx_handle** out) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_res, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_res, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete h;
         return FLX_ERR_CUDA;
@@ -252,6 +260,11 @@ extern "C" void flx_destroy(flx_handle* h) {
 // src: L (or L^-1) dense on the device, n x n column-major with leading dimension n.  The buffer is CONSUMED: it becomes
 // h->Zdense and is inverted in place (cusolverDnXtrtri), so that the setup of n = 10^5 holds one dense matrix (80 GB), not two.
 static int whitening_from_device(flx_handle* h, DevBuf<double>& src, int64_t n, int is_inverse) {
+    if (h->n > 0 && n != h->n) {
+        // null model, design and permutation inputs are vectors of the OLD n: they must be given again
+        h->have_null = h->have_design = h->have_perm = false;
+        h->P = 0;
+    }
     h->n = n;
     h->n_pad = (n + TJ - 1) / TJ * TJ;
     h->KC = (int)(h->n_pad / KCH);
@@ -309,7 +322,6 @@ extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int6
         cusolverStatus_t _s = (expr);                                                      \
         if (_s != CUSOLVER_STATUS_SUCCESS) {                                               \
             set_error("%s:%d: %s failed: cusolver status %d", __FILE__, __LINE__, #expr, (int)_s); \
-            if (cs) cusolverDnDestroy(cs);                                                 \
             return FLX_ERR_CUDA;                                                           \
         }                                                                                  \
     } while (0)
@@ -318,7 +330,8 @@ extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double
                                double min_allowed_eig, double eig_replacement, double* L_out, double* y_mm_out, double* X_mm_out, int32_t* clipped_eigs) {
     if (!h || !K || n <= 0 || c < 0 || (c > 0 && !X)) { set_error("flx_decorrelate: bad arguments"); return FLX_ERR_BAD_ARG; }
     FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
-    cusolverDnHandle_t cs = nullptr;
+    struct CsGuard { cusolverDnHandle_t h = nullptr; ~CsGuard() { if (h) cusolverDnDestroy(h); } } csg;    // released on every return path
+    cusolverDnHandle_t& cs = csg.h;
     FLX_CUSOLVER_TRY(cusolverDnCreate(&cs));
     FLX_CUSOLVER_TRY(cusolverDnSetStream(cs, h->stream));
     DevBuf<double> V, work;
@@ -329,7 +342,7 @@ extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double
         FLX_CUDA_TRY(cudaMemcpyAsync(V.p, K, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         return launch_scale_add_diag(V.p, n, n, s2g, s2e, h->stream);       // V = s2g*K + s2e*I   (decorrelate.nf:54)
     };
-    if (int rc = build_V()) { cusolverDnDestroy(cs); return rc; }
+    if (int rc = build_V()) return rc;
     int lwork = 0, info = 0, nclip = 0;
     FLX_CUSOLVER_TRY(cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, &lwork));
     FLX_TRY(work.ensure((size_t)lwork));
@@ -338,7 +351,7 @@ extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double
     FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (info != 0) {
         // not positive definite: force it by replacing the non-positive eigenvalues (:58-69)
-        if (int rc = build_V()) { cusolverDnDestroy(cs); return rc; }
+        if (int rc = build_V()) return rc;
         DevBuf<double> lam, U, T2;
         FLX_TRY(lam.ensure(n)); FLX_TRY(U.ensure((size_t)n * n)); FLX_TRY(T2.ensure((size_t)n * n));
         FLX_CUSOLVER_TRY(cusolverDnDsyevd_bufferSize(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, lam.p, &lwork));
@@ -348,11 +361,10 @@ extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double
         FLX_CUDA_TRY(cudaMemcpyAsync(lh.data(), lam.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         FLX_CUDA_TRY(cudaMemcpyAsync(&info, info_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
-        if (info != 0) { set_error("flx_decorrelate: eigen-decomposition failed (info %d)", info); cusolverDnDestroy(cs); return FLX_ERR_CUDA; }
+        if (info != 0) { set_error("flx_decorrelate: eigen-decomposition failed (info %d)", info); return FLX_ERR_CUDA; }
         for (int64_t i = 0; i < n; i++) {
             if (!(lh[i] >= min_allowed_eig)) {
                 set_error("flx_decorrelate: eigenvalue %.6g below min_allowed_eig %.6g (decorrelate.nf:65 stopifnot)", lh[i], min_allowed_eig);
-                cusolverDnDestroy(cs);
                 return FLX_ERR_BAD_ARG;
             }
             if (lh[i] <= 0.0) { lh[i] = eig_replacement; nclip++; }
@@ -369,10 +381,10 @@ extern "C" int flx_decorrelate(flx_handle* h, const double* K, int64_t n, double
         FLX_CUSOLVER_TRY(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, (int)n, V.p, (int)n, work.p, lwork, info_d.p));
         FLX_CUDA_TRY(cudaMemcpyAsync(&info, info_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
-        if (info != 0) { set_error("flx_decorrelate: V is not positive definite even after eigenvalue replacement (info %d)", info); cusolverDnDestroy(cs); return FLX_ERR_BAD_ARG; }
+        if (info != 0) { set_error("flx_decorrelate: V is not positive definite even after eigenvalue replacement (info %d)", info); return FLX_ERR_BAD_ARG; }
     }
     cusolverDnDestroy(cs);
-    cs = nullptr;
+    cs = nullptr;                                       // the workspace-heavy handle goes before the factor is inverted
     if (clipped_eigs) *clipped_eigs = nclip;
     FLX_TRY(launch_zero_upper(V.p, n, n, h->stream));     // potrf leaves the input above the diagonal
     // y.mm, X.mm = forwardsolve(L, .)  (:71-72)
@@ -676,18 +688,23 @@ static int finalize_setup(flx_handle* h) {
     //   A_raw[t][v] = g_t' C_t V^-1 C_v g_v = g_t' T^(t,v) g_v + g_v' T^(v,t) g_t,   T^(a,b) = tril(C_a V^-1 C_b), half diagonal,
     // each form an exact int8 contraction against the digit planes of a matrix prepared once per task.
     h->fast = false;
+    h->fallback_reason = FLX_FALLBACK_NONE;
+    h->tiles_auto[0] = h->tiles_auto[1] = 0;
     flx_handle::FastPlan& pl = h->plan;
     pl = flx_handle::FastPlan();
     std::vector<std::vector<double>> cvecs;
-    if (!(h->cfg.flags & FLX_FLAG_NO_INT8) && h->have_Z && h->s <= 4 && cr + 1 <= 24) {
-        bool ok = true;
-        for (int t = 0; t < h->s && ok; t++) {
+    if (h->cfg.flags & FLX_FLAG_NO_INT8) h->fallback_reason = FLX_FALLBACK_FLAG;
+    else if (!h->have_Z) h->fallback_reason = FLX_FALLBACK_NO_DENSE_INVERSE;
+    else if (h->s > 4 || cr + 1 > 24) h->fallback_reason = FLX_FALLBACK_TOO_MANY_FORMS;
+    else {
+        int why = FLX_FALLBACK_NONE;
+        for (int t = 0; t < h->s && !why; t++) {
             const double* src[3] = {h->M0.data() + (size_t)snp_cols[t] * n, h->M1.data() + (size_t)snp_cols[t] * n, h->M2.data() + (size_t)snp_cols[t] * n};
             // the sample with the largest entry fixes the integer triple
             int64_t ibest = 0; double vbest = 0.0;
             for (int64_t i = 0; i < n; i++)
                 for (int g = 0; g < 3; g++) if (std::fabs(src[g][i]) > vbest) { vbest = std::fabs(src[g][i]); ibest = i; }
-            if (!(vbest > 0.0) || !std::isfinite(vbest)) { ok = false; break; }
+            if (!(vbest > 0.0) || !std::isfinite(vbest)) { why = FLX_FALLBACK_NOT_SEPARABLE; break; }
             int a[3] = {0, 0, 0};
             bool found = false;
             for (int mlt = 1; mlt <= 2 && !found; mlt++) {
@@ -698,22 +715,22 @@ static int finalize_setup(flx_handle* h) {
                 }
                 found = ints;
             }
-            if (!found) { ok = false; break; }
+            if (!found) { why = FLX_FALLBACK_NOT_SEPARABLE; break; }
             int g0 = 0; while (g0 < 3 && a[g0] == 0) g0++;
             if (a[g0] < 0) for (int g = 0; g < 3; g++) a[g] = -a[g];
             int gs = 0; for (int g = 1; g < 3; g++) if (std::abs(a[g]) > std::abs(a[gs])) gs = g;
             std::vector<double> c(n);
-            for (int64_t i = 0; i < n && ok; i++) {
+            for (int64_t i = 0; i < n && !why; i++) {
                 c[i] = src[gs][i] / a[gs];                       // exact: a in {+-1, +-2}
-                for (int g = 0; g < 3; g++) if (src[g][i] != a[g] * c[i]) ok = false;
+                for (int g = 0; g < 3; g++) if (src[g][i] != a[g] * c[i]) why = FLX_FALLBACK_NOT_SEPARABLE;
             }
-            if (!ok) break;
+            if (why) break;
             int al = -1, gr = -1;
             for (int q = 0; q < pl.NA; q++) if (pl.aval[q][0] == a[0] && pl.aval[q][1] == a[1] && pl.aval[q][2] == a[2]) al = q;
-            if (al < 0) { if (pl.NA == 2) { ok = false; break; } al = pl.NA++; for (int g = 0; g < 3; g++) pl.aval[al][g] = a[g]; }
+            if (al < 0) { if (pl.NA == 2) { why = FLX_FALLBACK_TOO_MANY_FORMS; break; } al = pl.NA++; for (int g = 0; g < 3; g++) pl.aval[al][g] = a[g]; }
             for (int q = 0; q < pl.NG; q++) if (memcmp(cvecs[q].data(), c.data(), n * sizeof(double)) == 0) gr = q;
             if (gr < 0) {
-                if (pl.NG == 2) { ok = false; break; }
+                if (pl.NG == 2) { why = FLX_FALLBACK_TOO_MANY_FORMS; break; }
                 gr = pl.NG++;
                 bool ones = true;
                 for (int64_t i = 0; i < n; i++) ones = ones && (c[i] == 1.0);
@@ -722,7 +739,8 @@ static int finalize_setup(flx_handle* h) {
             }
             pl.alp[t] = al; pl.grp[t] = gr;
         }
-        h->fast = ok;
+        h->fallback_reason = why;
+        h->fast = (why == FLX_FALLBACK_NONE);
     }
     if (h->fast) {
         // passes: one K2q launch per (matrix, triple on the right), its epilogue dots with every triple used on the left.
@@ -878,8 +896,8 @@ static int finalize_setup(flx_handle* h) {
         const size_t planes_b = (size_t)pl.NG * pl.NG * 2 * h->T256 * (h->T256 + 1) * h->Q * 16384;   // a full set = two triangular ones
         const size_t batch_b = (size_t)h->num_sms * h->NKB * 8192 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);   // one tile per SM at least
         if (planes_b + batch_b + (size_t)256 * n * 8 > free_b) {
-            if (h->cfg.verbose) fprintf(stderr, "[flx] int8 route needs %.1f GB of digit planes, %.1f GB free: using the FP64 route\n", planes_b / 1e9, free_b / 1e9);
             h->fast = false;
+            h->fallback_reason = FLX_FALLBACK_PLANES_DONT_FIT;
         }
     }
     if (h->fast) {
@@ -910,8 +928,22 @@ static int finalize_setup(flx_handle* h) {
     lap("V^-1 row tiles -> digit planes");
     FLX_TRY(h->df_count.ensure(16));
     FLX_TRY(h->missing.ensure(1));
-    // the dense inverse is only needed again if the null model / design / permutations are re-set: keep it while it is small
-    if ((size_t)n * n * sizeof(double) > ((size_t)4 << 30)) { h->Zdense.release(); h->have_Z = false; }
+    // a task that cannot use the int8 tensor-core route is ~14x slower: never silently (flx_stats.fallback_reason carries the code)
+    if (h->fallback_reason > FLX_FALLBACK_FLAG) {
+        static const char* why[] = {"", "", "a SNP term is not (integer genotype triple) x (per-sample scale)", "more distinct triples / scales / SNP terms than the int8 plan holds",
+                                    "the dense L^-1 was released after an earlier setup (call flx_set_whitening again before re-setting the design / permutations)",
+                                    "the digit planes do not fit in device memory", "real-valued dosages"};
+        fprintf(stderr, "[flx] warning: this task runs on the FP64 route (~14x slower than the int8 tensor-core route): %s\n", why[std::min(h->fallback_reason, 6)]);
+    }
+    // the dense inverse is only needed again if the null model / design / permutations are re-set: keep it while the device has
+    // room for it next to a default batch (n = 50,000: 20 GB, kept; n = 100,000: 80 GB next to 70 GB of panels and planes, released)
+    if (h->have_Z) {
+        size_t free_b = 0, total_b = 0;
+        FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t batch_b = h->fast ? (size_t)4 * h->num_sms * ((size_t)h->plan.NA * h->NKB * 8192 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 + (size_t)h->s * 128 * h->ntilesG * h->NB_G * 8)
+                                       : (size_t)2 * h->num_sms * h->KC * CHUNK * 8;
+        if (free_b < batch_b + ((size_t)8 << 30)) { h->Zdense.release(); h->have_Z = false; }
+    }
     h->dirty = false;
     return FLX_OK;
 }
@@ -929,7 +961,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     // route, where a tile is 128 n bytes and K1q / K3b / K4q want more SNPs in flight than one tile per SM (K2q is indifferent),
     // capped so that the batch buffers stay below a quarter of the free memory
     int tiles_per_batch = h->cfg.batch_tiles > 0 ? h->cfg.batch_tiles : h->num_sms;
-    if (h->cfg.batch_tiles <= 0 && use_fast) {
+    if (h->cfg.batch_tiles <= 0 && h->tiles_auto[use_fast ? 1 : 0] > 0) tiles_per_batch = h->tiles_auto[use_fast ? 1 : 0];
+    else if (h->cfg.batch_tiles <= 0 && use_fast) {
         size_t free_b = 0, total_b = 0;
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_tile = (size_t)h->plan.NA * h->NKB * 8192 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 +
@@ -938,6 +971,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         int mult = 4;
         while (mult > 1 && (size_t)mult * h->num_sms * per_tile > have / 4) mult--;
         tiles_per_batch = mult * h->num_sms;
+        h->tiles_auto[1] = tiles_per_batch;
     }
     // a run smaller than one batch sizes every batch buffer for itself, not for the default batch
     tiles_per_batch = (int)std::max<int64_t>(1, std::min<int64_t>(tiles_per_batch, (M + ts.snps - 1) / ts.snps));
@@ -1019,8 +1053,13 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     }
     if (!decode_only) FLX_TRY(upload_fit_const(h->fc));
 
-    std::vector<cudaEvent_t> evs;
-    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); evs.push_back(e); };
+    // stage stopwatch: events come from the handle's pool (created once, reused by every run; nothing to leak on an early return)
+    size_t nev = 0;
+    auto mark = [&]() {
+        if (nev == h->ev_pool.size()) { cudaEvent_t e = nullptr; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+        cudaEventRecord(h->ev_pool[nev++], h->stream);
+    };
+    std::vector<cudaEvent_t>& evs = h->ev_pool;
     std::vector<uint8_t> xhost;
 
     for (int64_t bi = 0; bi < nbatch; bi++) {
@@ -1296,8 +1335,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         cudaEventElapsedTime(&ms, e[3], e[4]); h->stats.ms_fit += ms;
         cudaEventElapsedTime(&ms, e[4], e[5]); h->stats.ms_perm += ms;
     }
-    if (!evs.empty()) { float ms; cudaEventElapsedTime(&ms, evs.front(), evs.back()); h->stats.ms_total += ms; }
-    for (auto e : evs) cudaEventDestroy(e);
+    if (nev > 0) { float ms; cudaEventElapsedTime(&ms, evs[0], evs[nev - 1]); h->stats.ms_batches += ms; }
     int pxe = 0;
     FLX_CUDA_TRY(cudaMemcpy(&pxe, h->px_err.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (pxe != 0) {
@@ -1314,16 +1352,8 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     return FLX_OK;
 }
 
-extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const flx_snp_out* out, double* minp, int64_t* nvars_tested) {
-    if (!h || (M > 0 && !var_idx) || M < 0) { set_error("flx_run: bad arguments"); return FLX_ERR_BAD_ARG; }
-    if (M >= INT_MAX) { set_error("flx_run: M too large"); return FLX_ERR_BAD_ARG; }
-    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
-    if (h->src == 0) { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
-    if (h->dirty) FLX_TRY(finalize_setup(h));
-    memset(&h->stats, 0, sizeof(h->stats));
-    const bool do_perm = h->have_perm && h->P > 0;
-    if (minp && !do_perm) { set_error("flx_run: minp requested but no permutations were set (flx_set_perm)"); return FLX_ERR_STATE; }
-    h->stats.snps = M; h->stats.n_pad = h->n_pad; h->stats.cols_per_tile = make_tile_shape(h->s).blocks * 8;
+// The rank-local part of flx_run: batches, FP64 refits, min-p finalisation, per-SNP results to the caller's arrays.
+static int run_local(flx_handle* h, const int32_t* var_idx, int64_t M, const flx_snp_out* out, bool do_perm) {
     if (M > 0) {
         const bool fast = h->fast;
         h->stats.int8_path = fast ? 1 : 0;
@@ -1331,24 +1361,28 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
         if (fast) for (const auto& ps : h->plan.passes) h->stats.int8_passes += (ps.mat / h->plan.NG != ps.mat % h->plan.NG) ? 2 : 1;
         FLX_TRY(run_batches(h, var_idx, M, out != nullptr, do_perm, nullptr, nullptr, fast, false, nullptr, M));
         if (fast) {
-            // SNPs whose x is (nearly) in the span of the constant columns lose digits in A = x'V^-1x - |u|^2: re-fit them in FP64
-            std::vector<int32_t> flags(M);
-            FLX_CUDA_TRY(cudaMemcpy(flags.data(), h->refit_flag.p, M * sizeof(int32_t), cudaMemcpyDeviceToHost));
-            std::vector<int32_t> sub, slot;
-            for (int64_t i = 0; i < M; i++)
-                if (flags[i]) { sub.push_back(var_idx[i]); slot.push_back((int32_t)i); }
-            h->stats.refit_snps = (int64_t)sub.size();
-            if (!sub.empty()) FLX_TRY(run_batches(h, sub.data(), (int64_t)sub.size(), out != nullptr, do_perm, nullptr, nullptr, false, true, slot.data(), M));
+            // SNPs whose x is (nearly) in the span of the constant columns lose digits in A = x'V^-1x - |u|^2: re-fit them in FP64.
+            // The flags are compacted on the device; the host reads a count and, only if it is not zero, the short list.
+            int nref = 0;
+            FLX_TRY(h->refit_list.ensure((size_t)M + 1));
+            FLX_TRY(launch_compact_flags(h->refit_flag.p, M, h->refit_list.p, h->stream));
+            h->stats.launches++;
+            FLX_CUDA_TRY(cudaMemcpyAsync(&nref, h->refit_list.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            h->stats.refit_snps = nref;
+            if (nref > 0) {
+                std::vector<int32_t> slot(nref), sub(nref);
+                FLX_CUDA_TRY(cudaMemcpy(slot.data(), h->refit_list.p + 1, (size_t)nref * sizeof(int32_t), cudaMemcpyDeviceToHost));
+                std::sort(slot.begin(), slot.end());      // atomics hand out list positions in any order: keep the run deterministic
+                for (int i = 0; i < nref; i++) sub[i] = var_idx[slot[i]];
+                FLX_TRY(run_batches(h, sub.data(), nref, out != nullptr, do_perm, nullptr, nullptr, false, true, slot.data(), M));
+            }
         }
         if (do_perm) {
-            FLX_TRY(launch_minp_finalize(h->maxratio.p, h->P_pad, h->P, h->s, h->lrs0p.p, (double)h->n, h->df_count.p, h->minp_d.p, h->stream));
+            FLX_TRY(launch_minp_finalize(h->maxratio.p, h->P_pad, h->P, h->s, h->cr + 1 - h->df_null, h->lrs0p.p, (double)h->n, h->df_count.p, h->minp_d.p, h->stream));
             h->stats.launches++;
         }
     }
-    // ---- results D2H
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, h->stream);
     if (out && M > 0) {
         const size_t k = (size_t)h->k;
         FLX_CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));       // the per-batch copies have landed (and cannot overtake what follows)
@@ -1383,38 +1417,76 @@ extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const f
         }
         for (const Cp& c : cps) if (c.dst) h->stats.d2h_bytes += (int64_t)c.bytes;
     }
+    if (do_perm && M == 0) {
+        std::vector<double> two(h->P, 2.0);
+        FLX_CUDA_TRY(cudaMemcpyAsync(h->minp_d.p, two.data(), h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return FLX_OK;
+}
+
+extern "C" int flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const flx_snp_out* out, double* minp, int64_t* nvars_tested) {
+    if (!h) { set_error("flx_run: NULL handle"); return FLX_ERR_BAD_ARG; }
+    const auto wall0 = std::chrono::steady_clock::now();
+    // Every rank of an attached communicator must reach the collectives below whatever happens locally (a missing genotype
+    // or a malformed record in ONE shard must not leave the other ranks blocked in ncclAllReduce): local failures are
+    // carried in `rc` to the status exchange instead of returning early.
+    int rc = FLX_OK;
+    bool do_perm = false;
+    if ((M > 0 && !var_idx) || M < 0) { set_error("flx_run: bad arguments"); rc = FLX_ERR_BAD_ARG; }
+    else if (M >= INT_MAX) { set_error("flx_run: M too large"); rc = FLX_ERR_BAD_ARG; }
+    else if (cudaSetDevice(h->cfg.device) != cudaSuccess) { set_error("flx_run: cudaSetDevice(%d) failed", h->cfg.device); rc = FLX_ERR_CUDA; }
+    else if (h->src == 0) { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); rc = FLX_ERR_STATE; }
+    else if ((int64_t)h->order0.size() != h->n) { set_error("flx_run: the genotype source was set for n=%lld samples, the whitening matrix has n=%lld", (long long)h->order0.size(), (long long)h->n); rc = FLX_ERR_STATE; }
+    if (rc == FLX_OK && h->dirty) rc = finalize_setup(h);
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->stats.fallback_reason = h->fallback_reason;
+    if (rc == FLX_OK) {
+        do_perm = h->have_perm && h->P > 0;
+        if (minp && !do_perm) { set_error("flx_run: minp requested but no permutations were set (flx_set_perm)"); rc = FLX_ERR_STATE; }
+    }
+    h->stats.snps = M; h->stats.n_pad = h->n_pad; h->stats.cols_per_tile = make_tile_shape(std::max(h->s, 1)).blocks * 8;
+    cudaEventRecord(h->ev_t0, h->stream);
+    if (rc == FLX_OK) rc = run_local(h, var_idx, M, out, do_perm);
     int64_t nv = M;
-    if (do_perm) {
-        if (M == 0) {
-            std::vector<double> two(h->P, 2.0);
-            FLX_CUDA_TRY(cudaMemcpyAsync(h->minp_d.p, two.data(), h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->comm && h->nranks > 1) {
+        // the only collective of the design: min over SNP shards of the length-P vector (get_null_p_dist.nf:77), with the sum
+        // of the tested-variant counts and the worst status of any rank riding along
+        long long word[2] = {rc == FLX_OK ? (long long)M : 0, (long long)rc};
+        ncclResult_t r0 = ncclSuccess, r1 = ncclSuccess, r2 = ncclSuccess;
+        bool ok = h->coll_d.ensure(2) == 0 &&
+                  cudaMemcpyAsync(h->coll_d.p, word, sizeof(word), cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+        if (ok) {
+            ncclGroupStart();
+            if (h->P > 0 && h->minp_d.p) r0 = ncclAllReduce(h->minp_d.p, h->minp_d.p, (size_t)h->P, ncclDouble, ncclMin, h->comm, h->stream);
+            r1 = ncclAllReduce(h->coll_d.p, h->coll_d.p, 1, ncclInt64, ncclSum, h->comm, h->stream);
+            r2 = ncclAllReduce(h->coll_d.p + 1, h->coll_d.p + 1, 1, ncclInt64, ncclMin, h->comm, h->stream);
+            ncclGroupEnd();
+            ok = r0 == ncclSuccess && r1 == ncclSuccess && r2 == ncclSuccess &&
+                 cudaMemcpyAsync(word, h->coll_d.p, sizeof(word), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+                 cudaStreamSynchronize(h->stream) == cudaSuccess;
         }
-        if (h->comm && h->nranks > 1) {
-            // the only collective of the design: min over SNP shards of the length-P vector (get_null_p_dist.nf:77)
-            DevBuf<long long> nvd;
-            FLX_TRY(nvd.ensure(1));
-            long long nvl = M;
-            FLX_CUDA_TRY(cudaMemcpyAsync(nvd.p, &nvl, sizeof(nvl), cudaMemcpyHostToDevice, h->stream));
-            ncclResult_t r1 = ncclAllReduce(h->minp_d.p, h->minp_d.p, (size_t)h->P, ncclDouble, ncclMin, h->comm, h->stream);
-            ncclResult_t r2 = ncclAllReduce(nvd.p, nvd.p, 1, ncclInt64, ncclSum, h->comm, h->stream);
-            if (r1 != ncclSuccess || r2 != ncclSuccess) { set_error("ncclAllReduce failed: %s", ncclGetErrorString(r1 != ncclSuccess ? r1 : r2)); return FLX_ERR_NCCL; }
-            FLX_CUDA_TRY(cudaMemcpyAsync(&nvl, nvd.p, sizeof(nvl), cudaMemcpyDeviceToHost, h->stream));
-            FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
-            nv = nvl;
-        }
-        if (minp) {
-            FLX_CUDA_TRY(cudaMemcpyAsync(minp, h->minp_d.p, h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            h->stats.d2h_bytes += h->P * (int64_t)sizeof(double);
+        if (!ok) {
+            if (rc == FLX_OK) { set_error("flx_run: the min-p allreduce failed (%s)", ncclGetErrorString(r0 != ncclSuccess ? r0 : r1 != ncclSuccess ? r1 : r2)); rc = FLX_ERR_NCCL; }
+        } else {
+            nv = word[0];
+            if (rc == FLX_OK && word[1] != FLX_OK) {
+                set_error("flx_run: another rank of the communicator failed with status %lld; this shard's results are discarded with it", word[1]);
+                rc = (int)word[1];
+            }
         }
     }
-    cudaEventRecord(e1, h->stream);
-    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (rc == FLX_OK && do_perm && minp) {
+        if (cudaMemcpyAsync(minp, h->minp_d.p, h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { set_error("flx_run: min-p copy failed"); rc = FLX_ERR_CUDA; }
+        h->stats.d2h_bytes += h->P * (int64_t)sizeof(double);
+    }
+    cudaEventRecord(h->ev_t1, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess && rc == FLX_OK) { set_error("flx_run: %s", cudaGetErrorString(cudaGetLastError())); rc = FLX_ERR_CUDA; }
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    h->stats.ms_d2h = ms;
-    h->stats.ms_total += ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1) == cudaSuccess) h->stats.ms_total = ms;
+    h->stats.ms_d2h = std::max(0.0, h->stats.ms_total - h->stats.ms_batches);
+    h->stats.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    if (rc != FLX_OK) return rc;
     if (nvars_tested) *nvars_tested = nv;
     return FLX_OK;
 }

@@ -9,6 +9,7 @@
 // B frag: row=lane&3, col=lane>>2 — the same element mapping serves both operands).
 // Chunks are contiguous, so the producer warp moves one chunk with one cp.async.bulk (TMA, 1-D).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -54,4 +55,13 @@ __host__ __device__ __forceinline__ TileShape make_tile_shape(int s) {
 
 namespace flx {
 void set_error(const char* fmt, ...);
+
+// cudaFuncSetAttribute applies to the CURRENT device only, and one process may hold handles on several GPUs (one host
+// thread each): one flag per device ordinal instead of one per process.
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+    bool need() const { return !((done.load(std::memory_order_acquire) >> dev()) & 1ull); }
+    void set() { done.fetch_or(1ull << dev(), std::memory_order_release); }
+};
 }

@@ -18,7 +18,7 @@ struct GemmArgs {
     int KC_live;              // K2: k-chunks that hold real samples = ceil(n / 16)
     int last_row_blocks;      // K2: 8-row blocks of the last row tile that hold real samples (1..16)
     // K4 epilogue
-    const int32_t* snp_df;    // per SNP in batch: lrt_df (0 => skip)
+    const int32_t* snp_df;    // per SNP in batch: rank bucket 1..s = lrt_df - (cr + 1 - df_null) (0 => skip)
     const double* snp_sm;     // per SNP: s(s+1)/2 packed symmetric matrix Sm, dSS = b' Sm b
     const double* perm_inv_rss;  // per permutation column: 1 / RSS_f,p (0 for padding)
     double* perm_maxratio;    // [s][P_pad] running max of dSS / RSS_f,p per (df, permutation)
@@ -146,7 +146,7 @@ struct SolveArgs {
     double* chisq; double* pval; int32_t* df; int32_t* rank; int32_t* pivot; double* coef;  // pivot/coef: [M][k]
     // batch-local outputs for K4
     int32_t* snp_df; double* snp_sm;
-    int* df_count;            // [9] run-wide count of SNPs per lrt_df (1..8)
+    int* df_count;            // [9] run-wide count of SNPs per rank bucket 0..s (lrt_df = cr + 1 - df_null + bucket, counted when lrt_df > 0)
     const int32_t* out_map;   // optional: run-wide output slot of batch SNP q (refit pass), else out_offset + q
     // fast (int8 quadratic form) mode: A_raw[t][v] = S[slot_a[t][v]] + S[slot_b[t][v]], S[slot] = sum of the qf_nparts partials
     // of K2q pass `slot` (qf_part: [slot][qf_nparts][nsnp]); u_t (cr values) and b_t from K4q: u_part[t * u_term_stride + snp * u_ld + j]
@@ -183,6 +183,8 @@ int launch_implicit_u1(const double* e_p, const int32_t* idx, int64_t m, int P, 
 int launch_gather_ep(const double* e_p, const int32_t* idx, int64_t m, int P, double* E, cudaStream_t st);
 // V = a*V + b*I in place (decorrelate.nf:54)
 int launch_scale_add_diag(double* V, int64_t n, int64_t ld, double a, double b, cudaStream_t st);
+// list[0] = number of non-zero flags, list[1..] = their indices (any order); list holds M + 1 entries
+int launch_compact_flags(const int32_t* flag, int64_t M, int32_t* list, cudaStream_t st);
 // fill identity
 int launch_set_identity(double* Z, int64_t n, int64_t ld, cudaStream_t st);
 // finalize min-p: minp[p] = min over df of pchisq_upper(N*(lrs0p[p] - log1p(-maxratio[df][p])), df)
@@ -193,6 +195,6 @@ struct PermReduceArgs {
     int64_t nsnp; int P; int64_t P_pad; int s;
 };
 int launch_perm_reduce(const PermReduceArgs& a, cudaStream_t st);
-int launch_minp_finalize(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp, cudaStream_t st);
+int launch_minp_finalize(const double* maxratio, int64_t P_pad, int P, int s, int df_off, const double* lrs0p, double N, const int* df_count, double* minp, cudaStream_t st);
 
 }  // namespace flx

@@ -293,11 +293,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_gemm_kernel(const GemmA
 
 template <int MODE, int S>
 static int launch_one(const GemmArgs& g, int num_sms, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(panel_gemm_kernel<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(panel_gemm): %s", cudaGetErrorString(e)); return -3; }
-        configured = true;
+        configured.set();
     }
     int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
     if (grid <= 0) return 0;

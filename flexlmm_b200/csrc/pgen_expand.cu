@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(PX_WARPS * 32) pgen_expand_kernel(const PgenEx
         if (!ok || dl > n) { if (lane == 0) px_fail(a.err, e, 3); return; }
         if (dl > 0) {
             const uint32_t ngroups = (dl + 63) / 64;
-            const int idb = n <= 256u ? 1 : n <= 65536u ? 2 : n <= 16777216u ? 3 : 4;
+            const int idb = n < 256u ? 1 : n < 65536u ? 2 : n < 16777216u ? 3 : 4;   // pgenlib BytesToRepresentNzU32(raw_sample_ct) = bsr / 8 + 1
             const uint8_t* first_ids = p;
             const uint8_t* cnts = first_ids + (uint64_t)ngroups * idb;
             const uint8_t* rare = cnts + (ngroups - 1);
@@ -153,8 +153,9 @@ int launch_pgen_expand(const PgenExpandArgs& a0, cudaStream_t st) {
     PgenExpandArgs a = a0;
     a.row_words = (int)(((a.bpv + 3) / 4 + 3) / 4 * 4);
     const size_t smem = (size_t)PX_WARPS * a.row_words * sizeof(uint32_t);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static std::atomic<size_t> configured_dev[64];          // per device: the attribute belongs to the current device
+    std::atomic<size_t>& configured = configured_dev[DeviceOnce::dev()];
+    if (smem > 48 * 1024 && smem > configured.load()) {
         if (smem > 227 * 1024) { set_error("pgen_expand: %u samples per record exceed the shared-memory row buffers", a.sample_ct); return -1; }
         cudaError_t e = cudaFuncSetAttribute(pgen_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pgen_expand): %s", cudaGetErrorString(e)); return -3; }

@@ -254,12 +254,12 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
 }
 
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(qf_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(qf): %s", cudaGetErrorString(e)); return -3; }
-        configured = true;
+        configured.set();
     }
     if (g.n_items <= 0) return 0;
     // the epilogue reduces 16 rows in s32: 16 * (128 * n_pad * xmax) * xmax with xmax = 2 must stay below 2^31
@@ -573,11 +573,11 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
 }
 
 int launch_xg(const XgArgs& g, int num_sms, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(xg_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XG_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(xg): %s", cudaGetErrorString(e)); return -3; }
-        configured = true;
+        configured.set();
     }
     if (g.NB % 16 != 0 || g.NB < 16 || g.NB > XG_MAX_NB || g.Q < 1 || g.Q > 6) { set_error("xg: bad column block %d / planes %d", g.NB, g.Q); return -1; }
     const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;

@@ -213,4 +213,27 @@ int launch_perm_prep(const PermPrepArgs& a, cudaStream_t st) {
     return 0;
 }
 
+// ---- refit flags of a run -> list[0] = count, list[1 + i] = run-wide index of a flagged SNP (order arbitrary; the host sorts
+//      the short list).  Replaces an M-element D2H copy and a host scan per flx_run.
+__global__ void compact_flags_kernel(const int32_t* __restrict__ flag, int64_t M, int32_t* __restrict__ list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < M && flag[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(list, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (on) list[1 + base + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
+}
+int launch_compact_flags(const int32_t* flag, int64_t M, int32_t* list, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(list, 0, sizeof(int32_t), st);
+    if (e == cudaSuccess && M > 0) {
+        compact_flags_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(flag, M, list);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { set_error("compact_flags launch: %s", cudaGetErrorString(e)); return -3; }
+    return 0;
+}
+
 }  // namespace flx

@@ -506,6 +506,10 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     const double chisq = N * (c.lrs0 - log1p(-ratio));
     const int df = rank + 1 - c.df_null;
     const double p = (df > 0) ? chisq_upper_tail(chisq, df) : nan("");
+    // permutation maxima are kept per lrt_df; the SNP columns add bucket = 0..s to the rank cr of the constant columns, so
+    // lrt_df = (cr + 1 - df_null) + bucket whatever the null model is (a null nested more than s columns deep has lrt_df > s).
+    // bucket 0 (no SNP direction survives) has dSS = 0 for every phenotype: counted, never reduced.
+    const int bucket = min(max(rank - cr, 0), s);
 
     const int64_t o = a.out_map ? (int64_t)a.out_map[snp] : a.out_offset + snp;
     a.chisq[o] = chisq;
@@ -555,9 +559,9 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
                 a.snp_sm[snp * nsym + q] = (df > 0 && !refit) ? v : 0.0;
                 q++;
             }
-        a.snp_df[snp] = (df > 0 && !refit) ? df : 0;
+        a.snp_df[snp] = (df > 0 && !refit) ? bucket : 0;
     }
-    if (a.df_count && df > 0 && df <= MAXS && !refit) atomicAdd(&a.df_count[df], 1);
+    if (a.df_count && df > 0 && !refit) atomicAdd(&a.df_count[bucket], 1);
 }
 
 int launch_snp_solve(const SolveArgs& a, cudaStream_t st) {
@@ -638,23 +642,24 @@ int launch_perm_reduce(const PermReduceArgs& a, cudaStream_t st) {
     return 0;
 }
 
-__global__ void minp_finalize_kernel(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp) {
+// bucket b = 0..s <-> lrt_df = df_off + b (snp_solve_kernel); maxratio rows are the buckets 1..s, bucket 0 has ratio 0
+__global__ void minp_finalize_kernel(const double* maxratio, int64_t P_pad, int P, int s, int df_off, const double* lrs0p, double N, const int* df_count, double* minp) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     double best = 2.0;  // "an impossibly large value" (fit_model.nf:104)
-    for (int t = 0; t < s; t++) {
-        const double mr = maxratio[(int64_t)t * P_pad + p];
-        if (df_count[t + 1] == 0) continue;  // no SNP with this df in the run
+    for (int b = 0; b <= s; b++) {
+        if (df_count[b] == 0 || df_off + b <= 0) continue;  // no SNP with this df in the run
+        const double mr = (b == 0) ? 0.0 : maxratio[(int64_t)(b - 1) * P_pad + p];
         const double chisq = N * (lrs0p[p] - log1p(-mr));
-        const double pv = chisq_upper_tail(chisq, t + 1);
+        const double pv = chisq_upper_tail(chisq, df_off + b);
         if (pv < best) best = pv;
     }
     minp[p] = best;
 }
 
-int launch_minp_finalize(const double* maxratio, int64_t P_pad, int P, int s, const double* lrs0p, double N, const int* df_count, double* minp, cudaStream_t st) {
+int launch_minp_finalize(const double* maxratio, int64_t P_pad, int P, int s, int df_off, const double* lrs0p, double N, const int* df_count, double* minp, cudaStream_t st) {
     if (P <= 0) return 0;
-    minp_finalize_kernel<<<(P + 127) / 128, 128, 0, st>>>(maxratio, P_pad, P, s, lrs0p, N, df_count, minp);
+    minp_finalize_kernel<<<(P + 127) / 128, 128, 0, st>>>(maxratio, P_pad, P, s, df_off, lrs0p, N, df_count, minp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("minp_finalize launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;

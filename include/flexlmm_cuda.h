@@ -82,7 +82,19 @@ typedef struct {
     int64_t int8_path;         /* 1: the batches ran K2q (int8 tensor cores), 0: K2 (FP64 DMMA)        */
     int64_t refit_snps;        /* SNPs re-fitted on the FP64 path (near-collinear with constant columns)*/
     int64_t int8_passes;       /* K2q work per batch in triangular-pass units (6 n^2 int8 ops per SNP): 1 for one SNP term, 5 for x + I(x==1) + x:cov */
+    int64_t fallback_reason;   /* FLX_FALLBACK_*: why the task runs on the FP64 route (0 when it runs on the int8 route)                         */
+    double ms_wall;            /* host wall clock of the whole flx_run* call (entry to return), ms                                              */
+    double ms_batches;         /* device time of the batch loop(s) alone (ms_total minus the final copies / collective)                          */
 } flx_stats;
+
+/* flx_stats.fallback_reason: the int8 tensor-core route (K2q/K4q) is ~14x the FP64 route, so a task that cannot use it says why */
+#define FLX_FALLBACK_NONE            0
+#define FLX_FALLBACK_FLAG            1   /* FLX_FLAG_NO_INT8 was set                                                            */
+#define FLX_FALLBACK_NOT_SEPARABLE   2   /* a SNP term is not (integer genotype triple) x (per-sample scale), e.g. exp(x * cov)  */
+#define FLX_FALLBACK_TOO_MANY_FORMS  3   /* more distinct triples / scales / terms than the int8 plan holds                      */
+#define FLX_FALLBACK_NO_DENSE_INVERSE 4  /* design / permutations re-set after the dense L^-1 was released (n^2 * 8 B did not fit next to the planes): call flx_set_whitening again */
+#define FLX_FALLBACK_PLANES_DONT_FIT 5   /* the digit planes of the design's scale pairs do not fit in HBM next to L^-1          */
+#define FLX_FALLBACK_DOSAGE          6   /* real-valued dosages (pgenlibr::Read): genotypes are not small integers               */
 
 const char* flx_last_error(void);
 const char* flx_version(void);

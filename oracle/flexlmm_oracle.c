@@ -168,7 +168,7 @@ static int apply_difflist(const uint8_t** pp, const uint8_t* end, uint32_t sampl
     if (dl == 0) return 0;
     if (dl > sample_ct) return -7;
     uint32_t group_ct = (dl + 63) / 64;
-    int idb = (sample_ct <= 256u) ? 1 : (sample_ct <= 65536u) ? 2 : (sample_ct <= 16777216u) ? 3 : 4;
+    int idb = (sample_ct < 256u) ? 1 : (sample_ct < 65536u) ? 2 : (sample_ct < 16777216u) ? 3 : 4;   /* pgenlib BytesToRepresentNzU32(raw_sample_ct) = bsr / 8 + 1 */
     const uint8_t* group_first = *pp;
     const uint8_t* p = group_first + (uint64_t)group_ct * idb;
     p += group_ct - 1;                       /* per-group byte counts (only needed for random access) */

@@ -9,6 +9,8 @@ c1_test_asset.json : BASELINE config C1 — the reference's own -profile test da
 synth_small.npz    : small synthetic tasks (seeded) with oracle outputs, so the GPU tests can also be checked against
                      numbers computed in this container.
 kat.json           : SURVEY.md Appendix B known answers.
+r_pin/*.in.txt     : input bundles for tests/golden/make_r_fixture.R, the script a maintainer with R runs to PIN the oracle and the
+                     CUDA path on R's own outputs (tests/test_r_pin.py picks the resulting r_pin/*.out.txt up when present).
 """
 import json
 import os
@@ -93,6 +95,44 @@ def synth_small():
     np.savez_compressed(f"{HERE}/synth_small.npz", **out)
 
 
+def r_pin_inputs():
+    """Input bundles of the R pin (tests/golden/make_r_fixture.R): the C1 test assets (both formula pairs, L = I and a GRM-based L,
+    all 22 variants as one task) and three small synthetic tasks.  Everything R needs to run fit_model.nf:96-143 literally, plus
+    the design lookups M0/M1/M2 the C ABI takes (R ignores them)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import r_pin
+    os.makedirs(r_pin.PIN_DIR, exist_ok=True)
+    c = json.load(open(f"{HERE}/c1_test_asset.json"))
+    formulas = {"test_config": "y ~ x + I(x == 1) + x:covar1 + covar1 + qcovar1", "baseline_simple": "y ~ x"}
+    codes = np.array(c["codes"], dtype=np.float64)            # (22, 12), already in model order (samples == psam)
+    for case in c["cases"]:
+        name = f"c1_{case['L']}_{case['formula']}"
+        items = {"case": name, "formula": formulas[case["formula"]], "L": np.array(case["Lmat"]), "y_mm": case["y_mm"],
+                 "X_null": np.array(case["X_null"]).reshape(len(case["y_mm"]), -1), "ll_null": [case["ll_null"]], "df_null": [case["df_null"]],
+                 "y_pred": case["y_pred"], "U1": np.array(case["U1"]), "e_p": np.array(case["e_p"]).reshape(-1, 1), "geno": codes.T,
+                 "seeds": [1, 2], "M0": np.array(case["M0"]), "M1": np.array(case["M1"]), "M2": np.array(case["M2"]),
+                 "factorlevels.covar1": " ".join(c["covar1_levels"]), "factorcodes.covar1": c["covar1"], "numeric.qcovar1": c["qcovar1"]}
+        assert all(" " not in lev for lev in c["covar1_levels"])
+        r_pin.write_bundle(os.path.join(r_pin.PIN_DIR, name + ".in.txt"), items)
+    formulas = {"additive": "y ~ x + cov1", "domgxe": "y ~ x + I(x == 1) + x:cov1 + cov1", "simple": "y ~ x"}
+    for model, (n, M, n_raw) in {"additive": (60, 24, None), "domgxe": (50, 24, 57), "simple": (65, 16, None)}.items():
+        t = synth.task(n, M, model=model, P=2, n_raw=n_raw, seed=21, effect=0.4)
+        # the reference's own null fit (eigen basis U1) instead of the synthetic Householder one, so U1 is what R would hold
+        nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+        cov1 = synth.design(model, n, seed=11 + 21)[6]
+        geno = t["codes_raw"][:, t["pgen_order"] - 1].astype(np.float64)
+        if model == "domgxe":
+            j = int(np.argmax(geno.mean(axis=1)))
+            geno[j] = np.where(geno[j] == 1, 2, geno[j])      # polymorphic without heterozygotes: I(x == 1) is all zero (the rank-deficient path)
+            geno[5] = 2.0                                      # monomorphic
+        items = {"case": f"synth_{model}", "formula": formulas[model], "L": t["L"], "y_mm": t["y_mm"], "X_null": t["X_null"], "ll_null": [nm["ll"]],
+                 "df_null": [nm["df"]], "y_pred": nm["y_pred"], "U1": nm["U1"], "e_p": np.asarray(nm["e_p"]).reshape(-1, 1), "geno": geno.T,
+                 "seeds": [1, 2], "M0": t["M0"], "M1": t["M1"], "M2": t["M2"]}
+        if model != "simple":
+            items["numeric.cov1"] = cov1
+        r_pin.write_bundle(os.path.join(r_pin.PIN_DIR, f"synth_{model}.in.txt"), items)
+
+
 def kat():
     json.dump({
         "sample10": {"1": [9, 4, 7, 1, 2, 5, 3, 10, 6, 8], "42": [1, 5, 10, 8, 2, 4, 6, 9, 7, 3], "123": [3, 10, 2, 8, 6, 9, 1, 7, 5, 4]},
@@ -105,5 +145,5 @@ def kat():
 
 if __name__ == "__main__":
     orc.build()
-    c1(); synth_small(); kat()
+    c1(); synth_small(); kat(); r_pin_inputs()
     print("golden fixtures written to", HERE)

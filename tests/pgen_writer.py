@@ -24,7 +24,7 @@ def _difflist(sample_ct, ids, vals):
     out = bytearray(_varint(dl))
     if dl == 0:
         return bytes(out)
-    idb = 1 if sample_ct <= 256 else 2 if sample_ct <= 65536 else 3 if sample_ct <= 16777216 else 4
+    idb = 1 if sample_ct < 256 else 2 if sample_ct < 65536 else 3 if sample_ct < 16777216 else 4   # pgenlib BytesToRepresentNzU32(raw_sample_ct)
     ngroups = (dl + 63) // 64
     deltas = []
     for g in range(ngroups):

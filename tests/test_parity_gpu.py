@@ -45,6 +45,27 @@ def oracle_run(orc, t, codes, seed=0):
     return orc.fit_model(t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"], t["M0"], t["M1"], t["M2"], codes, **kw)
 
 
+def oracle_parallel(orc, t, codes, seeds=(), threads=None):
+    """The oracle over many SNPs at the benched shapes: SNP chunks on host threads (the C call releases the GIL; L and U1 are
+    shared, not copied).  Returns (per-SNP dict of the ORIG task, {seed: min_pval})."""
+    from concurrent.futures import ThreadPoolExecutor
+    M = codes.shape[0]
+    threads = threads or max(1, min(os.cpu_count() or 1, 32, M))
+    cuts = np.linspace(0, M, threads + 1).astype(int)
+    chunks = [(cuts[i], cuts[i + 1]) for i in range(threads) if cuts[i + 1] > cuts[i]]
+    jobs = [(sd, lo, hi) for sd in (0, *seeds) for lo, hi in chunks]
+    with ThreadPoolExecutor(threads) as ex:
+        outs = list(ex.map(lambda j: oracle_run(orc, t, codes[j[1]:j[2]], seed=int(j[0])), jobs))
+    orig = [o for (sd, _, _), o in zip(jobs, outs) if sd == 0]
+    per_snp = {k2: np.concatenate([o[k2] for o in orig]) for k2 in ("chisq", "df", "pval", "rank", "pivot", "coef")}
+    minp = {int(sd): min(o["min_pval"] for (s2, _, _), o in zip(jobs, outs) if s2 == sd) for sd in seeds}
+    return per_snp, minp
+
+
+def pick_fields(r, idx):
+    return {k2: r[k2][idx] for k2 in ("lrt_df", "rank", "pivot", "pval", "lrt_chisq", "coef")}
+
+
 def compare(r, o):
     assert np.array_equal(r["lrt_df"], o["df"])
     assert np.array_equal(r["rank"], o["rank"])
@@ -315,6 +336,28 @@ def test_big_sample_against_oracle(fx, orc, big):
     pick = np.array([0, 1, 2, 3000, 5999])
     o = oracle_run(orc, t, t["codes_raw"][pick])
     compare({k2: r[k2][pick] for k2 in ("lrt_df", "rank", "pivot", "pval", "lrt_chisq", "coef")}, o)
+
+
+def test_c2_shape_256_snps_and_two_seeds_against_oracle(fx, orc, big):
+    """The headline shape (BASELINE configs[1]: n = 5,000, y ~ x + cov1 vs y ~ cov1, int8 route): 256 SNPs spread over the
+    run against the oracle for every per-SNP output, and min_pval of three seeds against the oracle's PERM tasks over the
+    same 256 SNPs (fit_model.nf:96-143 literally: the whole design re-whitened per SNP and per task)."""
+    t, fm, r = big
+    assert fm.stats()["int8_path"] == 1
+    pick = np.unique(np.linspace(0, 5999, 256).astype(int))
+    o, minp = oracle_parallel(orc, t, t["codes_raw"][pick], seeds=(1, 2, 100))
+    compare(pick_fields(r, pick), o)
+    r_sub = fm.run((pick + 1).astype(np.int32), per_snp=False)
+    assert r_sub["nvars_tested"] == pick.size
+    assert_logp_close(r_sub["min_pval"][[0, 1, 99]], [minp[1], minp[2], minp[100]])
+    # same SNPs on the FP64 route
+    with fx.FitModel(int8=False) as f2:
+        f2.set_whitening(t["L"]); f2.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); f2.set_design(t["M0"], t["M1"], t["M2"])
+        f2.set_perm(t["y_pred"], t["U1"], t["e_p"], [1, 2, 100]); f2.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r64 = f2.run((pick + 1).astype(np.int32))
+        assert f2.stats()["int8_path"] == 0 and f2.stats()["fallback_reason"] == 1
+    compare(r64, o)
+    assert_logp_close(r64["min_pval"], [minp[1], minp[2], minp[100]])
 
 
 def test_big_perm_path_agrees_with_orig_path(fx, big):
@@ -600,6 +643,147 @@ def test_int8_path_at_larger_n(fx, orc):
     pick = np.array([0, 150, 299])
     o = oracle_run(orc, t, t["codes_raw"][pick])
     compare({k2: r8[k2][pick] for k2 in ("lrt_df", "rank", "pivot", "pval", "lrt_chisq", "coef")}, o)
+
+
+@pytest.fixture(scope="module")
+def c3_task():
+    from flexlmm_b200 import synth
+    return synth.task(20000, 64, model="domgxe", P=1, seed=6, effect=0.03)
+
+
+@pytest.mark.parametrize("int8", [True, False])
+def test_c3_shape_slice_against_oracle(fx, orc, c3_task, int8):
+    """BASELINE configs[2] shape: n = 20,000, y ~ x + I(x == 1) + x:cov1 + cov1 vs y ~ cov1 (k = 5, s = 3): 64 SNPs, every
+    per-SNP output and the min_pval of seed 1 against the oracle, on the int8 route (5 pass units) and on the FP64 route."""
+    t = c3_task
+    o, minp = oracle_parallel(orc, t, t["codes_raw"], seeds=(1,))
+    with fx.FitModel(int8=int8) as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_perm(t["y_pred"], t["U1"], t["e_p"], t["seeds"]); fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r = fm.run(np.arange(1, 65, dtype=np.int32))
+        st = fm.stats()
+    assert st["int8_path"] == (1 if int8 else 0) and (not int8 or st["int8_passes"] == 5)
+    compare(r, o)
+    assert_logp_close(r["min_pval"], [minp[1]])
+
+
+def _structured_factor(n, seed):
+    """A non-singular lower-triangular factor without an n^3 host Cholesky: strict lower triangle of a rank-6 product plus a
+    positive diagonal (column blocks, so that the 8 n^2-byte matrix is written once)."""
+    rng = np.random.default_rng(seed)
+    L = np.zeros((n, n), order="F")
+    U = rng.standard_normal((n, 6)) * (1.5 / np.sqrt(n)); W = rng.standard_normal((n, 6))
+    for j0 in range(0, n, 2048):
+        j1 = min(n, j0 + 2048)
+        L[:, j0:j1] = np.tril(U @ W[j0:j1].T, k=-(j0 + 1))
+    L[np.arange(n), np.arange(n)] = 0.8 + 0.4 * rng.random(n)
+    return L
+
+
+def test_c4_shape_n50000_against_oracle(fx, orc):
+    """BASELINE configs[3] shape (n = 50,000, additive, one LOCO factor): a 20 GB factor inverted in place on the device, int8 route
+    against the FP64 route on 600 SNPs and against the oracle on 4 of them, permutations from the implicit complement."""
+    import scipy.linalg as sla
+    from flexlmm_b200 import synth
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 0
+    if avail < 60 * 2 ** 30:
+        pytest.skip("needs 60 GB of free host memory for the 20 GB factor and the oracle's copies")
+    n, M = 50000, 600
+    L = _structured_factor(n, 50)
+    M0, M1, M2, names, Xn, nn, cov1 = synth.design("additive", n, seed=3)
+    codes = synth.genotypes(M, n, seed=5)
+    rng = np.random.default_rng(8)
+    y = 0.3 * cov1 + L @ rng.standard_normal(n) + 0.05 * codes[0]
+    y_mm = sla.solve_triangular(L, y, lower=True, check_finite=False)
+    X_mm = np.asfortranarray(sla.solve_triangular(L, Xn, lower=True, check_finite=False))
+    nf = fx.fit_null_model(X_mm, y_mm)
+    packed = synth.pack_2bit(codes)
+    vi = np.arange(1, M + 1, dtype=np.int32)
+    res = {}
+    for int8 in (True, False):
+        with fx.FitModel(int8=int8) as fm:
+            fm.set_whitening(L); fm.set_null(X_mm, y_mm, nf["ll"], nf["df"]); fm.set_design(M0, M1, M2)
+            fm.set_perm_implicit([1, 2, 3]); fm.set_packed(packed, n)
+            res[int8] = fm.run(vi)
+            assert fm.stats()["int8_path"] == (1 if int8 else 0)
+    np.testing.assert_allclose(res[True]["lrt_chisq"], res[False]["lrt_chisq"], rtol=2e-9, atol=1e-9)
+    assert_logp_close(res[True]["pval"], res[False]["pval"])
+    assert_logp_close(res[True]["min_pval"], res[False]["min_pval"])
+    pick = np.array([0, 7, 311, 599])
+    t = dict(L=L, y_mm=y_mm, X_null=X_mm, ll_null=nf["ll"], df_null=nf["df"], M0=M0, M1=M1, M2=M2)
+    o, _ = oracle_parallel(orc, t, codes[pick], threads=4)
+    compare(pick_fields(res[True], pick), o)
+    compare(pick_fields(res[False], pick), o)
+
+
+def test_two_factors_on_one_handle(fx, orc):
+    """LOCO gives every chromosome its own Cholesky factor (lmm.nf:27-46): re-setting the whitening matrix, null model and
+    permutations on a LIVE handle must give bit for bit what two fresh handles give, and both must match the oracle."""
+    from flexlmm_b200 import synth
+    ta = synth.task(700, 150, model="additive", P=3, seed=41)
+    tb = synth.task(700, 150, model="additive", P=3, seed=42)
+    tc = synth.task(450, 90, model="additive", P=3, seed=43)          # a different n on the same handle
+    vi = np.arange(1, 151, dtype=np.int32)
+    fresh = []
+    for t in (ta, tb):
+        with make(fx, t) as fm:
+            fresh.append(fm.run(vi))
+    fm = make(fx, ta)
+    live = [fm.run(vi)]
+    for t in (tb, tc):
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_perm(t["y_pred"], t["U1"], t["e_p"], t["seeds"]); fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        live.append(fm.run(np.arange(1, t["M"] + 1, dtype=np.int32)))
+    fm.close()
+    for a, b in zip(fresh, live[:2]):
+        for k2 in ("lrt_chisq", "pval", "coef", "pivot", "min_pval"):
+            assert np.array_equal(a[k2], b[k2], equal_nan=True), k2
+    for t, r in zip((ta, tb, tc), live):
+        compare(r, oracle_run(orc, t, t["codes_raw"]))
+        want = np.array([oracle_run(orc, t, t["codes_raw"], seed=int(sd))["min_pval"] for sd in t["seeds"]])
+        assert_logp_close(r["min_pval"], want)
+    # a stale null model (vectors of the old n) must be refused, not read past its end
+    with make(fx, tc) as f2:
+        f2.set_whitening(ta["L"])
+        f2.set_packed(ta["packed"], ta["n_raw"], ta["pgen_order"])
+        with pytest.raises(fx.FlxError):
+            f2.run(vi)
+
+
+@pytest.mark.parametrize("int8", [True, False])
+def test_perm_minp_when_the_null_lacks_a_constant_column_of_the_real_model(fx, orc, int8):
+    """y ~ x + cov1 against y ~ 1: lrt_df = 2 > s = 1 for every SNP.  The permutation maxima are bucketed by the rank the SNP
+    columns add, not by lrt_df itself, so min_pval must follow the oracle (it used to come back as 2.0)."""
+    from flexlmm_b200 import synth
+    n = 220
+    t = synth.task(n, 60, model="additive", P=4, seed=15)
+    t["codes_raw"][7] = 1                                             # a monomorphic SNP: lrt_df = 1 from cov1 alone
+    t["packed"] = synth.pack_2bit(t["codes_raw"])
+    t["X_null"] = orc.forwardsolve(t["L"], np.ones((n, 1)))
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    for k2 in ("ll", "df", "y_pred", "U1", "e_p"):
+        t[{"ll": "ll_null", "df": "df_null"}.get(k2, k2)] = nm[k2]
+    with fx.FitModel(int8=int8) as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_perm(t["y_pred"], t["U1"], t["e_p"], t["seeds"]); fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r = fm.run(np.arange(1, 61, dtype=np.int32))
+    o = oracle_run(orc, t, t["codes_raw"])
+    compare(r, o)
+    assert sorted(set(r["lrt_df"].tolist())) == [1, 2]
+    want = np.array([oracle_run(orc, t, t["codes_raw"], seed=int(sd))["min_pval"] for sd in t["seeds"]])
+    assert np.all(want <= 1.0)
+    assert_logp_close(r["min_pval"], want)
+    # only SNPs without any SNP contribution: the bucket that is counted but never reduced
+    r1 = None
+    with fx.FitModel(int8=int8) as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_perm(t["y_pred"], t["U1"], t["e_p"], t["seeds"]); fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r1 = fm.run(np.array([8], dtype=np.int32))
+    want1 = np.array([oracle_run(orc, t, t["codes_raw"][7:8], seed=int(sd))["min_pval"] for sd in t["seeds"]])
+    assert_logp_close(r1["min_pval"], want1)
 
 
 @pytest.mark.parametrize("int8", [True, False])
