@@ -15,10 +15,14 @@ FLX_MAX_S = 8
 ERR_NAMES = {0: "FLX_OK", -1: "FLX_ERR_BAD_ARG", -2: "FLX_ERR_MISSING_GENOTYPE", -3: "FLX_ERR_CUDA", -4: "FLX_ERR_NCCL",
              -5: "FLX_ERR_OOM", -6: "FLX_ERR_PGEN", -7: "FLX_ERR_STATE", -8: "FLX_ERR_NO_DEVICE"}
 
-EXPORTS = ["flx_last_error", "flx_version", "flx_device_count", "flx_create", "flx_destroy", "flx_set_whitening", "flx_decorrelate",
+EXPORTS = ["flx_last_error", "flx_version", "flx_device_count", "flx_create", "flx_destroy", "flx_set_whitening", "flx_whitening_begin",
+           "flx_whitening_cols", "flx_whitening_end", "flx_decorrelate",
            "flx_set_null", "flx_set_design", "flx_set_perm", "flx_set_perm_implicit", "flx_fit_null_model", "flx_open_pgen", "flx_pgen_info", "flx_set_packed", "flx_make_resident",
-           "flx_run", "flx_get_stats", "flx_perm_indices", "flx_decode_tile", "flx_whiten", "flx_comm_unique_id",
-           "flx_comm_attach", "flx_minp_threshold"]
+           "flx_run", "flx_prepare", "flx_get_stats", "flx_perm_indices", "flx_decode_tile", "flx_whiten", "flx_comm_unique_id",
+           "flx_comm_attach", "flx_minp_threshold", "flx_set_whitening_bcast", "flx_set_perm_bcast", "flx_multi_create", "flx_multi_destroy",
+           "flx_multi_device_count", "flx_multi_set_whitening", "flx_multi_set_null", "flx_multi_set_design", "flx_multi_set_perm",
+           "flx_multi_set_perm_implicit", "flx_multi_open_pgen", "flx_multi_set_packed", "flx_multi_make_resident", "flx_multi_prepare",
+           "flx_multi_run", "flx_multi_get_stats"]
 
 
 class FlxError(RuntimeError):
@@ -72,6 +76,9 @@ def load(build_if_missing=True):
     L.flx_destroy.argtypes = [vp]
     L.flx_destroy.restype = None
     L.flx_set_whitening.argtypes = [vp, vp, i64, i64, C.c_int]
+    L.flx_whitening_begin.argtypes = [vp, i64]
+    L.flx_whitening_cols.argtypes = [vp, i64, i64, vp, i64]
+    L.flx_whitening_end.argtypes = [vp, C.c_int]
     L.flx_decorrelate.argtypes = [vp, vp, i64, dbl, dbl, vp, vp, i32, dbl, dbl, vp, vp, vp, C.POINTER(i32)]
     L.flx_set_null.argtypes = [vp, vp, i32, vp, dbl, i32]
     L.flx_set_design.argtypes = [vp, vp, vp, vp, i32]
@@ -83,12 +90,30 @@ def load(build_if_missing=True):
     L.flx_set_packed.argtypes = [vp, vp, i64, i64, i64, vp, i64]
     L.flx_make_resident.argtypes = [vp]
     L.flx_run.argtypes = [vp, vp, i64, C.POINTER(FlxSnpOut), vp, C.POINTER(i64)]
+    L.flx_prepare.argtypes = [vp]
     L.flx_get_stats.argtypes = [vp, C.POINTER(FlxStats)]
     L.flx_perm_indices.argtypes = [i32, i64, vp]
     L.flx_decode_tile.argtypes = [vp, vp, i64, vp, vp]
     L.flx_whiten.argtypes = [vp, vp, i64, vp]
     L.flx_comm_unique_id.argtypes = [vp]
     L.flx_comm_attach.argtypes = [vp, vp, i32, i32]
+    L.flx_set_whitening_bcast.argtypes = [vp, vp, i64, i64, C.c_int, i32]
+    L.flx_set_perm_bcast.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32]
+    L.flx_multi_create.argtypes = [C.POINTER(FlxConfig), vp, i32, C.POINTER(vp)]
+    L.flx_multi_destroy.argtypes = [vp]
+    L.flx_multi_destroy.restype = None
+    L.flx_multi_device_count.argtypes = [vp]
+    L.flx_multi_set_whitening.argtypes = [vp, vp, i64, i64, C.c_int]
+    L.flx_multi_set_null.argtypes = [vp, vp, i32, vp, dbl, i32]
+    L.flx_multi_set_design.argtypes = [vp, vp, vp, vp, i32]
+    L.flx_multi_set_perm.argtypes = [vp, vp, vp, vp, i64, vp, i32]
+    L.flx_multi_set_perm_implicit.argtypes = [vp, vp, i32]
+    L.flx_multi_open_pgen.argtypes = [vp, C.c_char_p, vp, i64]
+    L.flx_multi_set_packed.argtypes = [vp, vp, i64, i64, i64, vp, i64]
+    L.flx_multi_make_resident.argtypes = [vp]
+    L.flx_multi_prepare.argtypes = [vp]
+    L.flx_multi_run.argtypes = [vp, vp, i64, C.POINTER(FlxSnpOut), vp, C.POINTER(i64)]
+    L.flx_multi_get_stats.argtypes = [vp, i32, C.POINTER(FlxStats)]
     L.flx_minp_threshold.argtypes = [vp, i64, dbl]
     L.flx_minp_threshold.restype = dbl
     _LIB = L

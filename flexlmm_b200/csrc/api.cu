@@ -91,13 +91,15 @@ struct flx_handle {
     std::vector<cudaEvent_t> ev_pool;    // stage stopwatch events, created once and reused by every run
     cublasHandle_t cublas = nullptr;
     ncclComm_t comm = nullptr;
-    int nranks = 1;
+    int nranks = 1, comm_rank = 0;
 
     // whitening
     int64_t n = 0, n_pad = 0;
     int KC = 0, T = 0;
     DevBuf<double> linv;     // triangular packed panels
     DevBuf<double> Zdense;   // dense L^-1 (kept until finalize when the int8 path may be used)
+    DevBuf<double> Lstage;   // flx_whitening_begin / _cols / _end: the factor being assembled on the device
+    int64_t Lstage_n = 0;
     bool have_Z = false;
     // null model
     bool have_null = false;
@@ -155,6 +157,7 @@ struct flx_handle {
     PgenFile* pgen = nullptr;
     const uint8_t* packed_host = nullptr;
     bool host_registered = false;
+    bool host_pinned_by_owner = false;   // a flx_multi pinned packed_host once for all of its handles
     int64_t src_variants = 0, bpv = 0, raw_n = 0;
     std::vector<int32_t> order0;
     bool identity_order = true;
@@ -257,8 +260,37 @@ extern "C" void flx_destroy(flx_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// A = L dense on the device (n x n column-major, ld = n) -> L^-1 in place: LAPACK dtrtri's blocked lower-triangular sweep (last
+// block column first) on plain library trmm / trsm calls — setup only, outside the hot loop.  (cusolverDnXtrtri refuses n = 10^5.)
+static int invert_lower_in_place(flx_handle* h, double* A, int64_t n) {
+    std::vector<double> dg(n);
+    FLX_CUDA_TRY(cudaMemcpy2DAsync(dg.data(), sizeof(double), A, (n + 1) * sizeof(double), sizeof(double), n, cudaMemcpyDeviceToHost, h->stream));
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < n; i++)
+        if (!(dg[i] != 0.0) || !std::isfinite(dg[i])) { set_error("flx_set_whitening: L is singular or not finite (diagonal entry %lld)", (long long)i + 1); return FLX_ERR_BAD_ARG; }
+    const int64_t nb = 1024;
+    const double one = 1.0, mone = -1.0;
+    DevBuf<double> Tb;
+    FLX_TRY(Tb.ensure((size_t)nb * nb));
+    for (int64_t j = ((n - 1) / nb) * nb; j >= 0; j -= nb) {
+        const int64_t jb = std::min(nb, n - j), rest = n - j - jb;
+        if (rest > 0) {
+            FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, rest, jb, &one,
+                                          A + (j + jb) + (j + jb) * n, n, A + (j + jb) + j * n, n, A + (j + jb) + j * n, n));
+            FLX_CUBLAS_TRY(cublasDtrsm_64(h->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, rest, jb, &mone,
+                                          A + j + j * n, n, A + (j + jb) + j * n, n));
+        }
+        // diagonal block: solve against the identity, copy the lower triangle back
+        FLX_TRY(launch_set_identity(Tb.p, jb, jb, h->stream));
+        FLX_CUBLAS_TRY(cublasDtrsm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, jb, jb, &one, A + j + j * n, n, Tb.p, jb));
+        FLX_CUDA_TRY(cudaMemcpy2DAsync(A + j + j * n, n * sizeof(double), Tb.p, jb * sizeof(double), jb * sizeof(double), jb, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLX_OK;
+}
+
 // src: L (or L^-1) dense on the device, n x n column-major with leading dimension n.  The buffer is CONSUMED: it becomes
-// h->Zdense and is inverted in place (cusolverDnXtrtri), so that the setup of n = 10^5 holds one dense matrix (80 GB), not two.
+// h->Zdense and is inverted in place, so that the setup of n = 10^5 holds one dense matrix (80 GB), not two.
 static int whitening_from_device(flx_handle* h, DevBuf<double>& src, int64_t n, int is_inverse) {
     if (h->n > 0 && n != h->n) {
         // null model, design and permutation inputs are vectors of the OLD n: they must be given again
@@ -272,33 +304,7 @@ static int whitening_from_device(flx_handle* h, DevBuf<double>& src, int64_t n, 
     h->dirty = true;
     h->Zdense.release();
     h->Zdense.swap(src);
-    if (!is_inverse) {
-        // Z = L^-1 in place: LAPACK dtrtri's blocked lower-triangular sweep (last block column first) on plain library
-        // trmm / trsm calls — setup only, outside the hot loop.  (cusolverDnXtrtri refuses n = 10^5.)
-        std::vector<double> dg(n);
-        FLX_CUDA_TRY(cudaMemcpy2DAsync(dg.data(), sizeof(double), h->Zdense.p, (n + 1) * sizeof(double), sizeof(double), n, cudaMemcpyDeviceToHost, h->stream));
-        FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
-        for (int64_t i = 0; i < n; i++)
-            if (!(dg[i] != 0.0) || !std::isfinite(dg[i])) { set_error("flx_set_whitening: L is singular or not finite (diagonal entry %lld)", (long long)i + 1); return FLX_ERR_BAD_ARG; }
-        const int64_t nb = 1024;
-        const double one = 1.0, mone = -1.0;
-        DevBuf<double> Tb;
-        FLX_TRY(Tb.ensure((size_t)nb * nb));
-        double* A = h->Zdense.p;
-        for (int64_t j = ((n - 1) / nb) * nb; j >= 0; j -= nb) {
-            const int64_t jb = std::min(nb, n - j), rest = n - j - jb;
-            if (rest > 0) {
-                FLX_CUBLAS_TRY(cublasDtrmm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, rest, jb, &one,
-                                              A + (j + jb) + (j + jb) * n, n, A + (j + jb) + j * n, n, A + (j + jb) + j * n, n));
-                FLX_CUBLAS_TRY(cublasDtrsm_64(h->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, rest, jb, &mone,
-                                              A + j + j * n, n, A + (j + jb) + j * n, n));
-            }
-            // diagonal block: solve against the identity, copy the lower triangle back
-            FLX_TRY(launch_set_identity(Tb.p, jb, jb, h->stream));
-            FLX_CUBLAS_TRY(cublasDtrsm_64(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, jb, jb, &one, A + j + j * n, n, Tb.p, jb));
-            FLX_CUDA_TRY(cudaMemcpy2DAsync(A + j + j * n, n * sizeof(double), Tb.p, jb * sizeof(double), jb * sizeof(double), jb, cudaMemcpyDeviceToDevice, h->stream));
-        }
-    }
+    if (!is_inverse) FLX_TRY(invert_lower_in_place(h, h->Zdense.p, n));
     FLX_TRY(launch_zero_upper(h->Zdense.p, n, n, h->stream));      // the strict upper triangle of the caller's matrix may carry anything
     h->have_Z = true;
     FLX_TRY(h->linv.ensure((size_t)tri_chunks_before(h->T) * CHUNK));
@@ -307,14 +313,83 @@ static int whitening_from_device(flx_handle* h, DevBuf<double>& src, int64_t n, 
     return FLX_OK;
 }
 
+extern "C" int flx_whitening_begin(flx_handle* h, int64_t n) {
+    if (!h || n <= 0) { set_error("flx_whitening_begin: bad arguments"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->Zdense.release(); h->have_Z = false;          // the previous factor's dense inverse goes first: one n x n matrix at a time
+    h->Lstage.release();
+    FLX_TRY(h->Lstage.ensure((size_t)n * n));
+    h->Lstage_n = n;
+    return FLX_OK;
+}
+
+extern "C" int flx_whitening_cols(flx_handle* h, int64_t j0, int64_t ncols, const double* cols, int64_t ld) {
+    if (!h || !cols || j0 < 0 || ncols <= 0) { set_error("flx_whitening_cols: bad arguments"); return FLX_ERR_BAD_ARG; }
+    const int64_t n = h->Lstage_n;
+    if (n <= 0 || !h->Lstage.p) { set_error("flx_whitening_cols: call flx_whitening_begin first"); return FLX_ERR_STATE; }
+    if (j0 + ncols > n || ld < n) { set_error("flx_whitening_cols: columns %lld..%lld / ld %lld do not fit n = %lld", (long long)j0, (long long)(j0 + ncols), (long long)ld, (long long)n); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    // cudaMemcpyDefault: `cols` may be host memory (R's matrix) or device memory (a factor produced on the GPU)
+    FLX_CUDA_TRY(cudaMemcpy2DAsync(h->Lstage.p + j0 * n, n * sizeof(double), cols, ld * sizeof(double), n * sizeof(double), ncols, cudaMemcpyDefault, h->stream));
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));      // the caller may reuse `cols` as soon as this returns
+    return FLX_OK;
+}
+
+extern "C" int flx_whitening_end(flx_handle* h, int is_inverse) {
+    if (!h) { set_error("flx_whitening_end: NULL handle"); return FLX_ERR_BAD_ARG; }
+    if (h->Lstage_n <= 0 || !h->Lstage.p) { set_error("flx_whitening_end: call flx_whitening_begin first"); return FLX_ERR_STATE; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int64_t n = h->Lstage_n;
+    h->Lstage_n = 0;
+    return whitening_from_device(h, h->Lstage, n, is_inverse);
+}
+
 extern "C" int flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse) {
     if (!h || !L || n <= 0 || ld < n) { set_error("flx_set_whitening: bad arguments"); return FLX_ERR_BAD_ARG; }
+    FLX_TRY(flx_whitening_begin(h, n));
+    FLX_TRY(flx_whitening_cols(h, 0, n, L, ld));
+    return flx_whitening_end(h, is_inverse);
+}
+
+// min over the ranks of a status word (0 = ok, negative = error): nobody enters a large collective after a local failure elsewhere
+static int comm_min_status(flx_handle* h, int rc) {
+    if (!h->comm || h->nranks < 2) return rc;
+    long long w = rc;
+    if (h->coll_d.ensure(2) != 0 || cudaMemcpyAsync(h->coll_d.p, &w, sizeof(w), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+        ncclAllReduce(h->coll_d.p, h->coll_d.p, 1, ncclInt64, ncclMin, h->comm, h->stream) != ncclSuccess ||
+        cudaMemcpyAsync(&w, h->coll_d.p, sizeof(w), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        if (rc == FLX_OK) { set_error("status exchange over the communicator failed"); return FLX_ERR_NCCL; }
+        return rc;
+    }
+    if (rc == FLX_OK && w != FLX_OK) { set_error("another rank of the communicator failed with status %lld", w); return (int)w; }
+    return rc;
+}
+
+extern "C" int flx_set_whitening_bcast(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse, int32_t root) {
+    if (!h || n <= 0) { set_error("flx_set_whitening_bcast: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (!h->comm || h->nranks < 2) return flx_set_whitening(h, L, n, ld, is_inverse);
+    if (root < 0 || root >= h->nranks) { set_error("flx_set_whitening_bcast: root %d outside the communicator (%d ranks)", root, h->nranks); return FLX_ERR_BAD_ARG; }
     FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
-    h->Zdense.release(); h->have_Z = false;
-    DevBuf<double> Ld;
-    FLX_TRY(Ld.ensure((size_t)n * n));
-    FLX_CUDA_TRY(cudaMemcpy2DAsync(Ld.p, n * sizeof(double), L, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, h->stream));
-    return whitening_from_device(h, Ld, n, is_inverse);
+    int rc = FLX_OK;
+    if (h->comm_rank == root) {
+        // the one rank that holds the factor uploads it (once per box) and inverts it
+        if (!L || ld < n) { set_error("flx_set_whitening_bcast: the root rank must pass L"); rc = FLX_ERR_BAD_ARG; }
+        if (rc == FLX_OK) rc = flx_whitening_begin(h, n);
+        if (rc == FLX_OK) rc = flx_whitening_cols(h, 0, n, L, ld);
+        if (rc == FLX_OK && !is_inverse) rc = invert_lower_in_place(h, h->Lstage.p, n);
+    } else {
+        h->Zdense.release(); h->have_Z = false;
+        h->Lstage.release();
+        rc = h->Lstage.ensure((size_t)n * n);
+    }
+    rc = comm_min_status(h, rc);
+    if (rc != FLX_OK) { h->Lstage.release(); h->Lstage_n = 0; return rc; }
+    // L^-1 travels GPU to GPU over NVLink / NVSwitch: n^2 * 8 bytes once, instead of one host upload and one inversion per GPU
+    ncclResult_t r = ncclBroadcast(h->Lstage.p, h->Lstage.p, (size_t)n * (size_t)n, ncclDouble, root, h->comm, h->stream);
+    if (r != ncclSuccess) { set_error("ncclBroadcast of L^-1 failed: %s", ncclGetErrorString(r)); return FLX_ERR_NCCL; }
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->Lstage_n = 0;
+    return whitening_from_device(h, h->Lstage, n, 1);
 }
 
 #define FLX_CUSOLVER_TRY(expr)                                                             \
@@ -441,6 +516,30 @@ extern "C" int flx_set_perm(flx_handle* h, const double* y_pred, const double* U
     return FLX_OK;
 }
 
+extern "C" int flx_set_perm_bcast(flx_handle* h, const double* y_pred, const double* U1, const double* e_p, int64_t m, const int32_t* seeds, int32_t P, int32_t root) {
+    if (!h) { set_error("flx_set_perm_bcast: NULL handle"); return FLX_ERR_BAD_ARG; }
+    if (!h->comm || h->nranks < 2 || P == 0) return flx_set_perm(h, y_pred, U1, e_p, m, seeds, P);
+    if (root < 0 || root >= h->nranks) { set_error("flx_set_perm_bcast: root %d outside the communicator (%d ranks)", root, h->nranks); return FLX_ERR_BAD_ARG; }
+    int rc = FLX_OK;
+    if (!y_pred || !e_p || !seeds || m <= 0 || P < 0 || (h->comm_rank == root && !U1)) { set_error("flx_set_perm_bcast: bad arguments"); rc = FLX_ERR_BAD_ARG; }
+    else if (h->n <= 0) { set_error("flx_set_perm_bcast: call flx_set_whitening first"); rc = FLX_ERR_STATE; }
+    if (rc == FLX_OK && cudaSetDevice(h->cfg.device) != cudaSuccess) rc = FLX_ERR_CUDA;
+    if (rc == FLX_OK) rc = h->U1_d.ensure((size_t)h->n * m);
+    if (rc == FLX_OK && h->comm_rank == root && cudaMemcpy(h->U1_d.p, U1, (size_t)h->n * m * sizeof(double), cudaMemcpyDefault) != cudaSuccess) { set_error("flx_set_perm_bcast: upload of U1 failed"); rc = FLX_ERR_CUDA; }
+    rc = comm_min_status(h, rc);
+    if (rc != FLX_OK) return rc;
+    // U1 (n x m, as large as L) crosses the host link once per box; the other GPUs receive it over NVLink
+    ncclResult_t r = ncclBroadcast(h->U1_d.p, h->U1_d.p, (size_t)h->n * (size_t)m, ncclDouble, root, h->comm, h->stream);
+    if (r != ncclSuccess) { set_error("ncclBroadcast of U1 failed: %s", ncclGetErrorString(r)); return FLX_ERR_NCCL; }
+    FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->y_pred.assign(y_pred, y_pred + h->n);
+    h->e_p.assign(e_p, e_p + m);
+    h->m = m;
+    h->seeds.assign(seeds, seeds + P);
+    h->P = P; h->have_perm = true; h->perm_implicit = false; h->dirty = true;
+    return FLX_OK;
+}
+
 extern "C" int flx_set_perm_implicit(flx_handle* h, const int32_t* seeds, int32_t P) {
     if (!h || P < 0 || (P > 0 && !seeds)) { set_error("flx_set_perm_implicit: bad arguments"); return FLX_ERR_BAD_ARG; }
     if (P == 0) { h->have_perm = false; h->P = 0; h->dirty = true; return FLX_OK; }
@@ -515,13 +614,15 @@ extern "C" int flx_pgen_info(flx_handle* h, int64_t* variant_ct, int64_t* sample
     return FLX_OK;
 }
 
-extern "C" int flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n) {
+// pinned_by_owner: a flx_multi registered the buffer once (portable) for all of its handles
+static int set_packed_impl(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n, bool pinned_by_owner) {
     if (!h || !packed || n_variants < 0 || raw_sample_ct <= 0 || bytes_per_variant < (raw_sample_ct + 3) / 4 || n <= 0) { set_error("flx_set_packed: bad arguments"); return FLX_ERR_BAD_ARG; }
     if (h->host_registered && h->packed_host) { cudaHostUnregister(const_cast<uint8_t*>(h->packed_host)); h->host_registered = false; }
     h->src = 2;
     h->packed_host = packed;
+    h->host_pinned_by_owner = pinned_by_owner;
     // pin the caller's buffer in place so batches go H2D by DMA straight from it (no staging copy); harmless if it fails
-    if (cudaSetDevice(h->cfg.device) == cudaSuccess && n_variants * bytes_per_variant >= (1 << 20)) {
+    if (!pinned_by_owner && cudaSetDevice(h->cfg.device) == cudaSuccess && n_variants * bytes_per_variant >= (1 << 20)) {
         if (cudaHostRegister(const_cast<uint8_t*>(packed), (size_t)n_variants * bytes_per_variant, cudaHostRegisterReadOnly) == cudaSuccess ||
             (cudaGetLastError(), cudaHostRegister(const_cast<uint8_t*>(packed), (size_t)n_variants * bytes_per_variant, cudaHostRegisterDefault) == cudaSuccess))
             h->host_registered = true;
@@ -532,6 +633,10 @@ extern "C" int flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_va
     h->raw_n = raw_sample_ct;
     h->bpv = bytes_per_variant;
     return set_order(h, pgen_order, n, raw_sample_ct);
+}
+
+extern "C" int flx_set_packed(flx_handle* h, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n) {
+    return set_packed_impl(h, packed, n_variants, bytes_per_variant, raw_sample_ct, pgen_order, n, false);
 }
 
 extern "C" int flx_make_resident(flx_handle* h) {
@@ -1051,7 +1156,6 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         FLX_CUDA_TRY(cudaMemsetAsync(h->df_count.p, 0, 16 * sizeof(int), h->stream));
         if (do_perm) FLX_CUDA_TRY(cudaMemsetAsync(h->maxratio.p, 0, (size_t)h->s * h->P_pad * sizeof(double), h->stream));
     }
-    if (!decode_only) FLX_TRY(upload_fit_const(h->fc));
 
     // stage stopwatch: events come from the handle's pool (created once, reused by every run; nothing to leak on an early return)
     size_t nev = 0;
@@ -1078,7 +1182,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             FLX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_used[buf], 0));   // the decode of batch b-2 has read this buffer
             const uint8_t* src_ptr = nullptr;
             bool expanded_on_device = false;
-            if (h->src == 2 && contiguous && h->host_registered) {
+            if (h->src == 2 && contiguous && (h->host_registered || h->host_pinned_by_owner)) {
                 src_ptr = h->packed_host + (size_t)(var_idx[s0] - 1) * bpv;          // pinned in place: no staging copy
             } else {
                 if (bi >= 2) FLX_CUDA_TRY(cudaEventSynchronize(h->ev_h2d[buf]));      // the staging buffer's previous H2D is done
@@ -1291,7 +1395,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         sa.fast = use_fast ? 1 : 0; sa.qf_part = h->qf_part.p; sa.qf_nparts = h->T256 * h->Q;
         memcpy(sa.slot_a, h->plan.slot_a, sizeof(sa.slot_a)); memcpy(sa.slot_b, h->plan.slot_b, sizeof(sa.slot_b));
         sa.refit_flag = use_fast ? h->refit_flag.p + s0 : nullptr;
-        FLX_TRY(launch_snp_solve(sa, h->stream));
+        FLX_TRY(launch_snp_solve(sa, h->fc, h->stream));
         h->stats.launches += 1;
         if (want_results && !out_map_host) {
             // this batch's per-SNP results go to pinned staging while the permutation pass and the next batch run
@@ -1349,6 +1453,13 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         set_error("missing genotype (NA hard call) in tested variant var_idx[%d]=%d: the reference aborts on it (no imputation anywhere in the pipeline)", miss, var_idx[miss]);
         return FLX_ERR_MISSING_GENOTYPE;
     }
+    return FLX_OK;
+}
+
+extern "C" int flx_prepare(flx_handle* h) {
+    if (!h) { set_error("flx_prepare: NULL handle"); return FLX_ERR_BAD_ARG; }
+    FLX_CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->dirty) FLX_TRY(finalize_setup(h));
     return FLX_OK;
 }
 
@@ -1529,7 +1640,146 @@ extern "C" int flx_comm_attach(flx_handle* h, const uint8_t id[128], int32_t ran
     ncclResult_t r = ncclCommInitRank(&h->comm, nranks, u, rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", ncclGetErrorString(r)); h->comm = nullptr; return FLX_ERR_NCCL; }
     h->nranks = nranks;
+    h->comm_rank = rank;
     return FLX_OK;
+}
+
+
+// ================================================================================================
+// One caller, several GPUs (R is single-threaded, one process drives the box).  A flx_multi owns one handle per
+// device plus the NCCL communicator between them; every collective step runs on one host thread per device.
+// ================================================================================================
+struct flx_multi {
+    std::vector<flx_handle*> hs;
+    const uint8_t* pinned = nullptr;
+    ~flx_multi() {
+        if (pinned) cudaHostUnregister(const_cast<uint8_t*>(pinned));
+        for (auto h : hs) flx_destroy(h);
+    }
+};
+
+// f(handle, device index) on one thread per device; first failure (lowest index) wins, its message becomes the caller's
+template <typename F>
+static int multi_each(flx_multi* m, F f) {
+    const size_t nd = m->hs.size();
+    std::vector<int> rc(nd, 0);
+    std::vector<std::string> msg(nd);
+    auto body = [&](size_t i) { rc[i] = f(m->hs[i], (int)i); if (rc[i] != 0) msg[i] = g_err; };
+    if (nd == 1) body(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < nd; i++) th.emplace_back(body, i);
+        for (auto& t : th) t.join();
+    }
+    for (size_t i = 0; i < nd; i++)
+        if (rc[i] != 0) { set_error("device %d: %s", m->hs[i]->cfg.device, msg[i].c_str()); return rc[i]; }
+    return FLX_OK;
+}
+
+extern "C" int flx_multi_create(const flx_config* cfg, const int32_t* devices, int32_t ndev, flx_multi** out) {
+    if (!out || !devices || ndev < 1 || ndev > 64) { set_error("flx_multi_create: bad arguments"); return FLX_ERR_BAD_ARG; }
+    *out = nullptr;
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) { set_error("flx_multi_create: device %d listed twice", devices[i]); return FLX_ERR_BAD_ARG; }
+    flx_multi* m = new flx_multi();
+    for (int i = 0; i < ndev; i++) {
+        flx_config c{};
+        if (cfg) c = *cfg;
+        c.device = devices[i];
+        flx_handle* h = nullptr;
+        const int rc = flx_create(&c, &h);
+        if (rc != FLX_OK) { delete m; return rc; }
+        m->hs.push_back(h);
+    }
+    if (ndev > 1) {
+        std::vector<ncclComm_t> comms(ndev);
+        std::vector<int> devs(devices, devices + ndev);
+        ncclResult_t r = ncclCommInitAll(comms.data(), ndev, devs.data());
+        if (r != ncclSuccess) { set_error("ncclCommInitAll: %s", ncclGetErrorString(r)); delete m; return FLX_ERR_NCCL; }
+        for (int i = 0; i < ndev; i++) { m->hs[i]->comm = comms[i]; m->hs[i]->nranks = ndev; m->hs[i]->comm_rank = i; }
+    }
+    *out = m;
+    return FLX_OK;
+}
+
+extern "C" void flx_multi_destroy(flx_multi* m) { delete m; }
+extern "C" int flx_multi_device_count(flx_multi* m) { return m ? (int)m->hs.size() : 0; }
+
+extern "C" int flx_multi_set_whitening(flx_multi* m, const double* L, int64_t n, int64_t ld, int is_inverse) {
+    if (!m || !L) { set_error("flx_multi_set_whitening: bad arguments"); return FLX_ERR_BAD_ARG; }
+    // device 0 uploads and inverts; L^-1 reaches the others by ncclBroadcast over NVLink
+    return multi_each(m, [&](flx_handle* h, int i) { return flx_set_whitening_bcast(h, i == 0 ? L : nullptr, n, ld, is_inverse, 0); });
+}
+extern "C" int flx_multi_set_null(flx_multi* m, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null) {
+    if (!m) { set_error("flx_multi_set_null: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int) { return flx_set_null(h, X_null, c, y_mm, ll_null, df_null); });
+}
+extern "C" int flx_multi_set_design(flx_multi* m, const double* M0, const double* M1, const double* M2, int32_t k) {
+    if (!m) { set_error("flx_multi_set_design: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int) { return flx_set_design(h, M0, M1, M2, k); });
+}
+extern "C" int flx_multi_set_perm(flx_multi* m, const double* y_pred, const double* U1, const double* e_p, int64_t mm, const int32_t* seeds, int32_t P) {
+    if (!m) { set_error("flx_multi_set_perm: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int i) { return flx_set_perm_bcast(h, y_pred, i == 0 ? U1 : nullptr, e_p, mm, seeds, P, 0); });
+}
+extern "C" int flx_multi_set_perm_implicit(flx_multi* m, const int32_t* seeds, int32_t P) {
+    if (!m) { set_error("flx_multi_set_perm_implicit: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int) { return flx_set_perm_implicit(h, seeds, P); });
+}
+extern "C" int flx_multi_open_pgen(flx_multi* m, const char* path, const int32_t* pgen_order, int64_t n) {
+    if (!m) { set_error("flx_multi_open_pgen: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int) { return flx_open_pgen(h, path, pgen_order, n); });
+}
+extern "C" int flx_multi_set_packed(flx_multi* m, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct, const int32_t* pgen_order, int64_t n) {
+    if (!m || !packed) { set_error("flx_multi_set_packed: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (m->pinned) { cudaHostUnregister(const_cast<uint8_t*>(m->pinned)); m->pinned = nullptr; }
+    bool pinned = false;
+    if (n_variants * bytes_per_variant >= (1 << 20) && cudaSetDevice(m->hs[0]->cfg.device) == cudaSuccess) {
+        if (cudaHostRegister(const_cast<uint8_t*>(packed), (size_t)n_variants * bytes_per_variant, cudaHostRegisterPortable) == cudaSuccess) { pinned = true; m->pinned = packed; }
+        else cudaGetLastError();
+    }
+    for (auto h : m->hs) FLX_TRY(set_packed_impl(h, packed, n_variants, bytes_per_variant, raw_sample_ct, pgen_order, n, pinned));
+    return FLX_OK;
+}
+extern "C" int flx_multi_make_resident(flx_multi* m) {
+    if (!m) { set_error("flx_multi_make_resident: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int) { return flx_make_resident(h); });
+}
+extern "C" int flx_multi_prepare(flx_multi* m) {
+    if (!m) { set_error("flx_multi_prepare: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int) { return flx_prepare(h); });
+}
+
+extern "C" int flx_multi_run(flx_multi* m, const int32_t* var_idx, int64_t M, const flx_snp_out* out, double* minp, int64_t* nvars_tested) {
+    if (!m || (M > 0 && !var_idx) || M < 0) { set_error("flx_multi_run: bad arguments"); return FLX_ERR_BAD_ARG; }
+    const int64_t nd = (int64_t)m->hs.size();
+    std::vector<int64_t> nv(nd, 0);
+    // contiguous SNP blocks, one per device; per-SNP outputs land in disjoint slices of the caller's arrays (var_idx order is kept);
+    // inside flx_run the length-P min-p vector is min-allreduced and the counts summed, so every device ends with the box's result
+    const int rc = multi_each(m, [&](flx_handle* h, int i) {
+        const int64_t base = M / nd, extra = M % nd;
+        const int64_t lo = i * base + std::min<int64_t>(i, extra), cnt = base + (i < extra ? 1 : 0);
+        flx_snp_out o{};
+        const int64_t k = h->k;
+        if (out) {
+            o.lrt_chisq = out->lrt_chisq ? out->lrt_chisq + lo : nullptr; o.pval = out->pval ? out->pval + lo : nullptr;
+            o.lrt_df = out->lrt_df ? out->lrt_df + lo : nullptr;          o.rank = out->rank ? out->rank + lo : nullptr;
+            o.pivot = out->pivot ? out->pivot + lo * k : nullptr;         o.coef = out->coef ? out->coef + lo * k : nullptr;
+        }
+        std::vector<double> tmp;
+        double* mp = nullptr;
+        if (minp) { if (i == 0) mp = minp; else { tmp.resize((size_t)std::max(h->P, 1)); mp = tmp.data(); } }
+        return flx_run(h, var_idx + lo, cnt, out ? &o : nullptr, mp, &nv[i]);
+    });
+    if (rc != FLX_OK) return rc;
+    if (nvars_tested) *nvars_tested = nv[0];
+    return FLX_OK;
+}
+
+extern "C" int flx_multi_get_stats(flx_multi* m, int32_t device_index, flx_stats* out) {
+    if (!m || device_index < 0 || device_index >= (int)m->hs.size()) { set_error("flx_multi_get_stats: bad arguments"); return FLX_ERR_BAD_ARG; }
+    return flx_get_stats(m->hs[device_index], out);
 }
 
 extern "C" double flx_minp_threshold(const double* min_pval, int64_t P, double p_thr) {

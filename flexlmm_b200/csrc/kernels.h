@@ -157,8 +157,7 @@ struct SolveArgs {
     int8_t slot_a[8][8], slot_b[8][8];   // slot_b < 0: single term
     int32_t* refit_flag;      // [nsnp] set to 1 when the SNP must be re-fitted on the FP64 path (near-collinear with the constant columns)
 };
-int upload_fit_const(const FitConst& c);
-int launch_snp_solve(const SolveArgs& a, cudaStream_t st);
+int launch_snp_solve(const SolveArgs& a, const FitConst& c, cudaStream_t st);
 
 // ---------------------------------------------------------------- setup kernels (setup.cu)
 // dense column-major (n x ncols, ld) -> packed panel with k = row index, j = column index (tiles of 128 columns)

@@ -25,13 +25,9 @@
 
 namespace flx {
 
-__constant__ FitConst c_fit;
-
-int upload_fit_const(const FitConst& c) {
-    cudaError_t e = cudaMemcpyToSymbol(c_fit, &c, sizeof(FitConst));
-    if (e != cudaSuccess) { set_error("upload_fit_const: %s", cudaGetErrorString(e)); return -3; }
-    return 0;
-}
+// The per-task constants (FitConst, ~5 KB) travel as a __grid_constant__ kernel parameter (constant bank, like a __constant__
+// symbol, but private to the launch): two handles on one device — the LOCO driver sets the next chromosome's factor up while
+// the current one runs — never share mutable device state.
 
 // ------------------------------------------------------------------------------------------------
 // K3a  — two sweeps over the whitened tile, split along the sample axis for parallelism.
@@ -291,10 +287,9 @@ __device__ __forceinline__ void apply_reflector(const double* T, const double* q
     for (int i = l + 1; i < nrow; i++) v[i] += t * x[i];
 }
 
-__global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(64) snp_solve_kernel(const __grid_constant__ SolveArgs a, const __grid_constant__ FitConst c) {
     const int64_t snp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (snp >= a.nsnp) return;
-    const FitConst& c = c_fit;
     const int s = c.s, k = c.k, cr = c.cr;
     const int nr = cr + s;
     const int nrow = nr + 1;  // one zero row: the small problem must behave like n > p (dqrdc2's l == n exit never fires)
@@ -564,10 +559,10 @@ __global__ void __launch_bounds__(64) snp_solve_kernel(const SolveArgs a) {
     if (a.df_count && df > 0 && !refit) atomicAdd(&a.df_count[bucket], 1);
 }
 
-int launch_snp_solve(const SolveArgs& a, cudaStream_t st) {
+int launch_snp_solve(const SolveArgs& a, const FitConst& c, cudaStream_t st) {
     if (a.nsnp <= 0) return 0;
     const int threads = 64;
-    snp_solve_kernel<<<(unsigned)((a.nsnp + threads - 1) / threads), threads, 0, st>>>(a);
+    snp_solve_kernel<<<(unsigned)((a.nsnp + threads - 1) / threads), threads, 0, st>>>(a, c);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("snp_solve launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;

@@ -82,6 +82,18 @@ class FitModel:
         self.n = L.shape[0]
         check(self._lib.flx_set_whitening(self._h, ptr(L), self.n, self.n, int(bool(is_inverse))))
 
+    def whitening_begin(self, n):
+        """Streaming form of set_whitening (n = 100,000: the 80 GB factor exists once, on the device)."""
+        self.n = int(n)
+        check(self._lib.flx_whitening_begin(self._h, self.n))
+
+    def whitening_cols(self, j0, ncols, cols_ptr, ld):
+        """Columns [j0, j0 + ncols) of L from a raw host or device address (column-major, leading dimension ld)."""
+        check(self._lib.flx_whitening_cols(self._h, int(j0), int(ncols), int(cols_ptr), int(ld)))
+
+    def whitening_end(self, is_inverse=False):
+        check(self._lib.flx_whitening_end(self._h, int(bool(is_inverse))))
+
     def decorrelate(self, K, s2g, s2e, y, X, min_allowed_eig=-1e-6, eig_replacement=1e-10, want_L=True):
         """DECORRELATE on the GPU (decorrelate.nf:50-77).  Returns dict(L, y_mm, X_mm, clipped_eigs); the factor becomes this
         handle's whitening matrix without a host round trip."""
@@ -147,6 +159,20 @@ class FitModel:
     def make_resident(self):
         check(self._lib.flx_make_resident(self._h))
 
+    def set_whitening_bcast(self, L, n, root=0, is_inverse=False):
+        """Collective over the attached communicator: only `root` passes L (others None); L^-1 is broadcast over NVLink."""
+        self.n = int(n)
+        Lh = None if L is None else f64(L, fortran=True)
+        check(self._lib.flx_set_whitening_bcast(self._h, ptr(Lh), self.n, self.n, int(bool(is_inverse)), int(root)))
+
+    def set_perm_bcast(self, y_pred, U1, e_p, seeds, root=0):
+        """Collective: only `root` passes U1 (others None); it is uploaded once and broadcast over NVLink."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        self.P = int(seeds.size)
+        y_pred = f64(y_pred); e_p = f64(np.ravel(e_p))
+        U1h = None if U1 is None else f64(U1, fortran=True)
+        check(self._lib.flx_set_perm_bcast(self._h, ptr(y_pred), ptr(U1h), ptr(e_p), e_p.size, ptr(seeds), self.P, int(root)))
+
     def comm_attach(self, unique_id, rank, nranks):
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         assert uid.size == 128
@@ -176,6 +202,10 @@ class FitModel:
             res["min_pval"] = mp
         return res
 
+    def prepare(self):
+        """Run the once-per-task setup now (otherwise the first run() does it)."""
+        check(self._lib.flx_prepare(self._h))
+
     def stats(self):
         st = FlxStats()
         check(self._lib.flx_get_stats(self._h, C.byref(st)))
@@ -195,6 +225,96 @@ class FitModel:
         W = np.empty_like(X, order="F")
         check(self._lib.flx_whiten(self._h, ptr(X), X.shape[1], ptr(W)))
         return W
+
+
+class FitModelMulti:
+    """One FIT_MODEL task on several GPUs of one box from ONE caller thread (flx_multi_*): the factor and U1 are uploaded once
+    and broadcast over NVLink, var_idx is split into one contiguous SNP block per device, results come back in var_idx order and
+    are bit-identical to a single device's."""
+
+    def __init__(self, devices, batch_tiles=0, verbose=0, int8=True, planes=6):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        cfg = FlxConfig(0, int(batch_tiles), int(verbose), (0 if int8 else 1) | (4 if planes == 5 else 0))
+        check(self._lib.flx_multi_create(C.byref(cfg), ptr(devs), devs.size, C.byref(self._h)))
+        self.ndev = int(devs.size)
+        self._keep = {}
+        self.n = self.k = None
+        self.P = 0
+
+    def close(self):
+        if self._h:
+            self._lib.flx_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_whitening(self, L, is_inverse=False):
+        L = f64(L, fortran=True)
+        self.n = L.shape[0]
+        check(self._lib.flx_multi_set_whitening(self._h, ptr(L), self.n, self.n, int(bool(is_inverse))))
+
+    def set_null(self, X_null, y_mm, ll_null, df_null):
+        X = f64(X_null, fortran=True).reshape(self.n, -1, order="F"); y = f64(y_mm)
+        check(self._lib.flx_multi_set_null(self._h, ptr(X), X.shape[1], ptr(y), float(ll_null), int(df_null)))
+
+    def set_design(self, M0, M1, M2):
+        M0, M1, M2 = (f64(m, fortran=True) for m in (M0, M1, M2))
+        self.k = M0.shape[1]
+        check(self._lib.flx_multi_set_design(self._h, ptr(M0), ptr(M1), ptr(M2), self.k))
+
+    def set_perm(self, y_pred, U1, e_p, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        self.P = int(seeds.size)
+        y_pred = f64(y_pred); U1 = f64(U1, fortran=True); e_p = f64(np.ravel(e_p))
+        check(self._lib.flx_multi_set_perm(self._h, ptr(y_pred), ptr(U1), ptr(e_p), e_p.size, ptr(seeds), self.P))
+
+    def set_perm_implicit(self, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        self.P = int(seeds.size)
+        check(self._lib.flx_multi_set_perm_implicit(self._h, ptr(seeds), self.P))
+
+    def open_pgen(self, path, pgen_order=None, n=None):
+        po = None if pgen_order is None else np.ascontiguousarray(pgen_order, dtype=np.int32)
+        check(self._lib.flx_multi_open_pgen(self._h, str(path).encode(), ptr(po), int(self.n if n is None else n)))
+
+    def set_packed(self, packed, raw_sample_ct, pgen_order=None, n=None):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        po = None if pgen_order is None else np.ascontiguousarray(pgen_order, dtype=np.int32)
+        self._keep["packed"] = packed
+        check(self._lib.flx_multi_set_packed(self._h, ptr(packed), packed.shape[0], packed.shape[1], int(raw_sample_ct), ptr(po), int(self.n if n is None else n)))
+
+    def make_resident(self):
+        check(self._lib.flx_multi_make_resident(self._h))
+
+    def prepare(self):
+        check(self._lib.flx_multi_prepare(self._h))
+
+    def run(self, var_idx, per_snp=True):
+        var_idx = np.ascontiguousarray(var_idx, dtype=np.int32)
+        M = var_idx.size
+        res, out = {}, None
+        if per_snp:
+            res = dict(lrt_chisq=np.empty(M), pval=np.empty(M), lrt_df=np.empty(M, dtype=np.int32), rank=np.empty(M, dtype=np.int32),
+                       pivot=np.empty((M, self.k), dtype=np.int32), coef=np.empty((M, self.k)))
+            out = FlxSnpOut(*(res[f].ctypes.data for f in ("lrt_chisq", "pval", "lrt_df", "rank", "pivot", "coef")))
+        mp = np.empty(self.P) if self.P > 0 else None
+        nv = C.c_int64(0)
+        check(self._lib.flx_multi_run(self._h, ptr(var_idx), M, C.byref(out) if out is not None else None, ptr(mp), C.byref(nv)))
+        res["nvars_tested"] = nv.value
+        if mp is not None:
+            res["min_pval"] = mp
+        return res
+
+    def stats(self, device_index=0):
+        st = FlxStats()
+        check(self._lib.flx_multi_get_stats(self._h, int(device_index), C.byref(st)))
+        return st.as_dict()
 
 
 def _r_num(x):

@@ -108,6 +108,14 @@ void flx_destroy(flx_handle* h);
  * exactly what forwardsolve(L, X) reads (fit_model.nf:128).  is_inverse != 0: the matrix already is L^-1. */
 int  flx_set_whitening(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse);
 
+/* The same in pieces, for factors that should not exist twice (n = 100,000: 80 GB): _begin allocates the n x n device matrix
+ * (after releasing the previous factor's), _cols copies columns [j0, j0 + ncols) from `cols` (column-major, leading dimension ld;
+ * HOST or DEVICE memory), _end inverts in place and packs exactly like flx_set_whitening.  flx_set_whitening(L) is
+ * _begin(n); _cols(0, n, L, ld); _end(is_inverse). */
+int  flx_whitening_begin(flx_handle* h, int64_t n);
+int  flx_whitening_cols(flx_handle* h, int64_t j0, int64_t ncols, const double* cols, int64_t ld);
+int  flx_whitening_end(flx_handle* h, int is_inverse);
+
 /* DECORRELATE on the GPU (/root/reference/modules/local/r/decorrelate.nf:50-77) — the producer of the hot path's largest input:
  *   V = s2g*K + s2e*I (:54);  L = t(chol(V)) (:57);  if the Cholesky fails, eigen-decompose V, require every eigenvalue
  *   >= min_allowed_eig (:65), replace those <= 0 by eig_replacement, V <- U |lambda| U' and factor again (:58-69);
@@ -173,6 +181,12 @@ int  flx_make_resident(flx_handle* h);
  * With an attached communicator minp is min-allreduced and nvars_tested sum-allreduced over the ranks. */
 int  flx_run(flx_handle* h, const int32_t* var_idx, int64_t M, const flx_snp_out* out, double* minp, int64_t* nvars_tested);
 
+/* Derive the per-task operands (whitened constant columns, permutation prologue fit_model.nf:96-101 for every seed, digit
+ * planes) NOW instead of inside the first flx_run.  The LOCO driver (flexlmm_b200/loco.py; lmm.nf:27-46 gives every chromosome
+ * its own factor) calls it for chromosome k+1 on a second handle of the same device, from a host thread, while flx_run of
+ * chromosome k is in flight: handles share no mutable state. */
+int  flx_prepare(flx_handle* h);
+
 int  flx_get_stats(flx_handle* h, flx_stats* out);
 
 /* R-exact permutation indices (set.seed(seed); sample.int(m)), 1-based. Host-only, bit-exact. */
@@ -190,6 +204,36 @@ int  flx_whiten(flx_handle* h, const double* X, int64_t ncols, double* W);
  * flx_comm_unique_id fills 128 bytes on rank 0; broadcast them by any means, then attach on every rank. */
 int  flx_comm_unique_id(uint8_t id[128]);
 int  flx_comm_attach(flx_handle* h, const uint8_t id[128], int32_t rank, int32_t nranks);
+
+/* Replicate-once forms of the two n^2-sized inputs: collective over the attached communicator.  Only `root` reads L /
+ * U1 from the host (other ranks may pass NULL), uploads it and — for L — inverts it; L^-1 / U1 then reach the other GPUs with
+ * ncclBroadcast over NVLink: one host upload and one inversion per box instead of one per GPU.  Without a communicator they are
+ * flx_set_whitening / flx_set_perm.  A failure on any rank is reported on every rank before the broadcast starts. */
+int  flx_set_whitening_bcast(flx_handle* h, const double* L, int64_t n, int64_t ld, int is_inverse, int32_t root);
+int  flx_set_perm_bcast(flx_handle* h, const double* y_pred, const double* U1, const double* e_p, int64_t m, const int32_t* seeds, int32_t P, int32_t root);
+
+/* One caller thread, several GPUs of one box (R is single-threaded; "one process drives all 8 GPUs").  A flx_multi owns
+ * one handle per listed device and the NCCL communicator between them.  Each call below does what its single-GPU namesake does,
+ * on every device (one host thread per device inside the call); flx_multi_set_whitening / _set_perm upload once and broadcast;
+ * flx_multi_run splits var_idx into one contiguous SNP block per device (fit_model.nf:120 loop, lmm.nf:47-71 scatter), writes the
+ * per-SNP outputs into disjoint slices of the caller's arrays in var_idx order, and returns the min over all devices of the
+ * length-P min-p vector (ncclAllReduce(min) inside) and the summed count.  Results are bit-identical to one device's. */
+typedef struct flx_multi flx_multi;
+int  flx_multi_create(const flx_config* cfg /* device field ignored */, const int32_t* devices, int32_t ndev, flx_multi** out);
+void flx_multi_destroy(flx_multi* m);
+int  flx_multi_device_count(flx_multi* m);
+int  flx_multi_set_whitening(flx_multi* m, const double* L, int64_t n, int64_t ld, int is_inverse);
+int  flx_multi_set_null(flx_multi* m, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null);
+int  flx_multi_set_design(flx_multi* m, const double* M0, const double* M1, const double* M2, int32_t k);
+int  flx_multi_set_perm(flx_multi* m, const double* y_pred, const double* U1, const double* e_p, int64_t mm, const int32_t* seeds, int32_t P);
+int  flx_multi_set_perm_implicit(flx_multi* m, const int32_t* seeds, int32_t P);
+int  flx_multi_open_pgen(flx_multi* m, const char* path, const int32_t* pgen_order, int64_t n);
+int  flx_multi_set_packed(flx_multi* m, const uint8_t* packed, int64_t n_variants, int64_t bytes_per_variant, int64_t raw_sample_ct,
+                          const int32_t* pgen_order, int64_t n);
+int  flx_multi_make_resident(flx_multi* m);
+int  flx_multi_prepare(flx_multi* m);
+int  flx_multi_run(flx_multi* m, const int32_t* var_idx, int64_t M, const flx_snp_out* out, double* minp, int64_t* nvars_tested);
+int  flx_multi_get_stats(flx_multi* m, int32_t device_index, flx_stats* out);
 
 /* Downstream definition of the minP threshold (get_null_p_dist.nf:77-79; make_plots.nf:31):
  * quantile(min_pval, p_thr), R type 7. Host-only. */

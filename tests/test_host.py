@@ -141,6 +141,14 @@ def test_shard_bounds():
     assert shard_var_idx(np.arange(1, 11), 1, 3).tolist() == [5, 6, 7]
 
 
+def test_loco_chromosome_sharding():
+    from flexlmm_b200.loco import chromosomes_of_rank
+    for world in (1, 2, 4, 8):
+        parts = [chromosomes_of_rank(22, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(22))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
 def test_golden_synth_matches_oracle_now(orc):
     """The committed golden vectors are reproducible from the committed generator."""
     from flexlmm_b200 import synth
