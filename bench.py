@@ -292,7 +292,7 @@ def cpu_sample_snps(n, seconds):
 
 
 # ------------------------------------------------------------------------------------------------ rooflines
-def stage_roofline(w, acc, steps, int8_path, M):
+def stage_roofline(w, acc, steps, int8_path, M, handles=1):
     """Every stage against the roofline that bounds it: algorithmic bytes or ops per step / CUDA-event time."""
     n, P, s, c = w["n"], w["P"], w["s"], w["c"]
     n128 = (n + 127) // 128 * 128
@@ -308,7 +308,7 @@ def stage_roofline(w, acc, steps, int8_path, M):
 
     raw = (n + 3) // 4
     if int8_path:
-        passes = max(1, int(round(acc.get("int8_passes", steps) / steps)))
+        passes = max(1, int(round(acc.get("int8_passes", steps) / (steps * handles))))
         na = 2 if w["model"] == "domgxe" else 1
         put("K1q decode_i8", M * (raw + n256) * na, "GB/s", acc["ms_decode"], hbm, "hbm")
         put("K2q qf_i8 (g'C V^-1 C g, 6 planes x %d pass units)" % passes, 6.0 * n * n * M * passes, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
@@ -322,13 +322,13 @@ def stage_roofline(w, acc, steps, int8_path, M):
     return out
 
 
-def dominant_roofline(w, acc, steps, M):
+def dominant_roofline(w, acc, steps, M, handles=1):
     n = w["n"]
     int8_path = bool(acc.get("int8_path", 0))
     ms_whiten = acc["ms_whiten"]
     if int8_path:
         peak, peak_src = i8_peak()
-        passes = max(1, int(round(acc.get("int8_passes", steps) / steps)))
+        passes = max(1, int(round(acc.get("int8_passes", steps) / (steps * handles))))
         work = 6.0 * n * n * M * steps * passes
         kname = "qf_i8_kernel (K2q: g'C V^-1 C g, tcgen05.mma kind::i8, 6 exact base-256 digit planes, %d triangular-pass unit%s per batch)" % (passes, "" if passes == 1 else "s")
         tfile = "qf_traffic.json"
@@ -489,7 +489,7 @@ def run_workload(ctx, name, w, steps, warmup, route="auto", full=False, clocks=F
                 "gpu_launches": int(acc["launches"]), "int8_path": bool(acc.get("int8_path", 0)), "fallback_reason": int(acc.get("fallback_reason", 0) / max(1, steps * chroms)),
                 "refit_snps_per_step": acc.get("refit_snps", 0) / steps,
                 "stage_ms_per_step": {kk: acc[kk] / steps for kk in ("ms_decode", "ms_whiten", "ms_fit", "ms_perm", "ms_h2d", "ms_d2h")},
-                "roofline": dominant_roofline(w, acc, steps, Mtot), "stage_roofline": stage_roofline(w, acc, steps, bool(acc.get("int8_path", 0)), Mtot),
+                "roofline": dominant_roofline(w, acc, steps, Mtot, chroms), "stage_roofline": stage_roofline(w, acc, steps, bool(acc.get("int8_path", 0)), Mtot, chroms),
                 "min_pval_head": [float(x) for x in (mp[:3] if mp is not None else [])]})
     if chroms > 1:
         # the whole per-GPU LOCO job as the pipeline would run it once: factor setups (overlapped with the previous chromosome's

@@ -17,7 +17,7 @@ ERR_NAMES = {0: "FLX_OK", -1: "FLX_ERR_BAD_ARG", -2: "FLX_ERR_MISSING_GENOTYPE",
 
 EXPORTS = ["flx_last_error", "flx_version", "flx_device_count", "flx_create", "flx_destroy", "flx_set_whitening", "flx_whitening_begin",
            "flx_whitening_cols", "flx_whitening_end", "flx_decorrelate",
-           "flx_set_null", "flx_set_design", "flx_set_perm", "flx_set_perm_implicit", "flx_fit_null_model", "flx_open_pgen", "flx_pgen_info", "flx_set_packed", "flx_make_resident",
+           "flx_set_null", "flx_set_design", "flx_set_design_probes", "flx_set_use_dosage", "flx_set_perm", "flx_set_perm_implicit", "flx_fit_null_model", "flx_open_pgen", "flx_pgen_info", "flx_set_packed", "flx_make_resident",
            "flx_run", "flx_prepare", "flx_get_stats", "flx_perm_indices", "flx_decode_tile", "flx_whiten", "flx_comm_unique_id",
            "flx_comm_attach", "flx_minp_threshold", "flx_set_whitening_bcast", "flx_set_perm_bcast", "flx_multi_create", "flx_multi_destroy",
            "flx_multi_device_count", "flx_multi_set_whitening", "flx_multi_set_null", "flx_multi_set_design", "flx_multi_set_perm",
@@ -82,6 +82,8 @@ def load(build_if_missing=True):
     L.flx_decorrelate.argtypes = [vp, vp, i64, dbl, dbl, vp, vp, i32, dbl, dbl, vp, vp, vp, C.POINTER(i32)]
     L.flx_set_null.argtypes = [vp, vp, i32, vp, dbl, i32]
     L.flx_set_design.argtypes = [vp, vp, vp, vp, i32]
+    L.flx_set_design_probes.argtypes = [vp, vp, vp]
+    L.flx_set_use_dosage.argtypes = [vp, C.c_int]
     L.flx_set_perm.argtypes = [vp, vp, vp, vp, i64, vp, i32]
     L.flx_set_perm_implicit.argtypes = [vp, vp, i32]
     L.flx_fit_null_model.argtypes = [vp, i32, vp, i64, C.POINTER(dbl), C.POINTER(i32), vp, vp, vp, vp, C.POINTER(i64)]

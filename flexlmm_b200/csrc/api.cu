@@ -110,6 +110,14 @@ struct flx_handle {
     bool have_design = false;
     int k = 0;
     std::vector<double> M0, M1, M2;
+    // pgenlibr::Read (use_dosage): how every SNP column continues between the hard-call values, from two more probes of model.matrix
+    bool use_dosage = false, have_probes = false, dos_ok = false, run_dosage = false;
+    std::vector<double> M05, M15;
+    uint32_t dos_indicator = 0;
+    int dos_g[8]{};
+    std::string dos_why;
+    DevBuf<uint16_t> dos_d[2];
+    DevBuf<uint32_t> main_end_d[2];
     // permutations (raw inputs kept until finalisation)
     bool have_perm = false;
     bool perm_implicit = false;   // U1 is the implicit Householder complement of the null design
@@ -496,6 +504,22 @@ extern "C" int flx_set_design(flx_handle* h, const double* M0, const double* M1,
     const size_t sz = (size_t)h->n * k;
     h->M0.assign(M0, M0 + sz); h->M1.assign(M1, M1 + sz); h->M2.assign(M2, M2 + sz);
     h->k = k; h->have_design = true; h->dirty = true;
+    h->have_probes = false;      // probes belong to the design they were evaluated with
+    return FLX_OK;
+}
+
+extern "C" int flx_set_design_probes(flx_handle* h, const double* M05, const double* M15) {
+    if (!h || !M05 || !M15) { set_error("flx_set_design_probes: bad arguments"); return FLX_ERR_BAD_ARG; }
+    if (!h->have_design) { set_error("flx_set_design_probes: call flx_set_design first"); return FLX_ERR_STATE; }
+    const size_t sz = (size_t)h->n * h->k;
+    h->M05.assign(M05, M05 + sz); h->M15.assign(M15, M15 + sz);
+    h->have_probes = true; h->dirty = true;
+    return FLX_OK;
+}
+
+extern "C" int flx_set_use_dosage(flx_handle* h, int use_dosage) {
+    if (!h) { set_error("flx_set_use_dosage: NULL handle"); return FLX_ERR_BAD_ARG; }
+    h->use_dosage = use_dosage != 0;
     return FLX_OK;
 }
 
@@ -733,6 +757,38 @@ static int finalize_setup(flx_handle* h) {
     }
     FLX_TRY(h->lut.ensure(lut.size()));
     FLX_CUDA_TRY(cudaMemcpy(h->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // ---- dosages (pgenlibr::Read): a SNP column must be affine in x (x, x:cov: v(x) = v(0) + x (v(1) - v(0))) or the indicator of
+    // one hard-call value (I(x == 1): v(x) = v(g) if x == g else the common value elsewhere); the probes at x = 0.5, 1.5 tell which
+    h->dos_ok = false; h->dos_indicator = 0; h->dos_why.clear();
+    if (h->have_probes) {
+        bool all_ok = true;
+        for (int t = 0; t < h->s && all_ok; t++) {
+            const size_t o = (size_t)snp_cols[t] * n;
+            const double *v0 = h->M0.data() + o, *v1 = h->M1.data() + o, *v2 = h->M2.data() + o, *h05 = h->M05.data() + o, *h15 = h->M15.data() + o;
+            bool affine = true;
+            for (int64_t i = 0; i < n && affine; i++) {
+                const double sl = v1[i] - v0[i];
+                affine = (v2[i] == v0[i] + 2.0 * sl) && (h05[i] == v0[i] + 0.5 * sl) && (h15[i] == v0[i] + 1.5 * sl);
+            }
+            if (affine) continue;
+            int gfound = -1;
+            for (int g = 0; g < 3 && gfound < 0; g++) {
+                const double* vg[3] = {v0, v1, v2};
+                const double *va = vg[(g + 1) % 3], *vb = vg[(g + 2) % 3];
+                bool ind = true;
+                for (int64_t i = 0; i < n && ind; i++) ind = (va[i] == vb[i]) && (h05[i] == va[i]) && (h15[i] == va[i]);
+                if (ind) gfound = g;
+            }
+            if (gfound >= 0) { h->dos_indicator |= 1u << t; h->dos_g[t] = gfound; continue; }
+            all_ok = false;
+            char buf[200];
+            snprintf(buf, sizeof(buf), "design column %d is neither affine in x nor the indicator of one genotype value: it cannot be evaluated on dosages", snp_cols[t] + 1);
+            h->dos_why = buf;
+        }
+        h->dos_ok = all_ok;
+    } else {
+        h->dos_why = "use_dosage on a .pgen with dosage tracks needs flx_set_design_probes (model.matrix at x = 0.5 and 1.5)";
+    }
     lap("design split, lookup tables");
     // ---- whiten the constant columns of the real model, orthonormal basis Qc
     std::vector<double> Cw((size_t)n * std::max(h->ncf, 1));
@@ -1203,6 +1259,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                         const uint32_t v = (uint32_t)(var_idx[s0 + i] - 1);
                         const PgenFile::RecInfo ri = h->pgen->rec_info(v);
                         if (ri.vrtype & 0x08) { set_error("pgen variant %d: multiallelic record (the pipeline converts with --max-alleles 2)", var_idx[s0 + i]); return FLX_ERR_PGEN; }
+                    if (h->run_dosage && (ri.vrtype & 0x60) && (ri.vrtype & 0x90)) { set_error("pgen variant %d: phased record with a dosage track is not supported", var_idx[s0 + i]); return FLX_ERR_PGEN; }
                         ents[i] = Ent{ri.off, ri.len, ri.vrtype, 0, (int32_t)i};
                         if ((ri.vrtype & 6) != 2) row_of.emplace(v, (int32_t)i); else any_ld = true;
                     }
@@ -1259,8 +1316,15 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                     px.base_row = reinterpret_cast<const int32_t*>(bd + o_base); px.out_row = reinterpret_cast<const int32_t*>(bd + o_out); px.vrtype = bd + o_vt;
                     px.E = (int)E; px.sample_ct = (uint32_t)h->raw_n; px.bpv = bpv; px.out = h->packed_d[buf].p; px.scratch = h->px_scratch[buf].p;
                     px.err = h->px_err.p; px.any_ld = any_ld ? 1 : 0;
+                    if (h->run_dosage) {
+                        FLX_TRY(h->main_end_d[buf].ensure(E));
+                        FLX_TRY(h->dos_d[buf].ensure((size_t)snps_per_batch * h->raw_n));
+                        FLX_CUDA_TRY(cudaMemsetAsync(h->dos_d[buf].p, 0xFF, (size_t)nsnp * h->raw_n * sizeof(uint16_t), h->stream));
+                        px.main_end = h->main_end_d[buf].p; px.dos_out = h->dos_d[buf].p; px.dos_ld = h->raw_n;
+                    }
                     FLX_TRY(launch_pgen_expand(px, h->stream));
                     h->stats.launches += any_ld ? 2 : 1;
+                    if (h->run_dosage) { FLX_TRY(launch_pgen_dosage(px, h->stream)); h->stats.launches++; }
                     expanded_on_device = true;
                 } else { set_error("flx_run: no genotype source (flx_open_pgen / flx_set_packed)"); return FLX_ERR_STATE; }
                 src_ptr = st;
@@ -1281,6 +1345,10 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         da.lut = h->lut.p; memcpy(da.uni, h->uni, sizeof(da.uni)); da.uniform_mask = h->uniform_mask;
         da.n_pad = h->n_pad; da.X = h->X.p; da.NJ = NJ; da.missing_flag = h->missing.p;
         da.codes_out = codes_out ? codes_d.p : nullptr;
+        if (h->run_dosage && !use_resident && h->src == 1 && h->pgen->mode() == 0x10) {
+            da.dosage = h->dos_d[buf].p; da.dos_ld = h->raw_n; da.dos_indicator = h->dos_indicator;
+            memcpy(da.dos_g, h->dos_g, sizeof(da.dos_g));
+        }
         if (use_fast && !decode_only) {
             // K1q: one int8 tile set per integer triple of the design (x itself, I(x==1), ...)
             for (int al = 0; al < h->plan.NA; al++) {
@@ -1465,8 +1533,13 @@ extern "C" int flx_prepare(flx_handle* h) {
 
 // The rank-local part of flx_run: batches, FP64 refits, min-p finalisation, per-SNP results to the caller's arrays.
 static int run_local(flx_handle* h, const int32_t* var_idx, int64_t M, const flx_snp_out* out, bool do_perm) {
+    // pgenlibr::Read instead of ReadHardcalls (fit_model.nf:26): only a .pgen can carry dosages; real-valued x runs on the FP64 route
+    const bool dosage = h->use_dosage && h->src == 1 && h->pgen && h->pgen->mode() == 0x10 && h->pgen->has_dosage();
+    if (dosage && !h->dos_ok) { set_error("flx_run: %s", h->dos_why.c_str()); return h->have_probes ? FLX_ERR_BAD_ARG : FLX_ERR_STATE; }
+    h->run_dosage = dosage;
+    if (dosage) h->stats.fallback_reason = FLX_FALLBACK_DOSAGE;
     if (M > 0) {
-        const bool fast = h->fast;
+        const bool fast = h->fast && !dosage;
         h->stats.int8_path = fast ? 1 : 0;
         h->stats.int8_passes = 0;      // in units of one triangular pass (6 n^2 int8 ops per SNP); a full-matrix pass counts two
         if (fast) for (const auto& ps : h->plan.passes) h->stats.int8_passes += (ps.mat / h->plan.NG != ps.mat % h->plan.NG) ? 2 : 1;
@@ -1620,6 +1693,8 @@ extern "C" int flx_decode_tile(flx_handle* h, const int32_t* var_idx, int64_t M,
     if (h->src == 0) { set_error("flx_decode_tile: no genotype source"); return FLX_ERR_STATE; }
     if (h->dirty) FLX_TRY(finalize_setup(h));
     if (codes) memset(codes, 3, (size_t)M * h->n);
+    h->run_dosage = h->use_dosage && h->src == 1 && h->pgen && h->pgen->mode() == 0x10 && h->pgen->has_dosage();
+    if (h->run_dosage && !h->dos_ok) { set_error("flx_decode_tile: %s", h->dos_why.c_str()); return FLX_ERR_STATE; }
     return run_batches(h, var_idx, M, false, false, X, codes);
 }
 

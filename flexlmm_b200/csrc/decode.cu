@@ -56,7 +56,21 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_2bit_tile_kernel(const Dec
                 if (in_n && valid[h]) {
                     const uint8_t byte = __ldg(a.packed + rec[h] * a.bpv + (ro >> 2));
                     const int code = (byte >> (2 * (int)(ro & 3))) & 3;
-                    if (code == 3) {
+                    const uint32_t d16 = a.dosage ? (uint32_t)__ldg(a.dosage + rec[h] * a.dos_ld + ro) : 0xffffu;
+                    if (d16 != 0xffffu) {
+                        // pgenlibr::Read: x = dosage / 16384 (exact); the term as model.matrix evaluates it on a real x
+                        const double x = (double)d16 * 0.00006103515625;
+                        const int tt = term[h];
+                        const bool un = (a.uniform_mask >> tt) & 1u;
+                        const double* lt = a.lut + (int64_t)(tt * 3) * a.n_pad + k;
+                        if ((a.dos_indicator >> tt) & 1u) {
+                            const int g = a.dos_g[tt], o = (g == 0) ? 1 : 0;
+                            v = (x == (double)g) ? (un ? a.uni[tt][g] : __ldg(lt + (int64_t)g * a.n_pad)) : (un ? a.uni[tt][o] : __ldg(lt + (int64_t)o * a.n_pad));
+                        } else {
+                            const double v0 = un ? a.uni[tt][0] : __ldg(lt), v1 = un ? a.uni[tt][1] : __ldg(lt + a.n_pad);
+                            v = (v0 == 0.0) ? x * v1 : v0 + x * (v1 - v0);      // x, x:cov exactly as R forms them; general affine terms in one rounding more
+                        }
+                    } else if (code == 3) {
                         atomicMin(a.missing_flag, (int)(a.snp_offset + snp[h]));
                     } else if ((a.uniform_mask >> term[h]) & 1u) {
                         v = a.uni[term[h]][code];

@@ -82,8 +82,14 @@ struct PgenExpandArgs {
     int* err;                 // 0, or (entry << 4) | code of the first malformed record
     int any_ld;               // host hint: skip the second launch when no record is LD-compressed
     int pass, row_words;      // set by the launcher
+    // dosage track (pgenlibr::Read, vrtype bits 5-6), optional
+    uint32_t* main_end;       // out [E]: bytes of the record taken by the main genotype track (where the next track starts)
+    uint16_t* dos_out;        // out: row r >= 0 at dos_out + r * dos_ld, one uint16 per raw sample (0..32768 = dosage 0..2); rows
+    int64_t dos_ld;           //      must be pre-filled with 0xFFFF = "no dosage for this sample: use the hard call"
 };
 int launch_pgen_expand(const PgenExpandArgs& a, cudaStream_t st);
+// after launch_pgen_expand (needs main_end): the dosage tracks of the batch's own records -> dos_out
+int launch_pgen_dosage(const PgenExpandArgs& a, cudaStream_t st);
 
 // ---------------------------------------------------------------- K1 (decode.cu)
 struct DecodeArgs {
@@ -104,6 +110,11 @@ struct DecodeArgs {
     int NJ;                   // tiles in batch
     int* missing_flag;        // out: atomicMin(run-wide index of a SNP holding a missing call); INT_MAX = none
     uint8_t* codes_out;       // optional (tests): nsnp x n gathered codes
+    // pgenlibr::Read: x = dosage / 16384 where the record has one for the sample (row = the SNP's record row, like `packed`)
+    const uint16_t* dosage;   // nullptr: hard calls only
+    int64_t dos_ld;
+    uint32_t dos_indicator;   // bit t: term t is base + (peak - base) [x == g_t] (I(x == 1)); else affine in x: v(0) + x (v(1) - v(0))
+    int dos_g[8];             // g_t of the indicator terms
 };
 int launch_decode(const DecodeArgs& a, cudaStream_t st);
 int launch_decode_i8(const DecodeArgs& a, int8_t* X8, int NJ, int NKB, cudaStream_t st);

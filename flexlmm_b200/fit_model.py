@@ -120,6 +120,15 @@ class FitModel:
         self.s = int(sum(not (np.array_equal(M0[:, j], M1[:, j]) and np.array_equal(M0[:, j], M2[:, j])) for j in range(self.k)))
         check(self._lib.flx_set_design(self._h, ptr(M0), ptr(M1), ptr(M2), self.k))
 
+    def set_design_probes(self, M05, M15):
+        """model.matrix evaluated with x = 0.5 and x = 1.5: how the SNP columns continue between hard calls (needed by use_dosage)."""
+        M05, M15 = (f64(m, fortran=True) for m in (M05, M15))
+        check(self._lib.flx_set_design_probes(self._h, ptr(M05), ptr(M15)))
+
+    def set_use_dosage(self, use_dosage=True):
+        """fit_model.nf:26: pgenlibr::Read (dosages) instead of ReadHardcalls."""
+        check(self._lib.flx_set_use_dosage(self._h, int(bool(use_dosage))))
+
     def set_perm(self, y_pred, U1, e_p, seeds):
         """y.mm.pred, U1, e.p (fit_model.nf:64-66) and the seeds (workflows/flexlmm.nf:67)."""
         seeds = np.ascontiguousarray(seeds, dtype=np.int32)

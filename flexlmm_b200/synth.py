@@ -64,6 +64,20 @@ def design(model, n, seed=11):
     return M0, M1, M2, names, Xn, nn, cov1
 
 
+def design_at(model, x, cov1):
+    """model.matrix of the named BASELINE model for a REAL-valued genotype vector x (dosages, pgenlibr::Read): what
+    model.frame + model.matrix (fit_model.nf:124-127) evaluate per SNP.  design() is this at x = 0, 1, 2."""
+    x = np.asarray(x, dtype=np.float64)
+    one = np.ones(x.size)
+    if model == "additive":
+        return np.column_stack([one, x, cov1])
+    if model == "domgxe":
+        return np.column_stack([one, x, (x == 1).astype(float), cov1, x * cov1])
+    if model == "simple":
+        return np.column_stack([one, x])
+    raise ValueError(model)
+
+
 def solve_lower(L, B):
     """forwardsolve(L, B) with LAPACK (input generation only)."""
     try:

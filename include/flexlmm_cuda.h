@@ -136,6 +136,16 @@ int  flx_set_null(flx_handle* h, const double* X_null, int32_t c, const double* 
  * columns in model.matrix order.  Columns identical in all three are SNP-independent. */
 int  flx_set_design(flx_handle* h, const double* M0, const double* M1, const double* M2, int32_t k);
 
+/* use_dosage (fit_model.nf:12,26 — true is the reference's default, nextflow.config:59): read variants with pgenlibr::Read instead of
+ * ReadHardcalls, i.e. x = dosage_uint16 / 16384 for every sample the record's dosage track lists, the hard call elsewhere.  A file
+ * without dosage tracks gives the same x either way (and keeps the int8 route).  With dosages x is real-valued, so the three
+ * hard-call lookups no longer determine a SNP column: flx_set_design_probes hands over model.matrix evaluated with x = 0.5 and
+ * x = 1.5 on every row (n x k, same column order), from which every SNP column is recognised as affine in x (x, x:cov — evaluated as
+ * v(0) + x (v(1) - v(0))) or as the indicator of one hard-call value (I(x == 1)); anything else is refused when the run starts.
+ * Such a task runs on the FP64 route (flx_stats.fallback_reason = FLX_FALLBACK_DOSAGE). */
+int  flx_set_design_probes(flx_handle* h, const double* M05, const double* M15);
+int  flx_set_use_dosage(flx_handle* h, int use_dosage);
+
 /* Permutation inputs (fit_model.nf:64-66,96-101): y.mm.pred (n), U1 (n x m col-major), e.p (m) and the
  * permutation seeds (workflows/flexlmm.nf:67: 1..P).  Index order is R's set.seed(seed); sample(e.p). */
 int  flx_set_perm(flx_handle* h, const double* y_pred, const double* U1, const double* e_p, int64_t m,
@@ -162,8 +172,8 @@ int  flx_set_perm_implicit(flx_handle* h, const int32_t* seeds, int32_t P);
 int  flx_open_pgen(flx_handle* h, const char* path, const int32_t* pgen_order, int64_t n);
 
 /* pgenlibr::NewPgen metadata of the open file: raw variant / sample counts and whether any record carries a dosage
- * track (vrtype bits 5-6).  The engine reads hard calls (ReadHardcalls, fit_model.nf:26 with use_dosage = false); the R
- * wrapper must refuse use_dosage = true on a file with dosages rather than silently drop them. */
+ * track (vrtype bits 5-6).  The engine reads hard calls (ReadHardcalls, fit_model.nf:26 with use_dosage = false) unless
+ * flx_set_use_dosage(h, 1) was called. */
 int  flx_pgen_info(flx_handle* h, int64_t* variant_ct, int64_t* sample_ct, int32_t* has_dosage);
 
 /* Genotype source B: packed 2-bit hard-call records already in host memory (pgen mode-0x02 body:

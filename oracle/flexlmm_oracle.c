@@ -186,28 +186,50 @@ static int apply_difflist(const uint8_t** pp, const uint8_t* end, uint32_t sampl
     return 0;
 }
 
-static int decode_record(const uint8_t* f, const vrec* r, uint32_t sample_ct, uint8_t* codes) {
+/* main genotype track of a non-LD record; *track_end (optional) = first byte after it (where the next track starts) */
+static int decode_record(const uint8_t* f, const vrec* r, uint32_t sample_ct, uint8_t* codes, const uint8_t** track_end) {
     const uint8_t* p = f + r->off;
     const uint8_t* end = p + r->len;
     int t = r->vrtype & 7;
+    int rc = -9; /* LD types handled by caller */
     if (t == 0) {
         if (r->len < (sample_ct + 3) / 4) return -8;
         for (uint32_t i = 0; i < sample_ct; i++) codes[i] = (p[i >> 2] >> (2 * (i & 3))) & 3;
-        return 0;
-    }
-    if (t == 1) {
+        p += (sample_ct + 3) / 4;
+        rc = 0;
+    } else if (t == 1) {
         uint8_t c2 = *p++;
         uint8_t lo = c2 >> 2, delta = c2 & 3;
         if (p + (sample_ct + 7) / 8 > end) return -8;
         for (uint32_t i = 0; i < sample_ct; i++) codes[i] = lo + (((p[i >> 3] >> (i & 7)) & 1) ? delta : 0);
         p += (sample_ct + 7) / 8;
-        return apply_difflist(&p, end, sample_ct, codes);
-    }
-    if (t >= 4) {
+        rc = apply_difflist(&p, end, sample_ct, codes);
+    } else if (t >= 4) {
         memset(codes, t & 3, sample_ct);
-        return apply_difflist(&p, end, sample_ct, codes);
+        rc = apply_difflist(&p, end, sample_ct, codes);
     }
-    return -9; /* LD types handled by caller */
+    if (track_end) *track_end = p;
+    return rc;
+}
+
+static int read_hardcalls10(const uint8_t* f, int64_t len, uint32_t vct, uint32_t sct, uint32_t vidx, uint8_t* codes, vrec* rec_out, const uint8_t** track_end) {
+    vrec rec = {0, 0, 0}, base = {0, 0, 0};
+    int rc = locate10(f, len, vct, vidx, &rec, &base);
+    if (rc) return rc;
+    if (rec_out) *rec_out = rec;
+    if (rec.vrtype & 0x08) return -10; /* multiallelic track: pipeline guarantees biallelic (geno_to_pgen.nf:32-42) */
+    if ((rec.vrtype & 6) == 2) {
+        rc = decode_record(f, &base, sct, codes, NULL);
+        if (rc) return rc;
+        const uint8_t* p = f + rec.off;
+        rc = apply_difflist(&p, p + rec.len, sct, codes);
+        if (rc) return rc;
+        if ((rec.vrtype & 7) == 3)
+            for (uint32_t i = 0; i < sct; i++) if (codes[i] != 1 && codes[i] != 3) codes[i] = 2 - codes[i];
+        if (track_end) *track_end = p;
+        return 0;
+    }
+    return decode_record(f, &rec, sct, codes, track_end);
 }
 
 int orc_pgen_read_hardcalls(const uint8_t* f, int64_t len, uint32_t vidx, uint8_t* codes) {
@@ -222,21 +244,76 @@ int orc_pgen_read_hardcalls(const uint8_t* f, int64_t len, uint32_t vidx, uint8_
         for (uint32_t i = 0; i < sct; i++) codes[i] = (p[i >> 2] >> (2 * (i & 3))) & 3;
         return 0;
     }
-    vrec rec = {0, 0, 0}, base = {0, 0, 0};
-    rc = locate10(f, len, vct, vidx, &rec, &base);
+    return read_hardcalls10(f, len, vct, sct, vidx, codes, NULL, NULL);
+}
+
+/* pgenlibr::Read (fit_model.nf:26 with use_dosage = true, :123): the hard calls of ReadHardcalls, overlaid with dosage / 16384
+ * for every sample that has an entry in the record's dosage track (vrtype bits 5-6: 01 = sample-id delta list, 11 = bitarray over
+ * all samples, 10 = a value for every sample with 65535 = none; values uint16, 0..32768 = ALT dosage 0..2; pgenlib PgrGetD +
+ * Dosage16ToDoubles).  buf[i] = NA for a missing hard call without a dosage.  Phased records (bit 4) and phased dosages (bit 7)
+ * are not produced by the pipeline's conversion (geno_to_pgen.nf:30-42) and are refused. */
+int orc_pgen_read_dosage(const uint8_t* f, int64_t len, uint32_t vidx, double* buf) {
+    uint32_t vct, sct; int mode;
+    int rc = orc_pgen_info(f, len, &vct, &sct, &mode);
     if (rc) return rc;
-    if (rec.vrtype & 0x08) return -10; /* multiallelic track: pipeline guarantees biallelic (geno_to_pgen.nf:32-42) */
-    if ((rec.vrtype & 6) == 2) {
-        rc = decode_record(f, &base, sct, codes);
-        if (rc) return rc;
-        const uint8_t* p = f + rec.off;
-        rc = apply_difflist(&p, p + rec.len, sct, codes);
-        if (rc) return rc;
-        if ((rec.vrtype & 7) == 3)
-            for (uint32_t i = 0; i < sct; i++) if (codes[i] != 1 && codes[i] != 3) codes[i] = 2 - codes[i];
+    if (vidx >= vct) return -2;
+    uint8_t* codes = (uint8_t*)malloc(sct ? sct : 1);
+    if (mode == 0x02) {
+        rc = orc_pgen_read_hardcalls(f, len, vidx, codes);
+        if (!rc) orc_codes_to_buf(codes, sct, buf);
+        free(codes);
+        return rc;
+    }
+    vrec rec = {0, 0, 0};
+    const uint8_t* p = NULL;
+    rc = read_hardcalls10(f, len, vct, sct, vidx, codes, &rec, &p);
+    if (rc) { free(codes); return rc; }
+    orc_codes_to_buf(codes, sct, buf);
+    free(codes);
+    int dmode = (rec.vrtype >> 5) & 3;
+    if (dmode == 0) return 0;
+    if (rec.vrtype & 0x90) return -11;
+    const uint8_t* end = f + rec.off + rec.len;
+    const double scale = 0.00006103515625;   /* 1 / 16384 */
+    if (dmode == 2) {
+        if (p + 2ull * sct > end) return -12;
+        for (uint32_t i = 0; i < sct; i++) { uint32_t d = p[2 * i] | ((uint32_t)p[2 * i + 1] << 8); if (d != 65535u) buf[i] = d * scale; }
         return 0;
     }
-    return decode_record(f, &rec, sct, codes);
+    if (dmode == 3) {
+        const uint8_t* bits = p;
+        const uint8_t* vals = p + (sct + 7) / 8;
+        if (vals > end) return -12;
+        for (uint32_t i = 0; i < sct; i++)
+            if ((bits[i >> 3] >> (i & 7)) & 1) {
+                if (vals + 2 > end) return -12;
+                buf[i] = (vals[0] | ((uint32_t)vals[1] << 8)) * scale;
+                vals += 2;
+            }
+        return 0;
+    }
+    /* dmode == 1: delta list of sample ids (a difflist without genotypes), then one uint16 per entry */
+    uint32_t dl;
+    if (rd_varint(&p, end, &dl)) return -12;
+    if (dl == 0) return 0;
+    if (dl > sct) return -12;
+    uint32_t group_ct = (dl + 63) / 64;
+    int idb = (sct < 256u) ? 1 : (sct < 65536u) ? 2 : (sct < 16777216u) ? 3 : 4;
+    const uint8_t* group_first = p;
+    p += (uint64_t)group_ct * idb + (group_ct - 1);
+    if (p > end) return -12;
+    uint32_t* ids = (uint32_t*)malloc(sizeof(uint32_t) * dl);
+    uint32_t sid = 0;
+    for (uint32_t e = 0; e < dl; e++) {
+        if ((e & 63) == 0) sid = (uint32_t)rd_le(group_first + (uint64_t)(e >> 6) * idb, idb);
+        else { uint32_t d; if (rd_varint(&p, end, &d)) { free(ids); return -12; } sid += d; }
+        if (sid >= sct) { free(ids); return -12; }
+        ids[e] = sid;
+    }
+    if (p + 2ull * dl > end) { free(ids); return -12; }
+    for (uint32_t e = 0; e < dl; e++) buf[ids[e]] = (p[2 * e] | ((uint32_t)p[2 * e + 1] << 8)) * scale;
+    free(ids);
+    return 0;
 }
 
 void orc_codes_to_buf(const uint8_t* codes, int64_t n, double* buf) {

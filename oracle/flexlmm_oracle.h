@@ -35,6 +35,9 @@ void   orc_sample_perm(int32_t seed, int64_t m, int32_t* out);
  * Returns 0 on success, negative on error. */
 int orc_pgen_info(const uint8_t* file, int64_t len, uint32_t* variant_ct, uint32_t* sample_ct, int* mode);
 int orc_pgen_read_hardcalls(const uint8_t* file, int64_t len, uint32_t vidx0, uint8_t* codes);
+/* pgenlibr::Read (use_dosage = true, the reference's default: nextflow.config:59): hard calls overlaid with dosage_uint16 / 16384
+ * where the record's dosage track (vrtype bits 5-6) has an entry; NA (NaN) for a missing call without dosage. */
+int orc_pgen_read_dosage(const uint8_t* file, int64_t len, uint32_t vidx0, double* buf);
 /* pgenlibr buffer semantics: 0,1,2 -> 0.0,1.0,2.0 ; 3 -> NA (R NA_real_, a NaN payload 1954). */
 void orc_codes_to_buf(const uint8_t* codes, int64_t n, double* buf);
 

@@ -32,6 +32,7 @@ def lib():
         L.orc_sample_perm.argtypes = [C.c_int32, C.c_int64, C.c_void_p]
         L.orc_pgen_info.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
         L.orc_pgen_read_hardcalls.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p]
+        L.orc_pgen_read_dosage.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p]
         L.orc_forwardsolve.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
         L.orc_lm_fit.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_double] + [C.c_void_p] * 5
         L.orc_lm_fit.restype = C.c_int
@@ -92,6 +93,49 @@ def pgen_read_hardcalls(buf, vidx0):
     if rc:
         raise ValueError(f"pgen decode failed ({rc})")
     return codes
+
+
+def pgen_read(buf, vidx0):
+    """pgenlibr::Read (fit_model.nf:26,123 with use_dosage = true): doubles, dosage / 16384 where the record carries one,
+    else the hard call; NaN for a missing call without a dosage."""
+    b = np.frombuffer(buf, dtype=np.uint8)
+    _, s, _ = pgen_info(buf)
+    out = np.empty(s, dtype=np.float64)
+    rc = lib().orc_pgen_read_dosage(b.ctypes.data, b.size, int(vidx0), out.ctypes.data)
+    if rc:
+        raise ValueError(f"pgen dosage read failed ({rc})")
+    return out
+
+
+def fit_model_x(L, y_mm, X_null, ll_null, df_null, design_of_x, xs, perm_seed=0, y_pred=None, U1=None, e_p=None):
+    """FIT_MODEL for REAL-valued genotypes (dosages): the literal loop fit_model.nf:120-143 with the design of each SNP evaluated by
+    `design_of_x(x) -> n x k matrix` (model.frame + model.matrix on the dosage vector, :124-127), built from the C primitives.
+    xs: (M, n) doubles in model order.  Small cases only (Python loop)."""
+    y = np.ascontiguousarray(y_mm, dtype=np.float64).copy()
+    n = y.size
+    if perm_seed:
+        idx = r_sample(perm_seed, len(np.ravel(e_p)))
+        y = np.asarray(y_pred, dtype=np.float64) + np.asarray(U1) @ np.ravel(e_p)[idx - 1]
+        f0 = lm_fit(X_null, y)
+        ll_null, df_null = loglik_lm(f0["residuals"]), f0["rank"] + 1
+    out = dict(chisq=[], df=[], pval=[], rank=[], pivot=[], coef=[])
+    min_pval = 2.0
+    for x in xs:
+        if np.isnan(x).any():
+            raise ValueError("missing genotype in a tested variant (the reference aborts: SURVEY §8 a4)")
+        X = np.asarray(design_of_x(x), dtype=np.float64)
+        fit = lm_fit(forwardsolve(L, X), y)
+        ll = loglik_lm(fit["residuals"])
+        df = fit["rank"] + 1 - df_null
+        chisq = 2.0 * (ll - ll_null)
+        p = pchisq_upper(chisq, df) if df > 0 else np.nan
+        if not np.isnan(p):
+            min_pval = min(min_pval, p)
+        for k2, v in (("chisq", chisq), ("df", df), ("pval", p), ("rank", fit["rank"]), ("pivot", fit["pivot"]), ("coef", fit["coefficients"])):
+            out[k2].append(v)
+    res = {k2: np.array(v) for k2, v in out.items()}
+    res["min_pval"], res["nvars"] = min_pval, len(xs)
+    return res
 
 
 # ------------------------------------------------------------------ small numerics

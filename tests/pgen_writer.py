@@ -67,8 +67,46 @@ def encode_variant(codes, vrtype, base=None):
     raise ValueError(vrtype)
 
 
-def write_pgen(codes, vrtypes=None, mode=0x10):
-    """codes: (M, N) uint8.  Returns the file bytes."""
+def _deltalist(sample_ct, ids):
+    """A difflist without genotypes (the sample ids of a dosage list, vrtype bits 5-6 = 01)."""
+    ids = list(map(int, ids)); dl = len(ids)
+    out = bytearray(_varint(dl))
+    if dl == 0:
+        return bytes(out)
+    idb = 1 if sample_ct < 256 else 2 if sample_ct < 65536 else 3 if sample_ct < 16777216 else 4
+    ngroups = (dl + 63) // 64
+    deltas = []
+    for g in range(ngroups):
+        out += int(ids[g * 64]).to_bytes(idb, "little")
+        d = bytearray()
+        for e in range(g * 64 + 1, min(dl, g * 64 + 64)):
+            d += _varint(ids[e] - ids[e - 1])
+        deltas.append(bytes(d))
+    for g in range(ngroups - 1):
+        out.append((len(deltas[g]) - 63) & 255)
+    for d in deltas:
+        out += d
+    return bytes(out)
+
+
+def encode_dosage(dos, dmode):
+    """dos: (N,) uint16 with 65535 = no dosage for that sample.  dmode 1 = list, 2 = unconditional, 3 = bitarray (vrtype bits 5-6)."""
+    dos = np.asarray(dos, dtype=np.uint16); n = dos.size
+    have = np.where(dos != 65535)[0]
+    if dmode == 2:
+        return dos.astype("<u2").tobytes()
+    vals = dos[have].astype("<u2").tobytes()
+    if dmode == 1:
+        return _deltalist(n, have) + vals
+    if dmode == 3:
+        bits = np.zeros((n + 7) // 8 * 8, dtype=np.uint8); bits[have] = 1
+        return np.packbits(bits, bitorder="little").tobytes() + vals
+    raise ValueError(dmode)
+
+
+def write_pgen(codes, vrtypes=None, mode=0x10, dosages=None, dosage_modes=None):
+    """codes: (M, N) uint8.  dosages: optional (M, N) uint16 (0..32768 = ALT dosage 0..2, 65535 = none for that sample) with
+    dosage_modes[v] in {0 (no track), 1, 2, 3}: the records then carry a dosage track and 8-bit vrtypes.  Returns the file bytes."""
     codes = np.asarray(codes, dtype=np.uint8); M, N = codes.shape
     hdr = bytes([0x6c, 0x1b, mode]) + int(M).to_bytes(4, "little") + int(N).to_bytes(4, "little")
     if mode == 0x02:
@@ -79,19 +117,27 @@ def write_pgen(codes, vrtypes=None, mode=0x10):
         t = vrtypes[v]
         if t in (2, 3) and base is None:
             t = 0
-        recs.append((t, encode_variant(codes[v], t, base)))
+        rec = encode_variant(codes[v], t, base)
         if t not in (2, 3):
             base = codes[v].copy()
+        if dosages is not None and dosage_modes is not None and dosage_modes[v]:
+            rec = rec + encode_dosage(dosages[v], dosage_modes[v])
+            t |= int(dosage_modes[v]) << 5
+        recs.append((t, rec))
     maxlen = max(len(r) for _, r in recs)
     len_bytes = 1 if maxlen < 256 else 2 if maxlen < 65536 else 3
-    ctrl = (len_bytes - 1) | 0x40
+    wide = any(t > 15 for t, _ in recs)                  # dosage bits need 8-bit vrtypes: record-length encoding 4..7
+    ctrl = (len_bytes - 1) | (4 if wide else 0) | 0x40
     nblk = (M + 65535) // 65536
     body = bytearray(); blocks = []
     for b in range(nblk):
         sub = recs[b * 65536:(b + 1) * 65536]
-        tb = bytearray((len(sub) + 1) // 2)
-        for i, (t, _) in enumerate(sub):
-            tb[i >> 1] |= t << (4 * (i & 1))
+        if wide:
+            tb = bytearray(t for t, _ in sub)
+        else:
+            tb = bytearray((len(sub) + 1) // 2)
+            for i, (t, _) in enumerate(sub):
+                tb[i >> 1] |= t << (4 * (i & 1))
         lb = b"".join(len(r).to_bytes(len_bytes, "little") for _, r in sub)
         blocks.append(bytes(tb) + lb)
     header_len = 12 + 8 * nblk + sum(len(x) for x in blocks)

@@ -56,6 +56,47 @@ def test_pgen_all_vrtypes_roundtrip(orc, N):
             assert np.array_equal(orc.pgen_read_hardcalls(b, v), c[v]), (mode, v)
 
 
+@pytest.mark.parametrize("N", [5, 64, 255, 256, 300, 1000])
+def test_pgen_read_dosage_tracks(orc, N):
+    """pgenlibr::Read semantics (fit_model.nf:26,123 with use_dosage = true): dosage / 16384 where the record's dosage track (list /
+    unconditional / bitarray, vrtype bits 5-6) has an entry for the sample, the hard call elsewhere, NA for a missing call without one."""
+    import pgen_writer as pw
+    rng = np.random.default_rng(N)
+    M = 24
+    codes = rng.integers(0, 4, size=(M, N)).astype(np.uint8)
+    dos = np.full((M, N), 65535, dtype=np.uint16)
+    m = rng.random((M, N)) < 0.3
+    dos[m] = rng.integers(0, 32769, size=int(m.sum()))
+    vr = [0, 1, 2, 3, 4, 6, 7, 0] * 3
+    dm = [v % 4 for v in range(M)]
+    f = pw.write_pgen(codes, vr, dosages=dos, dosage_modes=dm)
+    for v in range(M):
+        want = np.where(codes[v] == 3, np.nan, codes[v].astype(float))
+        if dm[v]:
+            want = np.where(dos[v] != 65535, dos[v] / 16384.0, want)
+        assert np.array_equal(orc.pgen_read(f, v), want, equal_nan=True)
+        assert np.array_equal(orc.pgen_read_hardcalls(f, v), codes[v])
+
+
+def test_fit_model_x_equals_fit_model_on_hard_calls(orc):
+    """The dosage loop (Python over the C primitives) reproduces orc_fit_model when the dosages are hard calls."""
+    from flexlmm_b200 import synth
+    t = synth.task(70, 12, model="domgxe", P=1, seed=4)
+    cov1 = synth.design("domgxe", 70, seed=15)[6]
+    args = (t["L"], t["y_mm"], t["X_null"], t["ll_null"], t["df_null"])
+    des = lambda x: synth.design_at("domgxe", x, cov1)      # noqa: E731
+    a = orc.fit_model(*args, t["M0"], t["M1"], t["M2"], t["codes_raw"])
+    b = orc.fit_model_x(*args, des, t["codes_raw"].astype(float))
+    for k2 in ("chisq", "df", "rank", "pivot", "coef"):
+        assert np.array_equal(a[k2], b[k2]), k2
+    # PERM task: U1 %*% sample(e.p) is summed in dgemv's column order in C and in numpy's order here
+    pk = dict(perm_seed=1, y_pred=t["y_pred"], U1=t["U1"], e_p=t["e_p"])
+    a = orc.fit_model(*args, t["M0"], t["M1"], t["M2"], t["codes_raw"], **pk)
+    b = orc.fit_model_x(*args, des, t["codes_raw"].astype(float), **pk)
+    np.testing.assert_allclose(a["chisq"], b["chisq"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(a["min_pval"], b["min_pval"], rtol=1e-9)
+
+
 def test_codes_to_na(orc):
     import ctypes
     codes = np.array([0, 1, 2, 3], dtype=np.uint8); buf = np.zeros(4)
