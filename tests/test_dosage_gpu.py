@@ -125,7 +125,7 @@ def test_missing_call_without_dosage_is_fatal_with_dosage_is_not(fx, orc, tmp_pa
 def test_use_dosage_needs_probes_and_refuses_what_it_cannot_evaluate(fx, tmp_path):
     from flexlmm_b200 import synth
     t = task(90, 12, "additive", 0, 10)
-    path, *_ = dosage_file(tmp_path, t, np.random.default_rng(1))
+    path, *_ = dosage_file(tmp_path, t, np.random.default_rng(1), missing_under_dosage=False)
     with setup(fx, t, path, probes=False) as fm:
         with pytest.raises(fx.FlxError) as e:
             fm.run(np.arange(1, 13, dtype=np.int32))
