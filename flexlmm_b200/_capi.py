@@ -20,7 +20,7 @@ EXPORTS = ["flx_last_error", "flx_version", "flx_device_count", "flx_create", "f
            "flx_set_null", "flx_set_design", "flx_set_design_probes", "flx_set_use_dosage", "flx_set_perm", "flx_set_perm_implicit", "flx_fit_null_model", "flx_open_pgen", "flx_pgen_info", "flx_set_packed", "flx_make_resident",
            "flx_run", "flx_prepare", "flx_get_stats", "flx_perm_indices", "flx_decode_tile", "flx_whiten", "flx_comm_unique_id",
            "flx_comm_attach", "flx_minp_threshold", "flx_set_whitening_bcast", "flx_set_perm_bcast", "flx_multi_create", "flx_multi_destroy",
-           "flx_multi_device_count", "flx_multi_set_whitening", "flx_multi_set_null", "flx_multi_set_design", "flx_multi_set_perm",
+           "flx_multi_device_count", "flx_multi_set_whitening", "flx_multi_set_null", "flx_multi_set_design", "flx_multi_set_design_probes", "flx_multi_set_use_dosage", "flx_multi_set_perm",
            "flx_multi_set_perm_implicit", "flx_multi_open_pgen", "flx_multi_set_packed", "flx_multi_make_resident", "flx_multi_prepare",
            "flx_multi_run", "flx_multi_get_stats"]
 
@@ -108,6 +108,8 @@ def load(build_if_missing=True):
     L.flx_multi_set_whitening.argtypes = [vp, vp, i64, i64, C.c_int]
     L.flx_multi_set_null.argtypes = [vp, vp, i32, vp, dbl, i32]
     L.flx_multi_set_design.argtypes = [vp, vp, vp, vp, i32]
+    L.flx_multi_set_design_probes.argtypes = [vp, vp, vp]
+    L.flx_multi_set_use_dosage.argtypes = [vp, C.c_int]
     L.flx_multi_set_perm.argtypes = [vp, vp, vp, vp, i64, vp, i32]
     L.flx_multi_set_perm_implicit.argtypes = [vp, vp, i32]
     L.flx_multi_open_pgen.argtypes = [vp, C.c_char_p, vp, i64]

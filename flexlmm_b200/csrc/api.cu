@@ -956,8 +956,9 @@ static int finalize_setup(flx_handle* h) {
     auto slice_G = [&](const double* G2, int64_t ld2, int P) -> int {
         const flx_handle::FastPlan& pl = h->plan;
         const int NC = cr + 1 + P;
-        h->ntilesG = (NC + 79) / 80;
-        h->NB_G = (((NC + h->ntilesG - 1) / h->ntilesG + 15) / 16) * 16;
+        const int nb_max = xg_block_cols(h->Q), gran = (h->Q % 2 == 0) ? 8 : 16;
+        h->ntilesG = (NC + nb_max - 1) / nb_max;
+        h->NB_G = (((NC + h->ntilesG - 1) / h->ntilesG + gran - 1) / gran) * gran;
         for (int gq = 0; gq < pl.NG; gq++) {
             FLX_TRY(h->G_scale[gq].ensure((size_t)h->ntilesG * h->NB_G));
             FLX_TRY(h->G8[gq].ensure((size_t)h->ntilesG * h->NKB * h->Q * h->NB_G * 64));
@@ -1056,7 +1057,7 @@ static int finalize_setup(flx_handle* h) {
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t planes_b = (size_t)pl.NG * pl.NG * 2 * h->T256 * (h->T256 + 1) * h->Q * 16384;   // a full set = two triangular ones
         const size_t batch_b = (size_t)h->num_sms * h->NKB * 8192 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);   // one tile per SM at least
-        if (planes_b + batch_b + (size_t)256 * n * 8 > free_b) {
+        if (planes_b + batch_b + (size_t)1024 * n * 8 > free_b) {
             h->fast = false;
             h->fallback_reason = FLX_FALLBACK_PLANES_DONT_FIT;
         }
@@ -1064,25 +1065,29 @@ static int finalize_setup(flx_handle* h) {
     if (h->fast) {
         const flx_handle::FastPlan& pl = h->plan;
         const double one = 1.0, zero = 0.0;
+        // row tiles are produced four at a time (1024 rows per library GEMM: the 256-row products ran at ~60 % of the DGEMM rate)
+        constexpr int64_t RT = 1024;
         DevBuf<double> Vt;
-        FLX_TRY(Vt.ensure((size_t)256 * n));
+        FLX_TRY(Vt.ensure((size_t)RT * n));
         const size_t tri_b = (size_t)2 * h->T256 * (h->T256 + 1) * h->Q * 16384, full_b = (size_t)h->T256 * h->NKB * h->Q * 16384;
         for (int a = 0; a < pl.NG; a++)
             for (int b = a; b < pl.NG; b++) {
                 FLX_TRY(h->rowscale[a * pl.NG + b].ensure((size_t)h->T256 * 256));
                 FLX_TRY(h->T8[a * pl.NG + b].ensure(a == b ? tri_b : full_b));
             }
-        for (int I = 0; I < h->T256; I++) {
-            const int64_t r0 = (int64_t)I * 256;
-            const int64_t m = std::min<int64_t>(256, n - r0), ncols = (pl.NG > 1) ? n : r0 + m, K = n - r0;
-            FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, m, ncols, K, &one, h->Zdense.p + r0 + r0 * n, n, h->Zdense.p + r0, n, &zero, Vt.p, 256));
-            for (int a = 0; a < pl.NG; a++)
-                for (int b = a; b < pl.NG; b++) {
-                    const int mi = a * pl.NG + b;
-                    const double* ca = pl.ones[a] ? nullptr : h->cvec_d.p + (size_t)a * n_pad;
-                    const double* cb = pl.ones[b] ? nullptr : h->cvec_d.p + (size_t)b * n_pad;
-                    FLX_TRY(launch_qf_slice(Vt.p, n, 256, I, h->T256, h->Q, ca, cb, a == b ? 0 : 1, h->rowscale[mi].p, h->T8[mi].p, h->stream));
-                }
+        for (int64_t r0 = 0; r0 < n; r0 += RT) {
+            const int64_t m = std::min<int64_t>(RT, n - r0), ncols = (pl.NG > 1) ? n : r0 + m, K = n - r0;
+            FLX_CUBLAS_TRY(cublasDgemm_64(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, m, ncols, K, &one, h->Zdense.p + r0 + r0 * n, n, h->Zdense.p + r0, n, &zero, Vt.p, RT));
+            for (int64_t sub = 0; sub < m; sub += 256) {
+                const int I = (int)((r0 + sub) / 256);
+                for (int a = 0; a < pl.NG; a++)
+                    for (int b = a; b < pl.NG; b++) {
+                        const int mi = a * pl.NG + b;
+                        const double* ca = pl.ones[a] ? nullptr : h->cvec_d.p + (size_t)a * n_pad;
+                        const double* cb = pl.ones[b] ? nullptr : h->cvec_d.p + (size_t)b * n_pad;
+                        FLX_TRY(launch_qf_slice(Vt.p + sub, n, RT, I, h->T256, h->Q, ca, cb, a == b ? 0 : 1, h->rowscale[mi].p, h->T8[mi].p, h->stream));
+                    }
+            }
         }
         FLX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
@@ -1428,7 +1433,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 XgArgs xa{};
                 xa.X8 = h->X8.p + h->plan.alp[t] * x8_stride; xa.G8 = h->G8[h->plan.grp[t]].p; xa.colscale = h->G_scale[h->plan.grp[t]].p;
                 for (int i = 0; i < 3; i++) xa.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
-                xa.n_items = (int64_t)h->ntilesG * NJ; xa.NCT = h->ntilesG; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_G; xa.NC = cr + 1 + (do_perm ? h->P : 0);
+                xa.n_items = (int64_t)h->ntilesG * ((NJ + 1) / 2); xa.NCT = h->ntilesG; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_G; xa.NC = cr + 1 + (do_perm ? h->P : 0);
                 xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = nkb_live;
                 xa.out = h->ub.p + (int64_t)t * nsnp * ldg; xa.ld_out = ldg;
                 FLX_TRY(launch_xg(xa, h->num_sms, h->stream));
@@ -1793,6 +1798,15 @@ extern "C" int flx_multi_set_null(flx_multi* m, const double* X_null, int32_t c,
 extern "C" int flx_multi_set_design(flx_multi* m, const double* M0, const double* M1, const double* M2, int32_t k) {
     if (!m) { set_error("flx_multi_set_design: NULL handle"); return FLX_ERR_BAD_ARG; }
     return multi_each(m, [&](flx_handle* h, int) { return flx_set_design(h, M0, M1, M2, k); });
+}
+extern "C" int flx_multi_set_design_probes(flx_multi* m, const double* M05, const double* M15) {
+    if (!m) { set_error("flx_multi_set_design_probes: NULL handle"); return FLX_ERR_BAD_ARG; }
+    return multi_each(m, [&](flx_handle* h, int) { return flx_set_design_probes(h, M05, M15); });
+}
+extern "C" int flx_multi_set_use_dosage(flx_multi* m, int use_dosage) {
+    if (!m) { set_error("flx_multi_set_use_dosage: NULL handle"); return FLX_ERR_BAD_ARG; }
+    for (auto h : m->hs) FLX_TRY(flx_set_use_dosage(h, use_dosage));
+    return FLX_OK;
 }
 extern "C" int flx_multi_set_perm(flx_multi* m, const double* y_pred, const double* U1, const double* e_p, int64_t mm, const int32_t* seeds, int32_t P) {
     if (!m) { set_error("flx_multi_set_perm: NULL handle"); return FLX_ERR_BAD_ARG; }

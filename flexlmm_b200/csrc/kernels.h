@@ -53,13 +53,14 @@ struct XgArgs {
     const int8_t* G8;         // [col block][NKB][Q][NB*64 B]
     const double* colscale;   // [ntiles*NB] power-of-two column scales
     double pair_scale[3];     // 2^-16, 2^-32, 2^-48
-    int64_t n_items;          // ntiles * NJ
+    int64_t n_items;          // column blocks * ceil(NJ / 2): a work item is a pair of SNP tiles against one column block
     int64_t nsnp;
     int NJ, NB, NC, Q, NKB, NKB_live;
-    int NCT;                  // column blocks (n_items = NJ * NCT)
-    double* out; int64_t ld_out;   // out[snp * ld_out + col]
+    int NCT;                  // column blocks
+    double* out; int64_t ld_out;   // out[snp * ld_out + col], ld_out = NCT * NB (a multiple of 8)
 };
 int launch_xg(const XgArgs& g, int num_sms, cudaStream_t st);
+int xg_block_cols(int Q);     // widest column block: Q * NB <= 256 TMEM columns per SNP tile
 // columns 0..c1-1 come from G (ld), columns c1..NC-1 from G2 (ld2) — [Qc | r] and R_f live in different buffers.
 // rowmul (optional, [n]): the planes are those of diag(rowmul) [G | G2]
 int launch_xg_slice(const double* G, int64_t ld, int c1, const double* G2, int64_t ld2, int64_t n, int NC, int NB, int ntiles, int Q, int NKB, const double* rowmul,

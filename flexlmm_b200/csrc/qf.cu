@@ -36,7 +36,6 @@ constexpr int QF_STAGE_BYTES = 2 * QF_A_BYTES + QF_B_BYTES;   // two SNP tiles s
 constexpr int QF_STAGES = 7;
 constexpr int QF_SMEM = QF_STAGES * QF_STAGE_BYTES + 256;
 constexpr int QF_THREADS = 384;                // warpgroup 0: warp 0 TMA, warp 1 MMA (56 registers); warps 4-11 epilogue (224): 128*56 + 256*224 = 384*168, the CTA's pool
-constexpr int XG_THREADS = 192;
 
 __device__ __forceinline__ uint32_t qsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void qbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qsmem_u32(bar)), "r"(count)); }
@@ -274,24 +273,16 @@ int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1q: packed 2-bit hard calls -> int8 tile in the UMMA canonical K-major layout (A operand of K2q)
+// K1q: packed 2-bit hard calls -> int8 tile in the UMMA canonical K-major layout (A operand of K2q / K4q)
 //   X8[J][kb][k16 chunk 4][SNP group 16][8 SNPs][16 samples]
 // ------------------------------------------------------------------------------------------------
 constexpr int DEC8_KBS = 8;   // k-blocks per CTA: 512 samples = 128 packed bytes per record, one cache line
 __global__ void __launch_bounds__(512) decode_i8_tile_kernel(const DecodeArgs a, int8_t* __restrict__ X8, int NKB) {
-    __shared__ uint32_t lut[256];      // packed byte (4 codes) -> 4 int8 design values
     const int J = blockIdx.x, kb0 = blockIdx.y * DEC8_KBS;
     const int r = threadIdx.x & 127, ch = threadIdx.x >> 7;
-    if (threadIdx.x < 256) {
-        uint32_t w = 0;
-        for (int q = 0; q < 4; q++) {
-            const int code = (threadIdx.x >> (2 * q)) & 3;
-            const int v = (code == 3) ? 0 : (int)a.uni[0][code];
-            w |= (uint32_t)(v & 0xff) << (8 * q);
-        }
-        lut[threadIdx.x] = w;
-    }
-    __syncthreads();
+    // the triple's values by code as the four bytes of one register (code 3 -> 0): PRMT then maps four 2-bit codes to four
+    // int8 values in one instruction — no shared-memory table, no bank conflicts
+    const uint32_t tbl = ((uint32_t)((int)a.uni[0][0] & 0xff)) | ((uint32_t)((int)a.uni[0][1] & 0xff) << 8) | ((uint32_t)((int)a.uni[0][2] & 0xff) << 16);
     const int64_t snp = (int64_t)J * 128 + r;
     const bool live = snp < a.nsnp;
     const uint8_t* rec = a.packed + (live ? (a.vmap ? (int64_t)a.vmap[snp] : snp) : 0) * a.bpv;
@@ -325,7 +316,13 @@ __global__ void __launch_bounds__(512) decode_i8_tile_kernel(const DecodeArgs a,
                 const uint32_t word = seg[r][(kb - kb0) * 4 + ch];
                 if (word & (word >> 1) & 0x55555555u) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
 #pragma unroll
-                for (int b4 = 0; b4 < 4; b4++) w[b4] = lut[(word >> (8 * b4)) & 0xffu];
+                for (int b4 = 0; b4 < 4; b4++) {
+                    // four 2-bit codes -> four selector nibbles (bits 0-1, 4-5, 8-9, 12-13)
+                    uint32_t sel = (word >> (8 * b4)) & 0xffu;
+                    sel = (sel | (sel << 4)) & 0x0f0fu;
+                    sel = (sel | (sel << 2)) & 0x3333u;
+                    w[b4] = __byte_perm(tbl, 0u, sel);
+                }
             } else {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
@@ -445,16 +442,25 @@ int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st) {
 // K4q: X8 (128 SNPs x n, int8) against a column block of G = C L^-T [Qc | r | R_f] split into Q digit planes:
 //      out[snp][col] = g_snp' G_col  exactly (up to the 2^-48 truncation of G below each column's power-of-two scale):
 //      u = Qc' w (cr columns), b = r' w, and b* for every permutation seed in ONE pass over the genotype tile per column block.
-// Same pipeline as K2q; the Q planes of a column block are accumulated side by side in TMEM (Q * NB <= 512 columns).
+// Same pipeline and the same operand economy as K2q: the work item is a PAIR of SNP tiles against one column block, so a
+// k-block costs 2 x 8 KB of genotypes + Q * NB * 64 B of planes for 2 x 128 x (Q NB) x 64 MACs (NB = 40: 31 KB per 480 tensor
+// clocks = 65 B/clk/SM, K2q's figure; the single-tile form with NB = 80 streamed 79 B/clk and idled the pipe).  The Q planes
+// of the block sit side by side along N in shared memory and in TMEM (plane q of tile t at column 256 t + q NB, Q NB <= 256), so
+// one instruction covers all planes and the A tile is read from shared memory once per K step.
+// Warps: 0 TMA producer, 1 MMA issuer, 4-11 epilogue (4 per SNP tile; thread = TMEM lane = SNP).
 // ================================================================================================
-constexpr int XG_MAX_NB = 80;
-constexpr int XG_STAGES = 5;
-constexpr int XG_STAGE_MAX = QF_A_BYTES + 6 * XG_MAX_NB * QF_KB;     // 8 KB + 30 KB
-constexpr int XG_SMEM = XG_STAGES * XG_STAGE_MAX + 256;
+constexpr int XG_STAGES = 7;
+constexpr int XG_STAGE_BYTES = 2 * QF_A_BYTES + 256 * QF_KB;     // 16 KB + at most 16 KB of planes
+constexpr int XG_SMEM = XG_STAGES * XG_STAGE_BYTES + 256;
 
-__global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
+#define XG_TMEM_LD8(v, taddr)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                          \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
+                 : "r"(taddr))
+
+__global__ void __launch_bounds__(QF_THREADS, 1) xg_i8_kernel(const XgArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XG_STAGES * XG_STAGE_MAX);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + XG_STAGES * XG_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + XG_STAGES;
     uint64_t* acc_full = empty_bar + XG_STAGES;
     uint64_t* acc_empty = acc_full + 1;
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < XG_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 1); }
         qbar_init(acc_full, 1);
-        qbar_init(acc_empty, 4);
+        qbar_init(acc_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -475,51 +481,54 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
     const int NB = g.NB, Q = g.Q;
-    const uint32_t b_bytes = (uint32_t)Q * NB * QF_KB;          // all planes of one k-block
-    const uint32_t stage_bytes = QF_A_BYTES + b_bytes;
+    const int n_total = Q * NB;                                  // MMA N: all planes of the column block
+    const uint32_t b_bytes = (uint32_t)n_total * QF_KB;          // all planes of one k-block
     const int nkb = g.NKB_live;
+    const int NJ2 = (g.NJ + 1) >> 1;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-                const int J = (int)(item / g.NCT), ct = (int)(item % g.NCT);   // column blocks of one SNP tile back to back: X8 stays L2-hot
-                const int8_t* a_src = g.X8 + (int64_t)J * g.NKB * QF_A_BYTES;
+                const int JP = (int)(item / g.NCT), ct = (int)(item % g.NCT);   // column blocks of one tile pair back to back: X8 stays L2-hot
+                const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;
+                const int8_t* a_src = g.X8 + (int64_t)(2 * JP) * g.NKB * QF_A_BYTES;
                 const int8_t* b_src = g.G8 + (int64_t)ct * g.NKB * b_bytes;
                 for (int kb = 0; kb < nkb; kb++) {
                     qbar_wait(&empty_bar[stage], phase ^ 1);
-                    unsigned char* dst = smem + (size_t)stage * XG_STAGE_MAX;
-                    qbar_expect_tx(&full_bar[stage], stage_bytes);
+                    unsigned char* dst = smem + (size_t)stage * XG_STAGE_BYTES;
+                    qbar_expect_tx(&full_bar[stage], nt * QF_A_BYTES + b_bytes);
+                    qtma_bulk_g2s(dst + 2 * QF_A_BYTES, b_src + (int64_t)kb * b_bytes, b_bytes, &full_bar[stage]);
                     qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
-                    qtma_bulk_g2s(dst + QF_A_BYTES, b_src + (int64_t)kb * b_bytes, b_bytes, &full_bar[stage]);
+                    if (nt == 2) qtma_bulk_g2s(dst + QF_A_BYTES, a_src + ((int64_t)g.NKB + kb) * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
                     if (++stage == XG_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // The Q planes of the column block sit side by side along N in the B block ([k16 chunk][(Q*NB)/8 groups][8][16 B]) and in
-            // TMEM (plane q at column q*NB), so one instruction covers up to 256 of the Q*NB columns: the A tile is read from
-            // shared memory once per 256 columns instead of once per plane (N = NB <= 80 alone would be smem-read bound).
-            const int n_total = Q * NB;
+            // B block: [k16 chunk 4][n_total / 8 groups][8 columns][16 B]  ->  LBO = n_total / 8 * 128 B between k16 chunks, SBO 128 B
             const uint32_t lbo_b = (uint32_t)(n_total / 8) * 128;
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)n_total >> 3) << 17) | ((128u >> 4) << 24);
             uint32_t stage = 0, phase = 0, aphase = 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                const int JP = (int)(item / g.NCT);
+                const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;
                 qbar_wait(acc_empty, aphase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < nkb; kb++) {
                     qbar_wait(&full_bar[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t sa = qsmem_u32(smem + (size_t)stage * XG_STAGE_MAX);
-                    const uint32_t sb = sa + QF_A_BYTES;
-                    for (int n0 = 0; n0 < n_total; n0 += 256) {
-                        const uint32_t n_this = (uint32_t)min(256, n_total - n0);
-                        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((n_this >> 3) << 17) | ((128u >> 4) << 24);
+                    const uint32_t sa = qsmem_u32(smem + (size_t)stage * XG_STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * QF_A_BYTES;
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        if (t >= nt) break;
 #pragma unroll
                         for (int j = 0; j < QF_KB / 32; j++) {
-                            const uint64_t ad = umma_desc(sa + j * 4096, 2048, 128);
-                            const uint64_t bd = umma_desc(sb + j * 2 * lbo_b + (n0 / 8) * 128, lbo_b, 128);
-                            umma_i8(tmem_base + n0, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            const uint64_t ad = umma_desc(sa + t * QF_A_BYTES + j * 4096, 2048, 128);
+                            const uint64_t bd = umma_desc(sb + j * 2 * lbo_b, lbo_b, 128);
+                            umma_i8(tmem_base + t * 256, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
@@ -529,38 +538,49 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
                 aphase ^= 1;
             }
         }
-    } else {
+    } else if (warp >= 4) {
         const int quad = warp & 3;
+        const int t = (warp - 4) >> 2;
         const int snp_l = quad * 32 + lane;
         uint32_t aphase = 0;
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-            const int J = (int)(item / g.NCT), ct = (int)(item % g.NCT);
+            const int JP = (int)(item / g.NCT), ct = (int)(item % g.NCT);
+            const int J = 2 * JP + t;
             const int64_t snp = (int64_t)J * 128 + snp_l;
+            const bool live = J < g.NJ && snp < g.nsnp;
             qbar_wait(acc_full, aphase);
             aphase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-            for (int c0 = 0; c0 < NB; c0 += 16) {
-                uint32_t v[6][16];
+            if (J < g.NJ) {
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
+                double* orow = g.out + snp * g.ld_out + (int64_t)ct * NB;
+                for (int c0 = 0; c0 < NB; c0 += 8) {
+                    uint32_t v[6][8];
 #pragma unroll
-                for (int q = 0; q < 6; q++)
-                    if (q < Q) XG_TMEM_LD16(v[q], trow + q * NB + c0);
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                    for (int q = 0; q < 6; q++)
+                        if (q < Q) XG_TMEM_LD8(v[q], trow + q * NB + c0);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;");
+                    double val[8];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int col = ct * NB + c0 + j;                 // column of G
-                    // planes pairwise exact in int64, then FP64: sum_q d_q 256^-(q+1)
-                    double val = 0.0;
+                    for (int j = 0; j < 8; j++) {
+                        // planes pairwise exact in int64, then FP64: sum_q d_q 256^-(q+1)
+                        double acc = 0.0;
 #pragma unroll
-                    for (int qq = 2; qq >= 0; qq--) {
-                        if (2 * qq < Q) {
-                            const long long comb = (long long)(int)v[2 * qq][j] * 256 + ((2 * qq + 1 < Q) ? (long long)(int)v[2 * qq + 1][j] : 0);
-                            // |comb| < 2^40: bias trick instead of I2F (16/clk/SM)
-                            val += (__longlong_as_double(0x4330000000000000LL + (comb + (1LL << 51))) - 6755399441055744.0) * g.pair_scale[qq];
+                        for (int qq = 2; qq >= 0; qq--) {
+                            if (2 * qq < Q) {
+                                const long long comb = (long long)(int)v[2 * qq][j] * 256 + ((2 * qq + 1 < Q) ? (long long)(int)v[2 * qq + 1][j] : 0);
+                                // |comb| < 2^40: bias trick instead of I2F (16/clk/SM)
+                                acc += (__longlong_as_double(0x4330000000000000LL + (comb + (1LL << 51))) - 6755399441055744.0) * g.pair_scale[qq];
+                            }
                         }
+                        val[j] = acc * __ldg(g.colscale + ct * NB + c0 + j);
                     }
-                    val *= g.colscale[col];
-                    if (snp < g.nsnp && col < g.NC) g.out[snp * g.ld_out + col] = val;
+                    if (live) {
+                        // NB and ld_out are multiples of 8: 16-byte stores, eight consecutive columns of the SNP's row
+                        double2* o2 = reinterpret_cast<double2*>(orow + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) o2[j] = make_double2(val[2 * j], val[2 * j + 1]);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -572,6 +592,9 @@ __global__ void __launch_bounds__(XG_THREADS, 1) xg_i8_kernel(const XgArgs g) {
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
+// column block width of K4q: the largest NB with Q * NB <= 256 that keeps the MMA N = Q * NB a multiple of 16
+int xg_block_cols(int Q) { return (Q % 2 == 0) ? (256 / Q) / 8 * 8 : (256 / Q) / 16 * 16; }
+
 int launch_xg(const XgArgs& g, int num_sms, cudaStream_t st) {
     static DeviceOnce configured;
     if (configured.need()) {
@@ -579,10 +602,10 @@ int launch_xg(const XgArgs& g, int num_sms, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(xg): %s", cudaGetErrorString(e)); return -3; }
         configured.set();
     }
-    if (g.NB % 16 != 0 || g.NB < 16 || g.NB > XG_MAX_NB || g.Q < 1 || g.Q > 6) { set_error("xg: bad column block %d / planes %d", g.NB, g.Q); return -1; }
+    if (g.NB % 8 != 0 || g.NB < 8 || g.Q < 1 || g.Q > 6 || g.Q * g.NB > 256 || (g.Q * g.NB) % 16 != 0 || g.ld_out % 8 != 0) { set_error("xg: bad column block %d / planes %d", g.NB, g.Q); return -1; }
     const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
     if (grid <= 0) return 0;
-    xg_i8_kernel<<<(unsigned)grid, XG_THREADS, XG_SMEM, st>>>(g);
+    xg_i8_kernel<<<(unsigned)grid, QF_THREADS, XG_SMEM, st>>>(g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("xg launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;

@@ -64,11 +64,16 @@ process FIT_MODEL {
     }
     M0 <- design_at(0); M1 <- design_at(1); M2 <- design_at(2)
     stopifnot(all(colnames(M0) == colnames(M1)), all(colnames(M0) == colnames(M2)), nrow(M0) == length(y.mm))
+    # two more probes tell the engine how every SNP column continues between the hard-call values (needed when the .pgen carries
+    # dosages and use_dosage is true, :26: x is then pgenlibr::Read's dosage and the columns are evaluated on it)
+    M05 <- design_at(0.5); M15 <- design_at(1.5)
+    # every visible GPU of the box works on this task's SNPs (FLEXLMM_DEVICES="0,1,..." narrows it)
+    devices <- as.integer(strsplit(Sys.getenv("FLEXLMM_DEVICES", "0"), ",")[[1]])
 
     seeds <- as.integer(${seeds})
     res <- .Call("flexlmm_fit", normalizePath("${pgen}"), as.integer(var_idx), as.integer(pgen_order),
                  L, as.numeric(y.mm), X.mm.null, as.numeric(ll.null), as.integer(attributes(ll.null)[["df"]]),
-                 M0, M1, M2, as.numeric(y.mm.pred), U1, as.numeric(e.p), seeds, 0L, ${dosage})
+                 M0, M1, M2, M05, M15, as.numeric(y.mm.pred), U1, as.numeric(e.p), seeds, devices, ${dosage})
     nvars <- length(var_idx)
 
     if (${do_permute}) {

@@ -235,6 +235,8 @@ int  flx_multi_device_count(flx_multi* m);
 int  flx_multi_set_whitening(flx_multi* m, const double* L, int64_t n, int64_t ld, int is_inverse);
 int  flx_multi_set_null(flx_multi* m, const double* X_null, int32_t c, const double* y_mm, double ll_null, int32_t df_null);
 int  flx_multi_set_design(flx_multi* m, const double* M0, const double* M1, const double* M2, int32_t k);
+int  flx_multi_set_design_probes(flx_multi* m, const double* M05, const double* M15);
+int  flx_multi_set_use_dosage(flx_multi* m, int use_dosage);
 int  flx_multi_set_perm(flx_multi* m, const double* y_pred, const double* U1, const double* e_p, int64_t mm, const int32_t* seeds, int32_t P);
 int  flx_multi_set_perm_implicit(flx_multi* m, const int32_t* seeds, int32_t P);
 int  flx_multi_open_pgen(flx_multi* m, const char* path, const int32_t* pgen_order, int64_t n);

@@ -173,14 +173,16 @@ def test_r_shim_compiles_against_stub():
 
 def test_shim_and_module_cover_every_abi_step():
     shim = open(os.path.join(ROOT, "flexlmm_b200", "r", "r_shim.c")).read()
-    for fn in ("flx_create", "flx_set_whitening", "flx_set_null", "flx_set_design", "flx_set_perm", "flx_open_pgen", "flx_pgen_info",
-               "flx_run", "flx_destroy", "flx_last_error", "flx_perm_indices"):
+    # one entry point per reference step, in the several-GPUs-from-one-caller form (ndev = 1 is the plain handle)
+    for fn in ("flx_multi_create", "flx_multi_set_whitening", "flx_multi_set_null", "flx_multi_set_design", "flx_multi_set_design_probes",
+               "flx_multi_set_use_dosage", "flx_multi_set_perm", "flx_multi_open_pgen", "flx_multi_run", "flx_multi_destroy", "flx_last_error",
+               "flx_perm_indices"):
         assert fn in shim
     nf = open(os.path.join(ROOT, "flexlmm_b200", "r", "fit_model.nf")).read()
     # same process interface as the reference (fit_model.nf:7-16)
     for line in ("tuple val(meta), path(mm), path(var_idx), path(null_model_fit), val(perm_seed)",
                  "tuple val(meta2), path(pgen), path(pvar), path(psam)", "path model", "tuple val(meta3), path(model_frame)", "val use_dosage",
-                 "path \"versions.yml\" , emit: versions", "chr\\\\tpos\\\\tid\\\\tref\\\\talt\\\\tlrt_chisq\\\\tlrt_df\\\\tpval\\\\tbeta"):
+                 "path \"versions.yml\" , emit: versions", "design_at(0.5)", "design_at(1.5)", "FLEXLMM_DEVICES", "chr\\\\tpos\\\\tid\\\\tref\\\\talt\\\\tlrt_chisq\\\\tlrt_df\\\\tpval\\\\tbeta"):
         assert line in nf, line
 
 
