@@ -133,11 +133,17 @@ def task_chol(w, dev, seed=13):
     del Q, U1, L
     torch.cuda.empty_cache()
 
-    def task(fm, packed, n_raw):
-        fm.set_whitening(inp["L"])
+    def task(fm, packed, n_raw, bcast_rank=None):
+        if bcast_rank is None:
+            fm.set_whitening(inp["L"])
+        else:   # N > 1: rank 0 alone uploads and inverts the factor; L^-1 and U1 reach the other GPUs by ncclBroadcast over NVLink
+            fm.set_whitening_bcast(inp["L"] if bcast_rank == 0 else None, n, root=0)
         fm.set_null(inp["X_null"], inp["y_mm"], inp["ll_null"], inp["df_null"])
         fm.set_design(inp["M0"], inp["M1"], inp["M2"])
-        fm.set_perm(inp["y_pred"], inp["U1"], inp["e_p"], inp["seeds"])
+        if bcast_rank is None:
+            fm.set_perm(inp["y_pred"], inp["U1"], inp["e_p"], inp["seeds"])
+        else:
+            fm.set_perm_bcast(inp["y_pred"], inp["U1"] if bcast_rank == 0 else None, inp["e_p"], inp["seeds"], root=0)
         fm.set_packed(packed, n_raw)
     return task, inp
 
@@ -154,7 +160,7 @@ def task_structured(w, dev, seed=13):
     M0, M1, M2, names, Xn, nn, cov1 = synth.design(w["model"], n, seed=11)
     seeds = np.arange(1, P + 1, dtype=np.int32)
 
-    def task(fm, packed, n_raw):
+    def task(fm, packed, n_raw, bcast_rank=None):
         g2 = torch.Generator(device=dev); g2.manual_seed(seed)
         U = torch.randn((n, 6), generator=g2, device=dev, dtype=torch.float64) * (1.5 / np.sqrt(n))
         W = torch.randn((n, 6), generator=g2, device=dev, dtype=torch.float64)
@@ -415,8 +421,11 @@ def run_workload(ctx, name, w, steps, warmup, route="auto", full=False, clocks=F
 
     if chroms == 1:
         fm = fx.FitModel(device=ctx.local_rank, int8=int8)
+        if ctx.world > 1:
+            attach_comm(ctx, fm)
+        ctx.barrier()
         t0 = time.perf_counter()
-        tasks[0](fm, packs[0], n)
+        tasks[0](fm, packs[0], n, bcast_rank=(ctx.rank if ctx.world > 1 else None))
         fm.prepare()
         out["setup_s_once"] = time.perf_counter() - t0
         fms = [fm]
@@ -434,9 +443,9 @@ def run_workload(ctx, name, w, steps, warmup, route="auto", full=False, clocks=F
         out["loco_first_run_s_per_factor"] = list(runner.run_s)
         out["setup_s_once"] = float(np.sum(runner.setup_s))
         fms = runner.fms
-    if ctx.world > 1:
-        for fm in fms:            # every handle reduces its own min-p vector over the ranks; min over chromosomes afterwards
-            attach_comm(ctx, fm)
+        if ctx.world > 1:
+            for fm in fms:        # every handle reduces its own min-p vector over the ranks; min over chromosomes afterwards
+                attach_comm(ctx, fm)
 
     def one_step(per_snp, res):
         acc = {}
