@@ -410,6 +410,15 @@ def run_workload(ctx, name, w, steps, warmup, route="auto", full=False, clocks=F
     chroms = w.get("chroms_full", w["chroms"]) if full else w["chroms"]
     int8 = (route == "auto")
     gen = task_chol if w["gen"] == "chol" else task_structured
+    # the packed genotypes of all local ranks live in host memory (like a page-cached .pgen): never ask for more than a third of it
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        need = M * chroms * ((n + 3) // 4) * max(1, ctx.world)
+        if need > avail / 3:
+            M = max(1024, int(M * (avail / 3) / need))
+    except Exception:
+        pass
     out = {"workload": name, "n": n, "permutations": P, "snps_per_gpu": M * chroms, "chromosomes_per_gpu": chroms}
 
     t_gen0 = time.perf_counter()
