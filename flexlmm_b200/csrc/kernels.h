@@ -41,6 +41,7 @@ struct QfArgs {
     int64_t n_items;
     int64_t nsnp;
     int T256, NJ, Q;
+    int GP;                   // SNP tile pairs per L2 group (qf_item); >= ceil(NJ / 2): no grouping
     int NKB;                  // k-blocks per X8 tile (n_pad256 / 64)
     int NKB_live;             // k-blocks that hold real samples
     long long* prof;          // optional [4 * grid]: MMA-issuer cycles total / waiting for the epilogue / waiting for TMA / of which in the first ring of an item

@@ -84,6 +84,22 @@ __device__ __forceinline__ int sext_byte(uint32_t w, int b) {
     return (int)d;
 }
 
+// item -> (row tile I, SNP tile pair JP, digit plane q).  Tile pairs are taken in groups of GP: a group goes through ALL row tiles
+// (long ones first) before the next group starts, so the group's genotype tiles (GP x 2 x NKB x 8 KB, sized for L2 by the host)
+// are read from HBM once per launch instead of once per row tile; planes innermost, so the Q CTAs that work on one tile pair at
+// the same time stream the same A blocks.  GP >= the pair count reproduces the plain (I, JP, q) order.
+__device__ __forceinline__ void qf_item(const QfArgs& g, int64_t item, int NJ2, int& I, int& JP, int& q) {
+    const int64_t per_group = (int64_t)g.T256 * g.GP * g.Q;
+    const int G = (int)(item / per_group);
+    int64_t rem = item - (int64_t)G * per_group;
+    const int pairs = min(g.GP, NJ2 - G * g.GP);
+    const int per_I = pairs * g.Q;
+    I = g.T256 - 1 - (int)(rem / per_I);
+    rem %= per_I;
+    JP = G * g.GP + (int)(rem / g.Q);
+    q = (int)(rem % g.Q);
+}
+
 template <int NDOT>
 __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -113,7 +129,6 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     // time stream the same A blocks, so a pair's genotype tiles come from HBM once per row tile, not once per plane (at
     // n = 20,000 a batch's tiles, 383 MB, no longer fit L2); long row tiles first
     const int NJ2 = (g.NJ + 1) >> 1;
-    const int per_I = NJ2 * g.Q;
     // the register file is partitioned per SM sub-partition, so the split must be explicit: the producer warpgroup gives its
     // registers to the eight epilogue warps, whose sixteen 16-byte genotype words per left vector then stay in registers
     if (warp < 4) {
@@ -123,9 +138,8 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-                const int I = g.T256 - 1 - (int)(item / per_I);
-                const int rem = (int)(item % per_I);
-                const int JP = rem / g.Q, q = rem % g.Q;
+                int I, JP, q;
+                qf_item(g, item, NJ2, I, JP, q);
                 int nkb = g.full ? g.NKB_live : 4 * (I + 1);      // lower-triangular matrices: k runs to the diagonal block
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
                 const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;      // an odd tile count leaves the last pair a single tile
@@ -150,8 +164,8 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             long long t_acc = 0, t_full = 0, t_head = 0, t0 = 0;
             const long long t_begin = g.prof ? clock64() : 0;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-                const int I = g.T256 - 1 - (int)(item / per_I);
-                const int JP = (int)(item % per_I) / g.Q;
+                int I, JP, q;
+                qf_item(g, item, NJ2, I, JP, q);
                 const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;
                 int nkb = g.full ? g.NKB_live : 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
@@ -195,9 +209,8 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         const int snp_l = quad * 32 + lane;
         uint32_t aphase = 0;
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-            const int I = g.T256 - 1 - (int)(item / per_I);
-            const int rem = (int)(item % per_I);
-            const int JP = rem / g.Q, q = rem % g.Q;
+            int I, JP, q;
+            qf_item(g, item, NJ2, I, JP, q);
             const int J = 2 * JP + t;
             const bool live = J < g.NJ;
             // the left vectors at the rows of the tile (for a plain quadratic form the SNP's own genotypes):
@@ -261,6 +274,7 @@ int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
         configured.set();
     }
     if (g.n_items <= 0) return 0;
+    if (g.GP < 1) { set_error("qf: GP must be >= 1"); return -1; }
     // the epilogue reduces 16 rows in s32: 16 * (128 * n_pad * xmax) * xmax with xmax = 2 must stay below 2^31
     if ((int64_t)g.NKB * QF_KB * 16 * 128 * 4 >= ((int64_t)1 << 31)) { set_error("qf: n too large for the s32 chunk reduction"); return -1; }
     const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
