@@ -1413,16 +1413,12 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 q.NKB_live = nkb_live;
                 q.n_items = (int64_t)h->T256 * h->Q * ((NJ + 1) / 2);
                 {
-                    // L2 grouping of the tile pairs (qf_item): HBM traffic of the launch is  groups x |planes| + |tiles|  with
-                    // groups of ~48 MB of genotype tiles, against  |tiles| x T256 / 2 + |planes|  ungrouped: group when it is less
-                    const double pair_b = 2.0 * h->NKB * 8192, tiles_b = pair_b * ((NJ + 1) / 2);
-                    const double planes_b = (q.full ? 2.0 : 1.0) * h->T256 * (h->T256 + 1) * 2.0 * h->Q * 16384;
-                    int gp = (int)std::max(1.0, std::floor(48e6 / pair_b));
-                    const int groups = ((NJ + 1) / 2 + gp - 1) / gp;
-                    const char* env = getenv("FLX_QF_GROUP_PAIRS");     // experiments: 0 = never group, k = pairs per group
-                    if (env) gp = atoi(env) > 0 ? atoi(env) : (NJ + 1) / 2;
-                    else if (groups * planes_b + tiles_b >= tiles_b * h->T256 / 2.0 + planes_b) gp = (NJ + 1) / 2;
-                    q.GP = std::max(1, std::min(gp, (NJ + 1) / 2));
+                    // L2 grouping of the tile pairs (qf_item) is OFF by default: measured (tools/qf_group_sweep.py, profiles/r02_qf_group_sweep.txt)
+                    // it buys nothing at n = 5,000 (K2q is not HBM bound: 13 % DRAM utilisation) and costs 25 % at n = 20,000, where groups
+                    // small enough for L2 leave too few CTAs sharing a digit-plane block.  FLX_QF_GROUP_PAIRS=k keeps the experiment reachable.
+                    const char* env = getenv("FLX_QF_GROUP_PAIRS");
+                    const int all = (NJ + 1) / 2;
+                    q.GP = (env && atoi(env) > 0) ? std::min(atoi(env), all) : all;
                 }
                 DevBuf<long long> prof_d;
                 const bool prof = h->cfg.verbose >= 2 && bi == 0 && pi == 0;
