@@ -141,12 +141,16 @@ struct flx_handle {
     // int8 quadratic-form path (K2q)
     bool fast = false;
     int Q = 6, T256 = 0, NKB = 0;
-    // every SNP term is g_t(x) * c_t[sample] with an integer triple g_t (|g| <= 2, "alpha") and a per-sample scale c_t ("group")
+    // every SNP term is g_t(x) * c_t[sample] with an integer triple g_t (|g| <= 2) and a per-sample scale c_t.  A 0/1 scale (the
+    // indicator column of an x:factor interaction) is folded into the int8 genotype tile as a sample mask, so such terms share the
+    // digit planes of the unscaled matrix: a tile set ("alpha") = (triple, mask); a real-valued scale is a "group" with its own planes
     struct QfPass { int mat, amma, ndot, adot[2], slot[2]; };
+    static constexpr int MAX_NA = 4;
     struct FastPlan {
-        int NG = 0, NA = 0, nslots = 0;
+        int NG = 0, NA = 0, nslots = 0, nmask = 0;
         int grp[8]{}, alp[8]{};
-        int aval[2][3]{};
+        int aval[MAX_NA][3]{};
+        int amask[MAX_NA]{};            // sample mask of the tile set (index into mask_d), -1: none
         bool ones[2]{};                 // group scale is identically 1
         std::vector<QfPass> passes;     // one K2q launch each
         int8_t slot_a[8][8]{}, slot_b[8][8]{};
@@ -155,6 +159,7 @@ struct flx_handle {
     DevBuf<double> rowscale[4], qf_part, G_scale[2], cvec_d, ub, Hd;
     int NB_G = 16, ntilesG = 1;                    // column blocks of G: ntilesG x NB_G >= cr + 1 + P
     DevBuf<int32_t> refit_flag, refit_list, out_map_d;
+    DevBuf<uint8_t> mask_d;                        // [nmask][n_pad256]: 0xFF keep / 0x00 zero, per model sample (tile-set masks of the int8 plan)
     DevBuf<int> df_count, missing;
     DevBuf<long long> coll_d;                      // [nvars, status] of the end-of-run collective
     int fallback_reason = 0;                       // FLX_FALLBACK_*: why `fast` is false
@@ -854,76 +859,129 @@ static int finalize_setup(flx_handle* h) {
     flx_handle::FastPlan& pl = h->plan;
     pl = flx_handle::FastPlan();
     std::vector<std::vector<double>> cvecs;
+    std::vector<std::vector<uint8_t>> masks;
+    int slot_of[2][2][flx_handle::MAX_NA][flx_handle::MAX_NA];
+    memset(slot_of, -1, sizeof(slot_of));
     if (h->cfg.flags & FLX_FLAG_NO_INT8) h->fallback_reason = FLX_FALLBACK_FLAG;
     else if (!h->have_Z) h->fallback_reason = FLX_FALLBACK_NO_DENSE_INVERSE;
     else if (h->s > 4 || cr + 1 > 24) h->fallback_reason = FLX_FALLBACK_TOO_MANY_FORMS;
     else {
-        int why = FLX_FALLBACK_NONE;
-        for (int t = 0; t < h->s && !why; t++) {
-            const double* src[3] = {h->M0.data() + (size_t)snp_cols[t] * n, h->M1.data() + (size_t)snp_cols[t] * n, h->M2.data() + (size_t)snp_cols[t] * n};
-            // the sample with the largest entry fixes the integer triple
-            int64_t ibest = 0; double vbest = 0.0;
-            for (int64_t i = 0; i < n; i++)
-                for (int g = 0; g < 3; g++) if (std::fabs(src[g][i]) > vbest) { vbest = std::fabs(src[g][i]); ibest = i; }
-            if (!(vbest > 0.0) || !std::isfinite(vbest)) { why = FLX_FALLBACK_NOT_SEPARABLE; break; }
-            int a[3] = {0, 0, 0};
-            bool found = false;
-            for (int mlt = 1; mlt <= 2 && !found; mlt++) {
-                bool ints = true;
-                for (int g = 0; g < 3; g++) {
-                    const double v = src[g][ibest] * mlt / vbest;
-                    if (v != std::floor(v)) ints = false; else a[g] = (int)v;
+        // Two ways to lay a design out, tried in turn; the cheaper feasible one (in K2q pass units) wins:
+        //   plain  — every distinct per-sample scale is a group with its own digit planes (x + I(x==1) + x:cov: 5 units);
+        //   folded — 0/1 scales (the indicator columns of an x:factor interaction) become sample masks of the int8 genotype tiles,
+        //            so those terms share the unscaled planes (x + I(x==1) + x:factor with three levels: 8 units instead of the
+        //            FP64 route, which costs ~14).
+        struct Trial { int why = FLX_FALLBACK_NONE; flx_handle::FastPlan pl; std::vector<std::vector<double>> cvecs; std::vector<std::vector<uint8_t>> masks;
+                       int slot_of[2][2][flx_handle::MAX_NA][flx_handle::MAX_NA]; int units = 0; };
+        auto build = [&](bool fold, Trial& T) {
+            flx_handle::FastPlan& pl = T.pl;
+            std::vector<std::vector<double>>& cvecs = T.cvecs;
+            std::vector<std::vector<uint8_t>>& masks = T.masks;
+            int& why = T.why;
+            auto& slot_of = T.slot_of;
+            for (int t = 0; t < h->s && !why; t++) {
+                const double* src[3] = {h->M0.data() + (size_t)snp_cols[t] * n, h->M1.data() + (size_t)snp_cols[t] * n, h->M2.data() + (size_t)snp_cols[t] * n};
+                // the sample with the largest entry fixes the integer triple
+                int64_t ibest = 0; double vbest = 0.0;
+                for (int64_t i = 0; i < n; i++)
+                    for (int g = 0; g < 3; g++) if (std::fabs(src[g][i]) > vbest) { vbest = std::fabs(src[g][i]); ibest = i; }
+                if (!(vbest > 0.0) || !std::isfinite(vbest)) { why = FLX_FALLBACK_NOT_SEPARABLE; break; }
+                int a[3] = {0, 0, 0};
+                bool found = false;
+                for (int mlt = 1; mlt <= 2 && !found; mlt++) {
+                    bool ints = true;
+                    for (int g = 0; g < 3; g++) {
+                        const double v = src[g][ibest] * mlt / vbest;
+                        if (v != std::floor(v)) ints = false; else a[g] = (int)v;
+                    }
+                    found = ints;
                 }
-                found = ints;
+                if (!found) { why = FLX_FALLBACK_NOT_SEPARABLE; break; }
+                int g0 = 0; while (g0 < 3 && a[g0] == 0) g0++;
+                if (a[g0] < 0) for (int g = 0; g < 3; g++) a[g] = -a[g];
+                int gs = 0; for (int g = 1; g < 3; g++) if (std::abs(a[g]) > std::abs(a[gs])) gs = g;
+                std::vector<double> c(n);
+                for (int64_t i = 0; i < n && !why; i++) {
+                    c[i] = src[gs][i] / a[gs];                       // exact: a in {+-1, +-2}
+                    for (int g = 0; g < 3; g++) if (src[g][i] != a[g] * c[i]) why = FLX_FALLBACK_NOT_SEPARABLE;
+                }
+                if (why) break;
+                // a 0/1 scale becomes a sample mask of the tile set and the term joins the unscaled group
+                bool binary = true, all_one = true;
+                for (int64_t i = 0; i < n; i++) { binary = binary && (c[i] == 0.0 || c[i] == 1.0); all_one = all_one && (c[i] == 1.0); }
+                int mk = -1;
+                if (fold && binary && !all_one) {
+                    std::vector<uint8_t> mv(n);
+                    for (int64_t i = 0; i < n; i++) mv[i] = c[i] != 0.0 ? 0xFF : 0x00;
+                    for (int q = 0; q < (int)masks.size(); q++) if (masks[q] == mv) mk = q;
+                    if (mk < 0) { mk = (int)masks.size(); masks.push_back(std::move(mv)); }
+                    std::fill(c.begin(), c.end(), 1.0);
+                }
+                int al = -1, gr = -1;
+                for (int q = 0; q < pl.NA; q++) if (pl.aval[q][0] == a[0] && pl.aval[q][1] == a[1] && pl.aval[q][2] == a[2] && pl.amask[q] == mk) al = q;
+                if (al < 0) {
+                    if (pl.NA == flx_handle::MAX_NA) { why = FLX_FALLBACK_TOO_MANY_FORMS; break; }
+                    al = pl.NA++;
+                    for (int g = 0; g < 3; g++) pl.aval[al][g] = a[g];
+                    pl.amask[al] = mk;
+                }
+                for (int q = 0; q < pl.NG; q++) if (memcmp(cvecs[q].data(), c.data(), n * sizeof(double)) == 0) gr = q;
+                if (gr < 0) {
+                    if (pl.NG == 2) { why = FLX_FALLBACK_TOO_MANY_FORMS; break; }
+                    gr = pl.NG++;
+                    bool ones = true;
+                    for (int64_t i = 0; i < n; i++) ones = ones && (c[i] == 1.0);
+                    pl.ones[gr] = ones;
+                    cvecs.push_back(std::move(c));
+                }
+                pl.alp[t] = al; pl.grp[t] = gr;
             }
-            if (!found) { why = FLX_FALLBACK_NOT_SEPARABLE; break; }
-            int g0 = 0; while (g0 < 3 && a[g0] == 0) g0++;
-            if (a[g0] < 0) for (int g = 0; g < 3; g++) a[g] = -a[g];
-            int gs = 0; for (int g = 1; g < 3; g++) if (std::abs(a[g]) > std::abs(a[gs])) gs = g;
-            std::vector<double> c(n);
-            for (int64_t i = 0; i < n && !why; i++) {
-                c[i] = src[gs][i] / a[gs];                       // exact: a in {+-1, +-2}
-                for (int g = 0; g < 3; g++) if (src[g][i] != a[g] * c[i]) why = FLX_FALLBACK_NOT_SEPARABLE;
-            }
-            if (why) break;
-            int al = -1, gr = -1;
-            for (int q = 0; q < pl.NA; q++) if (pl.aval[q][0] == a[0] && pl.aval[q][1] == a[1] && pl.aval[q][2] == a[2]) al = q;
-            if (al < 0) { if (pl.NA == 2) { why = FLX_FALLBACK_TOO_MANY_FORMS; break; } al = pl.NA++; for (int g = 0; g < 3; g++) pl.aval[al][g] = a[g]; }
-            for (int q = 0; q < pl.NG; q++) if (memcmp(cvecs[q].data(), c.data(), n * sizeof(double)) == 0) gr = q;
-            if (gr < 0) {
-                if (pl.NG == 2) { why = FLX_FALLBACK_TOO_MANY_FORMS; break; }
-                gr = pl.NG++;
-                bool ones = true;
-                for (int64_t i = 0; i < n; i++) ones = ones && (c[i] == 1.0);
-                pl.ones[gr] = ones;
-                cvecs.push_back(std::move(c));
-            }
-            pl.alp[t] = al; pl.grp[t] = gr;
-        }
-        h->fallback_reason = why;
-        h->fast = (why == FLX_FALLBACK_NONE);
+            if (why) return;
+            constexpr int MA = flx_handle::MAX_NA;
+            memset(slot_of, -1, sizeof(slot_of));
+            bool used[2][MA] = {};
+            for (int t = 0; t < h->s; t++) used[pl.grp[t]][pl.alp[t]] = true;
+            for (int a = 0; a < pl.NG; a++)
+                for (int b = a; b < pl.NG; b++)
+                    for (int ar = 0; ar < pl.NA; ar++) {
+                        if (!used[b][ar]) continue;
+                        // the epilogue of a pass dots with at most two left vectors: more tile sets on the left take more passes
+                        flx_handle::QfPass ps{};
+                        ps.mat = a * pl.NG + b; ps.amma = ar; ps.ndot = 0;
+                        for (int al = 0; al < pl.NA; al++) {
+                            if (!used[a][al]) continue;
+                            ps.adot[ps.ndot] = al; ps.slot[ps.ndot] = pl.nslots; slot_of[a][b][al][ar] = pl.nslots++; ps.ndot++;
+                            if (ps.ndot == 2) { pl.passes.push_back(ps); ps.ndot = 0; }
+                        }
+                        if (ps.ndot > 0) pl.passes.push_back(ps);
+                    }
+            if (pl.nslots > 16) { why = FLX_FALLBACK_TOO_MANY_FORMS; return; }
+            for (const auto& ps : pl.passes) T.units += (ps.mat / pl.NG != ps.mat % pl.NG) ? 2 : 1;
+        };
+        Trial plain, folded;
+        build(false, plain);
+        build(true, folded);
+        Trial* best = nullptr;
+        if (!plain.why) best = &plain;
+        if (!folded.why && (!best || folded.units < best->units)) best = &folded;
+        h->fallback_reason = best ? FLX_FALLBACK_NONE : (plain.why == FLX_FALLBACK_NOT_SEPARABLE ? plain.why : folded.why);
+        h->fast = best != nullptr;
+        if (best) { pl = best->pl; cvecs = best->cvecs; masks = best->masks; memcpy(slot_of, best->slot_of, sizeof(slot_of)); }
     }
     if (h->fast) {
-        // passes: one K2q launch per (matrix, triple on the right), its epilogue dots with every triple used on the left.
+        // passes: one K2q launch per (matrix, tile set on the right), its epilogue dots with the tile sets used on the left.
         //   same scale a:      T^(a,a) = tril(C_a V^-1 C_a), half diagonal: A_raw[t][v] = g_t' T g_v + g_v' T g_t
         //   scales a < b:      the FULL matrix F^(a,b) = C_a V^-1 C_b:        A_raw[t][v] = g_t' F g_v  (t in a, v in b)
         // (a full pass costs two triangular ones, but one full pass with two left vectors replaces three triangular passes
         //  of the x + I(x==1) + x:cov model: 5 pass units instead of 6)
-        int slot_of[2][2][2][2];
-        memset(slot_of, -1, sizeof(slot_of));
-        bool used[2][2] = {{false, false}, {false, false}};
-        for (int t = 0; t < h->s; t++) used[pl.grp[t]][pl.alp[t]] = true;
-        for (int a = 0; a < pl.NG; a++)
-            for (int b = a; b < pl.NG; b++)
-                for (int ar = 0; ar < pl.NA; ar++) {
-                    if (!used[b][ar]) continue;
-                    flx_handle::QfPass ps{};
-                    ps.mat = a * pl.NG + b; ps.amma = ar; ps.ndot = 0;
-                    for (int al = 0; al < pl.NA; al++)
-                        if (used[a][al]) { ps.adot[ps.ndot] = al; ps.slot[ps.ndot] = pl.nslots; slot_of[a][b][al][ar] = pl.nslots++; ps.ndot++; }
-                    pl.passes.push_back(ps);
-                }
-        if (pl.nslots > 16) { set_error("internal: %d int8 forms exceed the K3b slot table", pl.nslots); return FLX_ERR_BAD_ARG; }
+        pl.nmask = (int)masks.size();
+        if (pl.nmask > 0) {
+            const size_t np256 = (size_t)((n + 255) / 256) * 256;
+            std::vector<uint8_t> mh((size_t)pl.nmask * np256, 0);
+            for (int q = 0; q < pl.nmask; q++) memcpy(mh.data() + (size_t)q * np256, masks[q].data(), n);
+            FLX_TRY(h->mask_d.ensure(mh.size()));
+            FLX_CUDA_TRY(cudaMemcpy(h->mask_d.p, mh.data(), mh.size(), cudaMemcpyHostToDevice));
+        }
         for (int t = 0; t < h->s; t++)
             for (int v = 0; v < h->s; v++) {
                 const int a = pl.grp[t], b = pl.grp[v];
@@ -1358,6 +1416,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             // K1q: one int8 tile set per integer triple of the design (x itself, I(x==1), ...)
             for (int al = 0; al < h->plan.NA; al++) {
                 for (int g = 0; g < 3; g++) da.uni[0][g] = (double)h->plan.aval[al][g];
+                da.smask = h->plan.amask[al] >= 0 ? h->mask_d.p + (size_t)h->plan.amask[al] * ((size_t)h->T256 * 256) : nullptr;
                 FLX_TRY(launch_decode_i8(da, h->X8.p + al * x8_stride, NJ, h->NKB, h->stream));
                 h->stats.launches++;
             }

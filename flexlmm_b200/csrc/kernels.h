@@ -112,6 +112,7 @@ struct DecodeArgs {
     int NJ;                   // tiles in batch
     int* missing_flag;        // out: atomicMin(run-wide index of a SNP holding a missing call); INT_MAX = none
     uint8_t* codes_out;       // optional (tests): nsnp x n gathered codes
+    const uint8_t* smask;     // K1q only: per model sample 0xFF keep / 0x00 zero (an x:factor indicator folded into the int8 tile); nullptr: none
     // pgenlibr::Read: x = dosage / 16384 where the record has one for the sample (row = the SNP's record row, like `packed`)
     const uint16_t* dosage;   // nullptr: hard calls only
     int64_t dos_ld;

@@ -337,6 +337,10 @@ __global__ void __launch_bounds__(512) decode_i8_tile_kernel(const DecodeArgs a,
                     sel = (sel | (sel << 2)) & 0x3333u;
                     w[b4] = __byte_perm(tbl, 0u, sel);
                 }
+                if (a.smask) {
+                    const uint4 mk = __ldg(reinterpret_cast<const uint4*>(a.smask + k0));     // k0 is a multiple of 16
+                    w[0] &= mk.x; w[1] &= mk.y; w[2] &= mk.z; w[3] &= mk.w;
+                }
             } else {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(512) decode_i8_tile_kernel(const DecodeArgs a,
                         const int64_t ro = a.order ? (int64_t)a.order[k] : k;
                         const int code = (__ldg(rec + (ro >> 2)) >> (2 * (int)(ro & 3))) & 3;
                         if (code == 3) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));
-                        else w[b >> 2] |= (uint32_t)((int)a.uni[0][code] & 0xff) << (8 * (b & 3));
+                        else if (!a.smask || a.smask[k]) w[b >> 2] |= (uint32_t)((int)a.uni[0][code] & 0xff) << (8 * (b & 3));
                     }
                 }
             }

@@ -600,6 +600,59 @@ def test_int8_path_factor_interaction_and_rare_variants(fx, orc):
     assert_logp_close(r8["min_pval"], want)
 
 
+def _factor_task(orc, n, M, levels, seed, dominance=True, P=3):
+    """y ~ x [+ I(x == 1)] + x:group + group vs y ~ group with a `levels`-level factor (treatment contrasts): the reference's own
+    test formula shape (conf/test.config:35-36: covar1 is a factor)."""
+    from flexlmm_b200 import synth
+    t = synth.task(n, M, model="additive", P=P, seed=seed, effect=0.1)
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, levels, size=n)
+    ind = [(g == lv).astype(float) for lv in range(1, levels)]
+    one = np.ones(n)
+
+    def mm(v):
+        cols = [one, np.full(n, float(v))] + ([np.full(n, float(v == 1))] if dominance else []) + ind + [v * i for i in ind]
+        return np.column_stack(cols)
+    t["M0"], t["M1"], t["M2"] = mm(0), mm(1), mm(2)
+    t["X_null"] = orc.forwardsolve(t["L"], np.column_stack([one] + ind))
+    nm = orc.fit_null_model(t["y_mm"], t["X_null"])
+    t["ll_null"], t["df_null"] = nm["ll"], nm["df"]
+    t["y_pred"], t["U1"], t["e_p"] = nm["y_pred"], nm["U1"], nm["e_p"]
+    return t
+
+
+@pytest.mark.parametrize("levels,dominance,passes", [(3, False, 6), (3, True, 8), (4, False, 8), (2, True, 5)])
+def test_int8_path_multi_level_factor_interaction(fx, orc, levels, dominance, passes):
+    """x:factor with more than two levels used to drop to the FP64 route without a word (three scales).  The indicator columns are now
+    folded into the int8 genotype tiles as sample masks (up to four tile sets sharing the unscaled digit planes); the two-level case
+    keeps its cheaper plain plan (5 pass units)."""
+    t = _factor_task(orc, 380, 140, levels, seed=20 + levels, dominance=dominance)
+    r8, st8 = _run(fx, t, True, 140)
+    assert st8["int8_path"] == 1 and st8["fallback_reason"] == 0 and st8["int8_passes"] == passes
+    r64, st64 = _run(fx, t, False, 140)
+    assert st64["int8_path"] == 0
+    o = oracle_run(orc, t, t["codes_raw"])
+    compare(r8, o)
+    compare(r64, o)
+    want = np.array([oracle_run(orc, t, t["codes_raw"], seed=int(sd))["min_pval"] for sd in t["seeds"]])
+    assert_logp_close(r8["min_pval"], want)
+    assert_logp_close(r64["min_pval"], want)
+
+
+def test_fp64_fallback_is_reported(fx, orc, capfd):
+    """A design the int8 plan cannot hold (x:factor with five levels plus dominance: five tile sets) runs on the FP64 route and SAYS so:
+    flx_stats.fallback_reason and one line on stderr."""
+    t = _factor_task(orc, 300, 60, 5, seed=31, dominance=True, P=0)
+    with fx.FitModel() as fm:
+        fm.set_whitening(t["L"]); fm.set_null(t["X_null"], t["y_mm"], t["ll_null"], t["df_null"]); fm.set_design(t["M0"], t["M1"], t["M2"])
+        fm.set_packed(t["packed"], t["n_raw"], t["pgen_order"])
+        r = fm.run(np.arange(1, 61, dtype=np.int32))
+        st = fm.stats()
+    assert st["int8_path"] == 0 and st["fallback_reason"] == 3
+    assert "FP64 route" in capfd.readouterr().err
+    compare(r, oracle_run(orc, t, t["codes_raw"]))
+
+
 def test_int8_digit_planes_when_the_leading_digit_would_be_128(fx, orc):
     """Regression: a row (or column) whose largest entry has a mantissa above 127/128 needs one more bit of headroom in
     its power-of-two scale, or its leading balanced digit is 128 and wraps.  V^-1 = diag(1 / sigma^2) is built so that
@@ -875,7 +928,7 @@ def test_decorrelate_eigenvalue_clipping_fallback(fx):
     rng = np.random.default_rng(5)
     Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
     lam = np.abs(rng.standard_normal(n)) + 0.1
-    lam[:3] = [-2e-7, -5e-8, 0.0]
+    lam[:3] = [-2e-7, -5e-8, -3e-9]           # clearly below the rounding of syevd (an exact 0 comes back as +-1e-16: either side of the rule)
     K = (Q * lam) @ Q.T
     K = 0.5 * (K + K.T)
     y = rng.standard_normal(n); X = np.ones((n, 1))
