@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libflexlmm_cuda.so")
+LIB = os.environ.get("FLX_LIB") or os.path.join(LIBDIR, "libflexlmm_cuda.so")     # FLX_LIB: A/B runs against another build (tools/)
 SOURCES = ["api.cu", "panel_gemm.cu", "qf.cu", "decode.cu", "pgen_expand.cu", "snp_fit.cu", "setup.cu", "host_math.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -22,7 +22,7 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
+    if os.environ.get("FLX_LIB") or (not force and not _stale()):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []

@@ -1468,7 +1468,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 q.ndot = ps.ndot;
                 for (int d = 0; d < ps.ndot; d++) { q.Xd[d] = h->X8.p + ps.adot[d] * x8_stride; q.part[d] = h->qf_part.p + (int64_t)ps.slot[d] * nparts * nsnp; }
                 for (int i = 0; i < 8; i++) q.plane_scale[i] = std::ldexp(1.0, -8 * (i + 1));
-                q.nsnp = nsnp; q.T256 = h->T256; q.NJ = NJ; q.Q = h->Q; q.NKB = h->NKB;
+                q.nsnp = nsnp; q.n = h->n; q.T256 = h->T256; q.NJ = NJ; q.Q = h->Q; q.NKB = h->NKB;
                 q.NKB_live = nkb_live;
                 q.n_items = (int64_t)h->T256 * h->Q * ((NJ + 1) / 2);
                 {
@@ -1481,15 +1481,18 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                 }
                 DevBuf<long long> prof_d;
                 const bool prof = h->cfg.verbose >= 2 && bi == 0 && pi == 0;
-                if (prof) { FLX_TRY(prof_d.ensure(4 * (size_t)h->num_sms)); q.prof = prof_d.p; }
+                if (prof) { FLX_TRY(prof_d.ensure(16 * (size_t)h->num_sms)); FLX_CUDA_TRY(cudaMemsetAsync(prof_d.p, 0, 16 * (size_t)h->num_sms * sizeof(long long), h->stream)); q.prof = prof_d.p; }
                 FLX_TRY(launch_qf(q, h->num_sms, h->stream));
                 if (prof) {
-                    std::vector<long long> pv(4 * (size_t)h->num_sms);
+                    std::vector<long long> pv(16 * (size_t)h->num_sms);
                     FLX_CUDA_TRY(cudaMemcpy(pv.data(), prof_d.p, pv.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                    for (int i = 0; i < h->num_sms; i++) { a0 += pv[4 * i]; a1 += pv[4 * i + 1]; a2 += pv[4 * i + 2]; a3 += pv[4 * i + 3]; }
-                    fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA (%.1f%% in the first ring of an item), items/CTA %.1f\n",
-                            a0 / h->num_sms, 100 * a1 / a0, 100 * a2 / a0, 100 * a3 / a0, (double)q.n_items / h->num_sms);
+                    double a[16] = {};
+                    for (int i = 0; i < h->num_sms; i++) for (int j = 0; j < 16; j++) a[j] += (double)pv[16 * i + j] / h->num_sms;
+                    const double items = (double)q.n_items / h->num_sms;
+                    fprintf(stderr, "[flx] K2q MMA issuer: %.0f cycles/CTA, %.1f%% waiting for the epilogue, %.1f%% waiting for TMA (%.1f%% in the first ring of an item; waits > 200 clk: %.1f%%, %.1f per item), %.1f%% issuing, items/CTA %.1f\n",
+                            a[0], 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0], a[5] / items, 100 * a[6] / a[0], items);
+                    fprintf(stderr, "[flx] K2q producer: %.1f%% waiting for a free stage (waits > 200 clk: %.1f%%, %.1f per item); epilogue warp: %.0f clk per item draining, %.0f waiting\n",
+                            100 * a[9] / a[8], 100 * a[10] / a[8], a[11] / items, a[13] / items, a[12] / items);
                 }
                 h->stats.launches += 1; h->stats.launches_whiten++;
             }

@@ -40,11 +40,12 @@ struct QfArgs {
     double* part[2];          // per left vector: [T256][Q][nsnp] partial forms
     int64_t n_items;
     int64_t nsnp;
+    int64_t n;                // model samples (rows of T beyond n are padding)
     int T256, NJ, Q;
     int GP;                   // SNP tile pairs per L2 group (qf_item); >= ceil(NJ / 2): no grouping
     int NKB;                  // k-blocks per X8 tile (n_pad256 / 64)
     int NKB_live;             // k-blocks that hold real samples
-    long long* prof;          // optional [4 * grid]: MMA-issuer cycles total / waiting for the epilogue / waiting for TMA / of which in the first ring of an item
+    long long* prof;          // optional [16 * grid] cycle counters of the three roles (qf.cu, PROF builds): FitModel(verbose=2)
 };
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
 

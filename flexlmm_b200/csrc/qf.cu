@@ -62,7 +62,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(qsmem_u32(bar)) : "memory");
 }
 // instruction descriptor: D = S32 (2 @bit4), A = INT8 (1 @7), B = INT8 (1 @10), both K-major, N>>3 @17, M>>4 @24
-constexpr uint32_t QF_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t QF_IDESC_M128 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);      // | (N >> 3) << 17
 
 #define QF_TMEM_LD32(v, taddr)                                                                                                   \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
@@ -100,20 +100,50 @@ __device__ __forceinline__ void qf_item(const QfArgs& g, int64_t item, int NJ2, 
     q = (int)(rem % g.Q);
 }
 
-template <int NDOT>
+// ---- lean forms for the two single-thread loops (TMA producer, MMA issuer): at 512 tensor clocks per stage a dependent chain of
+// ~100 instructions IS the critical path (measured: the loops took 450-600 clk per stage), so barrier and descriptor words are
+// 32-bit shared-window values advanced by adds, nothing is recomputed per stage
+__device__ __forceinline__ bool qbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void qbar_wait_a(uint32_t bar, uint32_t parity) { while (!qbar_try_wait_a(bar, parity)) {} }
+__device__ __forceinline__ void qbar_expect_tx_a(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void qtma_bulk_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+// descriptors as (lo, hi) words: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14 (bit 46 of the 64-bit form)
+__device__ __forceinline__ void umma_i8_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one lane of a converged warp (the same lane every time): the single-thread roles run their loops WARP-WIDE and elect only the
+// issuing instruction, so that every loop variable stays warp-uniform and ptxas keeps barrier addresses and descriptors in uniform
+// registers; under `if (lane == 0)` it wraps each UTCIMMA / UBLKCP in an ELECT + R2UR.BROADCAST waterfall loop (~25 instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// prof (PROF builds only) [16 * grid] cycle counters — issuer: 0 total, 1 waiting for the epilogue, 2 waiting for operands, 3 of which in the first
+// ring of an item, 4-5 waits > 200 clk (sum, count), 6 issuing; producer: 8 total, 9 waiting for a free stage, 10-11 waits > 200 clk;
+// epilogue warp 4: 12 waiting for the accumulators, 13 draining them
+template <int NDOT, bool PROF>
 __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + QF_STAGES * QF_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + QF_STAGES;
-    uint64_t* acc_full = empty_bar + QF_STAGES;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* acc_full = empty_bar + QF_STAGES;      // [2]: one per SNP tile of the pair
+    uint64_t* acc_empty = acc_full + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < QF_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 1); }
-        qbar_init(acc_full, 1);
-        qbar_init(acc_empty, 8);
+        for (int s = 0; s < QF_STAGES; s++) { qbar_init(&full_bar[s], 1); qbar_init(&empty_bar[s], 2); }      // a stage is free when BOTH issuers' MMAs have read it
+        for (int t = 0; t < 2; t++) { qbar_init(&acc_full[t], 1); qbar_init(&acc_empty[t], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -124,6 +154,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem0 = qsmem_u32(smem), full0 = qsmem_u32(full_bar), empty0 = qsmem_u32(empty_bar);
 
     // item -> (row tile I, SNP tile pair JP, digit plane q), planes innermost: the Q CTAs that work on one tile pair at the same
     // time stream the same A blocks, so a pair's genotype tiles come from HBM once per row tile, not once per plane (at
@@ -134,71 +165,110 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
     if (warp < 4) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 0) {
-        // ---------------- TMA producer
-        if (lane == 0) {
+        // ---------------- TMA producer (warp-wide loop, one elected lane issues)
+        {
             uint32_t stage = 0, phase = 0;
+            long long p_empty = 0, p_long = 0, p_nlong = 0;
+            const long long p_begin = PROF ? clock64() : 0;
+            const int64_t b_step = (int64_t)g.Q * QF_B_BYTES;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 int I, JP, q;
                 qf_item(g, item, NJ2, I, JP, q);
                 int nkb = g.full ? g.NKB_live : 4 * (I + 1);      // lower-triangular matrices: k runs to the diagonal block
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
-                const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;      // an odd tile count leaves the last pair a single tile
-                const int8_t* a_src = g.X8 + (int64_t)(2 * JP) * g.NKB * QF_A_BYTES;
+                const bool two = 2 * JP + 1 < g.NJ;               // an odd tile count leaves the last pair a single tile
+                const int8_t* a0 = g.X8 + (int64_t)(2 * JP) * g.NKB * QF_A_BYTES;
+                const int8_t* a1 = a0 + (int64_t)g.NKB * QF_A_BYTES;
                 // triangular: 4*I*(I+1)/2 blocks precede tile I; full: NKB blocks per tile
-                const int8_t* b_src = g.T8 + ((g.full ? (int64_t)I * g.NKB : (int64_t)2 * I * (I + 1)) * g.Q + q) * QF_B_BYTES;
+                const int8_t* bp = g.T8 + ((g.full ? (int64_t)I * g.NKB : (int64_t)2 * I * (I + 1)) * g.Q + q) * QF_B_BYTES;
+                const uint32_t bytes = (two ? 2 : 1) * QF_A_BYTES + QF_B_BYTES;
                 for (int kb = 0; kb < nkb; kb++) {
-                    qbar_wait(&empty_bar[stage], phase ^ 1);
-                    unsigned char* dst = smem + (size_t)stage * QF_STAGE_BYTES;
-                    qbar_expect_tx(&full_bar[stage], nt * QF_A_BYTES + QF_B_BYTES);
-                    qtma_bulk_g2s(dst + 2 * QF_A_BYTES, b_src + (int64_t)kb * g.Q * QF_B_BYTES, QF_B_BYTES, &full_bar[stage]);
-                    qtma_bulk_g2s(dst, a_src + (int64_t)kb * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
-                    if (nt == 2) qtma_bulk_g2s(dst + QF_A_BYTES, a_src + ((int64_t)g.NKB + kb) * QF_A_BYTES, QF_A_BYTES, &full_bar[stage]);
+                    const uint32_t fb = full0 + 8 * stage, dst = smem0 + stage * QF_STAGE_BYTES;
+                    if (PROF) {
+                        const long long t0 = clock64();
+                        qbar_wait_a(empty0 + 8 * stage, phase ^ 1);
+                        const long long dt = clock64() - t0;
+                        p_empty += dt; if (dt > 200) { p_long += dt; p_nlong++; }
+                    } else qbar_wait_a(empty0 + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
+                        qbar_expect_tx_a(fb, bytes);
+                        qtma_bulk_a(dst + 2 * QF_A_BYTES, bp, QF_B_BYTES, fb);
+                        qtma_bulk_a(dst, a0, QF_A_BYTES, fb);
+                        if (two) qtma_bulk_a(dst + QF_A_BYTES, a1, QF_A_BYTES, fb);
+                    }
+                    bp += b_step; a0 += QF_A_BYTES; a1 += QF_A_BYTES;
                     if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (PROF && lane == 0) { long long* pp = g.prof + 16 * blockIdx.x; pp[8] = clock64() - p_begin; pp[9] = p_empty; pp[10] = p_long; pp[11] = p_nlong; }
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer
-        if (lane == 0) {
+      } else if (warp <= 2) {
+        // ---------------- MMA issuers: warp 1 drives SNP tile 0 of the pair (accumulator columns 0-255), warp 2 tile 1 (256-511).
+        // A tcgen05.mma costs its issuing thread ~85 clk whatever its size (measured with N = 32: same kernel time), so ONE thread
+        // issuing a stage's four MMAs plus the barrier round trip needs > 600 clk for 512 clk of tensor work — the kernel was bound
+        // by that thread, not by the pipe.  The two accumulators are independent, so each gets its own issuer (warp-wide loop, one
+        // elected lane issues); a stage is released when both have committed.
+        {
+            const int t = warp - 1;
             uint32_t stage = 0, phase = 0, aphase = 0;
-            long long t_acc = 0, t_full = 0, t_head = 0, t0 = 0;
-            const long long t_begin = g.prof ? clock64() : 0;
+            long long t_acc = 0, t_full = 0, t_head = 0, t0 = 0, t_long = 0, n_long = 0, t_issue = 0;
+            const long long t_begin = PROF ? clock64() : 0;
+            // A block: [k16 chunk 4][row group 16][8 rows][16 B] -> LBO 2048 B, SBO 128 B;  B block: [k16 chunk 4][row group 32][8 rows][16 B] -> LBO 4096 B
+            const uint32_t d_hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo0 = (((smem0 + t * QF_A_BYTES) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+            const uint32_t b_lo0 = (((smem0 + 2 * QF_A_BYTES) >> 4) & 0x3FFFu) | ((4096u >> 4) << 16);
+            const uint32_t acc_full_a = qsmem_u32(&acc_full[t]), acc_empty_a = qsmem_u32(&acc_empty[t]);
+            const uint32_t tacc = tmem_base + t * 256;
             for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
                 int I, JP, q;
                 qf_item(g, item, NJ2, I, JP, q);
-                const int nt = (2 * JP + 1 < g.NJ) ? 2 : 1;
+                const bool mine = 2 * JP + t < g.NJ;      // an odd tile count leaves the last pair a single tile: the second issuer only keeps step
                 int nkb = g.full ? g.NKB_live : 4 * (I + 1);
                 if (nkb > g.NKB_live) nkb = g.NKB_live;
-                if (g.prof) t0 = clock64();
-                qbar_wait(acc_empty, aphase ^ 1);           // epilogue has drained the accumulators of the previous item
-                if (g.prof) t_acc += clock64() - t0;
+                // rows of T the MMAs must cover: the last tile's padding rows are zero planes (N shrinks to the live rows, a multiple
+                // of 16), and on the diagonal tile of a triangular matrix the rows above the k range of a K step are zero as well
+                int nrows = 256;
+                if (g.n - 256 * (int64_t)I < 256) nrows = (int)((g.n - 256 * (int64_t)I + 15) & ~(int64_t)15);
+                const int kb_plain = g.full ? nkb : min(nkb, 4 * I);      // k-blocks below the diagonal tile: all rows
+                const uint32_t idesc_full = QF_IDESC_M128 | (((uint32_t)nrows >> 3) << 17);
+                if (PROF) t0 = clock64();
+                qbar_wait_a(acc_empty_a, aphase ^ 1);           // the epilogue has drained this accumulator of the previous item
+                if (PROF) t_acc += clock64() - t0;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (int kb = 0; kb < nkb; kb++) {
-                    if (g.prof) t0 = clock64();
-                    qbar_wait(&full_bar[stage], phase);
-                    if (g.prof) { const long long dt = clock64() - t0; t_full += dt; if (kb < QF_STAGES) t_head += dt; }
+                    if (PROF) t0 = clock64();
+                    qbar_wait_a(full0 + 8 * stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t sa = qsmem_u32(smem + (size_t)stage * QF_STAGE_BYTES);
-                    const uint32_t sb = sa + 2 * QF_A_BYTES;
+                    if (PROF) { const long long dt = clock64() - t0; t_full += dt; if (kb < QF_STAGES) t_head += dt; if (dt > 200) { t_long += dt; n_long++; } t0 = clock64(); }
+                    const uint32_t soff = stage * (QF_STAGE_BYTES >> 4);
+                    const uint32_t al = a_lo0 + soff, bl = b_lo0 + soff;
+                    if (mine) {
+                        if (kb < kb_plain) {
+                            if (elect_one()) {
+                                umma_i8_w(tacc, al, bl, d_hi, idesc_full, kb > 0 ? 1u : 0u);
+                                umma_i8_w(tacc, al + (4096 >> 4), bl + (8192 >> 4), d_hi, idesc_full, 1u);
+                            }
+                        } else {
+                            // diagonal tile: K step j of k-block kb only meets rows r >= r0 = 64 (kb - 4 I) + 32 j
 #pragma unroll
-                    for (int t = 0; t < 2; t++) {
-                        if (t >= nt) break;
-#pragma unroll
-                        for (int j = 0; j < QF_KB / 32; j++) {
-                            // A block: [k16 chunk 4][row group 16][8 rows][16 B]  -> LBO 2048 B, SBO 128 B
-                            // B block: [k16 chunk 4][row group 32][8 rows][16 B]  -> LBO 4096 B, SBO 128 B
-                            const uint64_t ad = umma_desc(sa + t * QF_A_BYTES + j * 4096, 2048, 128);
-                            const uint64_t bd = umma_desc(sb + j * 8192, 4096, 128);
-                            umma_i8(tmem_base + t * 256, ad, bd, QF_IDESC, (kb > 0 || j > 0) ? 1u : 0u);
+                            for (int j = 0; j < 2; j++) {
+                                const int r0 = 64 * (kb - 4 * I) + 32 * j;
+                                const int N = nrows - r0;
+                                if (N > 0) {
+                                    const uint32_t id = QF_IDESC_M128 | (((uint32_t)N >> 3) << 17);
+                                    if (elect_one()) umma_i8_w(tacc + r0, al + ((j * 4096) >> 4), bl + ((j * 8192) >> 4) + (uint32_t)(r0 >> 3) * (128 >> 4), d_hi, id, (kb > 0 || j > 0) ? 1u : 0u);
+                                }
+                            }
                         }
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (elect_one()) umma_commit_a(empty0 + 8 * stage);
+                    if (PROF) t_issue += clock64() - t0;
                     if (++stage == QF_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(acc_full);
+                if (elect_one()) umma_commit_a(acc_full_a);
                 aphase ^= 1;
             }
-            if (g.prof) { g.prof[4 * blockIdx.x] = clock64() - t_begin; g.prof[4 * blockIdx.x + 1] = t_acc; g.prof[4 * blockIdx.x + 2] = t_full; g.prof[4 * blockIdx.x + 3] = t_head; }
+            if (PROF && t == 0 && lane == 0) { long long* pp = g.prof + 16 * blockIdx.x; pp[0] = clock64() - t_begin; pp[1] = t_acc; pp[2] = t_full; pp[3] = t_head; pp[4] = t_long; pp[5] = n_long; pp[6] = t_issue; }
         }
       }
     } else {
@@ -208,6 +278,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         const int t = (warp - 4) >> 2;
         const int snp_l = quad * 32 + lane;
         uint32_t aphase = 0;
+        long long e_wait = 0, e_work = 0;
         for (int64_t item = blockIdx.x; item < g.n_items; item += gridDim.x) {
             int I, JP, q;
             qf_item(g, item, NJ2, I, JP, q);
@@ -216,14 +287,26 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
             // the left vectors at the rows of the tile (for a plain quadratic form the SNP's own genotypes):
             // k = 256 I + r  ->  block 4 I + r / 64, chunk (r % 64) / 16
             const int64_t xoff = ((int64_t)(live ? J : 0) * g.NKB + 4 * I) * QF_A_BYTES + ((snp_l >> 3) * 8 + (snp_l & 7)) * 16;
-            const double* rs = g.rowscale + 256 * (int64_t)I;
+            // the chunks' power-of-two scales: the high words of 16 doubles (the low words are zero), fetched with the left vectors
+            // BEFORE the accumulator wait — a load inside the chunk loop would put a global-memory round trip into every chunk.
+            // Chunks beyond the live rows of the last tile were not written by the (trimmed) MMAs: scale 0 discards whatever TMEM holds
+            const int* rs_hi = reinterpret_cast<const int*>(g.rowscale + 256 * (int64_t)I) + 1;
+            const int nch = (g.n - 256 * (int64_t)I < 256) ? (int)((g.n - 256 * (int64_t)I + 15) >> 4) : 16;
+            uint32_t rsp[8];            // sign + exponent (the top 12 bits of a power of two) of two chunks per register
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+                const uint32_t lo16 = (c < nch) ? ((uint32_t)__ldg(rs_hi + 32 * c) >> 20) : 0u, hi16 = (c + 1 < nch) ? ((uint32_t)__ldg(rs_hi + 32 * (c + 1)) >> 20) : 0u;
+                rsp[c >> 1] = lo16 | (hi16 << 16);
+            }
             uint4 xq[NDOT][16];
 #pragma unroll
             for (int d = 0; d < NDOT; d++)
 #pragma unroll
                 for (int c = 0; c < 16; c++) xq[d][c] = __ldg(reinterpret_cast<const uint4*>(g.Xd[d] + xoff + (int64_t)(c >> 2) * QF_A_BYTES + ((c & 3) * 16) * 128));
-            qbar_wait(acc_full, aphase);
+            const long long e0 = PROF ? clock64() : 0;
+            qbar_wait(&acc_full[t], aphase);
             aphase ^= 1;
+            const long long e1 = PROF ? clock64() : 0;
             asm volatile("tcgen05.fence::after_thread_sync;");
             double sum[NDOT];
 #pragma unroll
@@ -245,43 +328,51 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
                         int cx32 = 0;
 #pragma unroll
                         for (int j = 0; j < 16; j++) cx32 += (int)acc[c & 1][j] * sext_byte(xw[j >> 2], j & 3);
+                        // a chunk the MMAs did not write may hold anything: its scale is 0 and 0 * (finite integer) = 0
                         const long long cx = cx32;
                         const double dv = __longlong_as_double(0x4330000000000000LL + (cx + (1LL << 51))) - 6755399441055744.0;
-                        sum[d] = fma(dv, rs[16 * c], sum[d]);
+                        sum[d] = fma(dv, __hiloint2double((int)(((rsp[c >> 1] >> (16 * (c & 1))) & 0xffffu) << 20), 0), sum[d]);
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
-            if (lane == 0) qbar_arrive(acc_empty);
+            if (lane == 0) qbar_arrive(&acc_empty[t]);
+            if (PROF && warp == 4 && lane == 0) { e_wait += e1 - e0; e_work += clock64() - e1; }
             const int64_t snp = (int64_t)J * 128 + snp_l;
             if (live && snp < g.nsnp) {
 #pragma unroll
                 for (int d = 0; d < NDOT; d++) g.part[d][((int64_t)I * g.Q + q) * g.nsnp + snp] = sum[d] * g.plane_scale[q];
             }
         }
+        if (PROF && warp == 4 && lane == 0) { long long* pp = g.prof + 16 * blockIdx.x; pp[12] = e_wait; pp[13] = e_work; }
     }
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
+template <int NDOT, bool PROF>
+static cudaError_t qf_launch_one(const QfArgs& g, unsigned grid, cudaStream_t st) {
     static DeviceOnce configured;
     if (configured.need()) {
-        cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(qf_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(qf): %s", cudaGetErrorString(e)); return -3; }
+        cudaError_t e = cudaFuncSetAttribute(qf_i8_kernel<NDOT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM);
+        if (e != cudaSuccess) return e;
         configured.set();
     }
+    qf_i8_kernel<NDOT, PROF><<<grid, QF_THREADS, QF_SMEM, st>>>(g);
+    return cudaGetLastError();
+}
+
+int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
     if (g.n_items <= 0) return 0;
     if (g.GP < 1) { set_error("qf: GP must be >= 1"); return -1; }
     // the epilogue reduces 16 rows in s32: 16 * (128 * n_pad * xmax) * xmax with xmax = 2 must stay below 2^31
     if ((int64_t)g.NKB * QF_KB * 16 * 128 * 4 >= ((int64_t)1 << 31)) { set_error("qf: n too large for the s32 chunk reduction"); return -1; }
-    const int64_t grid = g.n_items < num_sms ? g.n_items : num_sms;
-    if (g.ndot == 1) qf_i8_kernel<1><<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
-    else if (g.ndot == 2) qf_i8_kernel<2><<<(unsigned)grid, QF_THREADS, QF_SMEM, st>>>(g);
+    const unsigned grid = (unsigned)(g.n_items < num_sms ? g.n_items : num_sms);
+    cudaError_t e;
+    if (g.ndot == 1) e = g.prof ? qf_launch_one<1, true>(g, grid, st) : qf_launch_one<1, false>(g, grid, st);
+    else if (g.ndot == 2) e = g.prof ? qf_launch_one<2, true>(g, grid, st) : qf_launch_one<2, false>(g, grid, st);
     else { set_error("qf: ndot must be 1 or 2"); return -1; }
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("qf launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;
 }

@@ -1,12 +1,20 @@
+"""K2q MMA-issuer cycle split (epilogue wait, TMA wait) via FitModel(verbose=2): python tools/qf_prof.py [batch_tiles] [workload] [snps]
+FLX_QF_PROBE=1|2|3 (timing experiments, results invalid) shows what a smaller operand stream would buy."""
 import sys, numpy as np
 sys.path.insert(0, ".")
+import torch
 import bench, flexlmm_b200 as fx
-w = dict(bench.WORKLOADS["C2-small"]); w["M"] = 18944 * 2
-inp = bench.make_inputs(w, 0, 0)
 bt = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-fm = fx.FitModel(verbose=2, batch_tiles=bt)
-fm.set_whitening(inp["L"]); fm.set_null(inp["X_null"], inp["y_mm"], inp["ll_null"], inp["df_null"]); fm.set_design(inp["M0"], inp["M1"], inp["M2"])
-fm.set_perm(inp["y_pred"], inp["U1"], inp["e_p"], inp["seeds"]); fm.set_packed(inp["packed"], w["n"]); fm.make_resident()
-vi = np.arange(1, w["M"] + 1, dtype=np.int32)
-for _ in range(3):
-    fm.run(vi, per_snp=False); print(fm.stats())
+name = sys.argv[2] if len(sys.argv) > 2 else "C2-small"
+w = dict(bench.WORKLOADS[name]); M = int(sys.argv[3]) if len(sys.argv) > 3 else 75776
+w["P"] = min(w["P"], 100)
+dev = torch.device("cuda:0")
+packed = bench.make_packed(w["n"], M, 7, dev)
+task = (bench.task_chol if w["gen"] == "chol" else bench.task_structured)(w, dev)[0]
+verbose = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+fm = fx.FitModel(verbose=verbose, batch_tiles=bt)
+task(fm, packed, w["n"]); fm.make_resident()
+vi = np.arange(1, M + 1, dtype=np.int32)
+for _ in range(4):
+    fm.run(vi, per_snp=False); st = fm.stats(); print({k: round(float(st[k]), 3) for k in ("ms_whiten", "ms_decode", "ms_fit", "ms_perm", "ms_total", "refit_snps")}, flush=True)
+fm.close()

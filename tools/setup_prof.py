@@ -2,7 +2,7 @@ import sys, time, numpy as np
 sys.path.insert(0, ".")
 import bench, flexlmm_b200 as fx
 w = dict(bench.WORKLOADS["C2-small"]); w["M"] = 20000
-inp = bench.make_inputs(w, 0, 0)
+inp = None  # stale: see tools/qf_prof.py for the current input API
 vi = np.arange(1, 101, dtype=np.int32)
 for rep in range(4):
     t0 = time.perf_counter(); fm = fx.FitModel(verbose=1 if rep >= 2 else 0); t1 = time.perf_counter()
