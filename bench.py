@@ -530,9 +530,9 @@ def run_workload(ctx, name, w, steps, warmup, route="auto", full=False, clocks=F
 def config_of(name, w, world, full, M, chroms):
     return {"workload": f"{name}: {w['desc']}", "n": w["n"], "snps_per_gpu": M * chroms, "permutations": w["P"], "chromosomes_per_gpu": chroms,
             "design": {"k": w["k"], "c": w["c"], "s": w["s"]},
-            "arithmetic": "exact int8 route: tcgen05.mma kind::i8 on 6 base-256 digit planes of V^-1 (48 bits below a power-of-two scale per 16 rows), s32 accumulation, FP64 everywhere else; FP64 DMMA re-fit of near-collinear SNPs",
+            "arithmetic": "exact int8 route: genotypes travel as 2-bit codes and are expanded to int8 in the SM, tcgen05.mma kind::i8 on 6 base-256 digit planes of V^-1 (48 bits below a power-of-two scale per 16 rows), s32 accumulation, FP64 everywhere else; FP64 DMMA re-fit of near-collinear SNPs",
             "sharding": ("chromosomes per GPU (LOCO), " if chroms > 1 else "SNP blocks per GPU, ") + "NCCL min-allreduce of min-p" if world > 1 else "single GPU",
-            "l2_policy": "no flush needed: each step streams the packed genotypes (C2: 1.25 GB) and, per batch of 75,776 SNPs, int8 tiles (C2: 388 MB) + digit planes (C2: 79 MB), all above the 126 MB L2"}
+            "l2_policy": "no flush needed: each step streams the packed genotypes (C2: 1.25 GB) and, per batch of 75,776 SNPs, 2-bit code tiles (C2: 97 MB, re-read for each of the 20 row-tile rounds) + digit planes (C2: 79 MB): above the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------ main

@@ -10,7 +10,7 @@ LIB = os.environ.get("FLX_LIB") or os.path.join(LIBDIR, "libflexlmm_cuda.so")   
 SOURCES = ["api.cu", "panel_gemm.cu", "qf.cu", "decode.cu", "pgen_expand.cu", "snp_fit.cu", "setup.cu", "host_math.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"] + os.environ.get("FLX_NVCC_EXTRA", "").split()
 
 
 def _stale():

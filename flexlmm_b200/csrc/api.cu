@@ -155,7 +155,8 @@ struct flx_handle {
         std::vector<QfPass> passes;     // one K2q launch each
         int8_t slot_a[8][8]{}, slot_b[8][8]{};
     } plan;
-    DevBuf<int8_t> T8[4], X8, G8[2];               // T8[a * NG + b]: digit planes of tril(C_a V^-1 C_b) / of C_a V^-1 C_b; G8[a]: of C_a L^-T [Qc | r | R_f]
+    DevBuf<uint32_t> X2;                           // 2-bit code tiles of the batch, one set per tile set of the plan (K1q -> K2q / K4q)
+    DevBuf<int8_t> T8[4], G8[2];                   // T8[a * NG + b]: digit planes of tril(C_a V^-1 C_b) / of C_a V^-1 C_b; G8[a]: of C_a L^-T [Qc | r | R_f]
     DevBuf<double> rowscale[4], qf_part, G_scale[2], cvec_d, ub, Hd;
     int NB_G = 16, ntilesG = 1;                    // column blocks of G: ntilesG x NB_G >= cr + 1 + P
     DevBuf<int32_t> refit_flag, refit_list, out_map_d;
@@ -1114,7 +1115,7 @@ static int finalize_setup(flx_handle* h) {
         size_t free_b = 0, total_b = 0;
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t planes_b = (size_t)pl.NG * pl.NG * 2 * h->T256 * (h->T256 + 1) * h->Q * 16384;   // a full set = two triangular ones
-        const size_t batch_b = (size_t)h->num_sms * h->NKB * 8192 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);   // one tile per SM at least
+        const size_t batch_b = (size_t)h->num_sms * h->NKB * 2048 * pl.NA + (size_t)pl.nslots * h->T256 * h->Q * h->num_sms * 128 * 8 + ((size_t)2 << 30);   // one tile per SM at least
         if (planes_b + batch_b + (size_t)1024 * n * 8 > free_b) {
             h->fast = false;
             h->fallback_reason = FLX_FALLBACK_PLANES_DONT_FIT;
@@ -1164,7 +1165,7 @@ static int finalize_setup(flx_handle* h) {
     if (h->have_Z) {
         size_t free_b = 0, total_b = 0;
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t batch_b = h->fast ? (size_t)4 * h->num_sms * ((size_t)h->plan.NA * h->NKB * 8192 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 + (size_t)h->s * 128 * h->ntilesG * h->NB_G * 8)
+        const size_t batch_b = h->fast ? (size_t)4 * h->num_sms * ((size_t)h->plan.NA * h->NKB * 2048 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 + (size_t)h->s * 128 * h->ntilesG * h->NB_G * 8)
                                        : (size_t)2 * h->num_sms * h->KC * CHUNK * 8;
         if (free_b < batch_b + ((size_t)8 << 30)) { h->Zdense.release(); h->have_Z = false; }
     }
@@ -1189,9 +1190,9 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     else if (h->cfg.batch_tiles <= 0 && use_fast) {
         size_t free_b = 0, total_b = 0;
         FLX_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_tile = (size_t)h->plan.NA * h->NKB * 8192 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 +
+        const size_t per_tile = (size_t)h->plan.NA * h->NKB * 2048 + (size_t)h->plan.nslots * h->T256 * h->Q * 128 * 8 +
                                 (size_t)h->s * 128 * h->ntilesG * h->NB_G * 8 + (size_t)128 * 40 * 8 * (h->s + 2);
-        const size_t have = free_b + h->X8.cap + h->qf_part.cap * 8 + h->ub.cap * 8;     // what this handle already holds is reusable
+        const size_t have = free_b + h->X2.cap * 4 + h->qf_part.cap * 8 + h->ub.cap * 8;     // what this handle already holds is reusable
         int mult = 4;
         while (mult > 1 && (size_t)mult * h->num_sms * per_tile > have / 4) mult--;
         tiles_per_batch = mult * h->num_sms;
@@ -1225,12 +1226,12 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
     }
     const size_t tile_elems = (size_t)h->KC * CHUNK;
     if (!use_fast || decode_only) FLX_TRY(h->X.ensure((size_t)tiles_per_batch * tile_elems));
-    const size_t x8_stride = (size_t)tiles_per_batch * h->NKB * 8192;
+    const size_t x2_stride = (size_t)((tiles_per_batch + 1) / 2) * h->NKB * 1024;     // words per tile set: tile pairs x k-blocks x (2 x 512)
     const int64_t ldg = (int64_t)h->ntilesG * h->NB_G;     // row length of the K4q output: u (cr), b, b* (P), padding
     if (!decode_only) {
         if (!use_fast) FLX_TRY(h->W.ensure((size_t)tiles_per_batch * tile_elems));
         if (use_fast) {
-            FLX_TRY(h->X8.ensure(x8_stride * h->plan.NA));
+            FLX_TRY(h->X2.ensure(x2_stride * h->plan.NA));
             FLX_TRY(h->qf_part.ensure((size_t)h->plan.nslots * h->T256 * h->Q * snps_per_batch));
             FLX_TRY(h->ub.ensure((size_t)h->s * snps_per_batch * ldg));
             FLX_TRY(h->refit_flag.ensure(M_total));
@@ -1415,12 +1416,12 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
         if (use_fast && !decode_only) {
             // K1q: one int8 tile set per integer triple of the design (x itself, I(x==1), ...)
             for (int al = 0; al < h->plan.NA; al++) {
-                for (int g = 0; g < 3; g++) da.uni[0][g] = (double)h->plan.aval[al][g];
+                uint32_t vt_unused;
+                tile_code_map(h->plan.aval[al], &da.gmap, &vt_unused);
                 da.smask = h->plan.amask[al] >= 0 ? h->mask_d.p + (size_t)h->plan.amask[al] * ((size_t)h->T256 * 256) : nullptr;
-                FLX_TRY(launch_decode_i8(da, h->X8.p + al * x8_stride, NJ, h->NKB, h->stream));
+                FLX_TRY(launch_decode_i8(da, h->X2.p + al * x2_stride, NJ, h->NKB, h->stream));
                 h->stats.launches++;
             }
-            memcpy(da.uni, h->uni, sizeof(da.uni));
         } else {
             FLX_TRY(launch_decode(da, h->stream));
             h->stats.launches++;
@@ -1463,10 +1464,15 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             for (size_t pi = 0; pi < h->plan.passes.size(); pi++) {
                 const flx_handle::QfPass& ps = h->plan.passes[pi];
                 QfArgs q{};
-                q.X8 = h->X8.p + ps.amma * x8_stride; q.T8 = h->T8[ps.mat].p; q.rowscale = h->rowscale[ps.mat].p;
+                uint32_t gm_unused;
+                q.X2 = h->X2.p + ps.amma * x2_stride; tile_code_map(h->plan.aval[ps.amma], &gm_unused, &q.vt_mma);
+                q.T8 = h->T8[ps.mat].p; q.rowscale = h->rowscale[ps.mat].p;
                 q.full = (ps.mat / h->plan.NG != ps.mat % h->plan.NG) ? 1 : 0;
                 q.ndot = ps.ndot;
-                for (int d = 0; d < ps.ndot; d++) { q.Xd[d] = h->X8.p + ps.adot[d] * x8_stride; q.part[d] = h->qf_part.p + (int64_t)ps.slot[d] * nparts * nsnp; }
+                for (int d = 0; d < ps.ndot; d++) {
+                    q.Xd2[d] = h->X2.p + ps.adot[d] * x2_stride; tile_code_map(h->plan.aval[ps.adot[d]], &gm_unused, &q.vt_dot[d]);
+                    q.part[d] = h->qf_part.p + (int64_t)ps.slot[d] * nparts * nsnp;
+                }
                 for (int i = 0; i < 8; i++) q.plane_scale[i] = std::ldexp(1.0, -8 * (i + 1));
                 q.nsnp = nsnp; q.n = h->n; q.T256 = h->T256; q.NJ = NJ; q.Q = h->Q; q.NKB = h->NKB;
                 q.NKB_live = nkb_live;
@@ -1501,7 +1507,9 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             // launch against the digit planes of C_t [H | L^-T R_f]
             for (int t = 0; t < h->s; t++) {
                 XgArgs xa{};
-                xa.X8 = h->X8.p + h->plan.alp[t] * x8_stride; xa.G8 = h->G8[h->plan.grp[t]].p; xa.colscale = h->G_scale[h->plan.grp[t]].p;
+                uint32_t gm_unused;
+                xa.X2 = h->X2.p + h->plan.alp[t] * x2_stride; tile_code_map(h->plan.aval[h->plan.alp[t]], &gm_unused, &xa.vt);
+                xa.G8 = h->G8[h->plan.grp[t]].p; xa.colscale = h->G_scale[h->plan.grp[t]].p;
                 for (int i = 0; i < 3; i++) xa.pair_scale[i] = std::ldexp(1.0, -16 * (i + 1));
                 xa.n_items = (int64_t)h->ntilesG * ((NJ + 1) / 2); xa.NCT = h->ntilesG; xa.nsnp = nsnp; xa.NJ = NJ; xa.NB = h->NB_G; xa.NC = cr + 1 + (do_perm ? h->P : 0);
                 xa.Q = h->Q; xa.NKB = h->NKB; xa.NKB_live = nkb_live;

@@ -29,8 +29,10 @@ int launch_perm_contract(const GemmArgs& g, int s, int num_sms, cudaStream_t st)
 
 // ---------------------------------------------------------------- K2q (qf.cu): x' V^-1 x on the int8 tensor cores
 struct QfArgs {
-    const int8_t* X8;         // [NJ][NKB][8 KB]  int8 genotype tiles (128 SNPs x 64 samples per block, UMMA canonical K-major): MMA operand g'
-    const int8_t* Xd[2];      // tiles of the left vectors g of the forms g' T g' (same layout; Xd[0] == X8 for a plain quadratic form)
+    const uint32_t* X2;       // [tile pair][NKB][tile 2][chunk 4][SNP 128] 2-bit code words of the MMA operand g' (qf.cu, K1q)
+    uint32_t vt_mma;          // its code -> int8 value table (byte c = value of code c; tile_code_map)
+    const uint32_t* Xd2[2];   // code tiles of the left vectors g of the forms g' T g' (same layout; Xd2[0] == X2 for a plain quadratic form)
+    uint32_t vt_dot[2];
     int ndot;                 // 1 or 2 left vectors per pass
     const int8_t* T8;         // [row tile I][kb < 4(I+1)][Q planes][16 KB] digit planes of T = tril(C_a V^-1 C_a) (half diagonal), or,
                               // full != 0, [row tile I][kb < NKB][Q planes][16 KB] planes of the full matrix C_a V^-1 C_b
@@ -43,7 +45,7 @@ struct QfArgs {
     int64_t n;                // model samples (rows of T beyond n are padding)
     int T256, NJ, Q;
     int GP;                   // SNP tile pairs per L2 group (qf_item); >= ceil(NJ / 2): no grouping
-    int NKB;                  // k-blocks per X8 tile (n_pad256 / 64)
+    int NKB;                  // k-blocks per tile (n_pad256 / 64)
     int NKB_live;             // k-blocks that hold real samples
     long long* prof;          // optional [16 * grid] cycle counters of the three roles (qf.cu, PROF builds): FitModel(verbose=2)
 };
@@ -51,7 +53,8 @@ int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
 
 // K4q (qf.cu): X8 against digit planes of a column block of G = L^-T [Qc | r | R_f]
 struct XgArgs {
-    const int8_t* X8;         // [NJ][NKB][8 KB]
+    const uint32_t* X2;       // [tile pair][NKB][tile 2][chunk 4][SNP 128] 2-bit code words
+    uint32_t vt;              // code -> int8 value table of the tile set
     const int8_t* G8;         // [col block][NKB][Q][NB*64 B]
     const double* colscale;   // [ntiles*NB] power-of-two column scales
     double pair_scale[3];     // 2^-16, 2^-32, 2^-48
@@ -113,7 +116,8 @@ struct DecodeArgs {
     int NJ;                   // tiles in batch
     int* missing_flag;        // out: atomicMin(run-wide index of a SNP holding a missing call); INT_MAX = none
     uint8_t* codes_out;       // optional (tests): nsnp x n gathered codes
-    const uint8_t* smask;     // K1q only: per model sample 0xFF keep / 0x00 zero (an x:factor indicator folded into the int8 tile); nullptr: none
+    const uint8_t* smask;     // K1q only: per model sample 0xFF keep / 0x00 zero (an x:factor indicator folded into the tile set); nullptr: none
+    uint32_t gmap;            // K1q only: byte g = 2-bit code of genotype g in this tile set (tile_code_map)
     // pgenlibr::Read: x = dosage / 16384 where the record has one for the sample (row = the SNP's record row, like `packed`)
     const uint16_t* dosage;   // nullptr: hard calls only
     int64_t dos_ld;
@@ -121,7 +125,8 @@ struct DecodeArgs {
     int dos_g[8];             // g_t of the indicator terms
 };
 int launch_decode(const DecodeArgs& a, cudaStream_t st);
-int launch_decode_i8(const DecodeArgs& a, int8_t* X8, int NJ, int NKB, cudaStream_t st);
+int launch_decode_i8(const DecodeArgs& a, uint32_t* X2, int NJ, int NKB, cudaStream_t st);
+void tile_code_map(const int a[3], uint32_t* gmap, uint32_t* vt);   // integer triple of a tile set -> genotype -> code map, code -> int8 value table
 
 // ---------------------------------------------------------------- K3 (snp_fit.cu)
 struct FitConst {
