@@ -544,7 +544,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--full", action="store_true", help="per-GPU SNP count of the BASELINE config at 8 GPUs instead of the default slice")
-    ap.add_argument("--shapes", default="auto", help="comma list of extra BASELINE shapes measured after the headline (auto: C3,C4,C5 with the default C2 workload; none)")
+    ap.add_argument("--shapes", default="auto", help="comma list of extra BASELINE shapes measured after the headline (auto: C3,C4,C5 with the default C2 workload on one GPU; none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--route", default="auto", choices=["auto", "fp64"], help="fp64: force the FP64 DMMA route (FLX_FLAG_NO_INT8)")
     ap.add_argument("--cpu-snps", type=int, default=0, help="SNPs per core for the CPU baseline sample (0 = auto)")
@@ -589,7 +589,9 @@ def main():
     res = run_workload(ctx, a.workload, w, a.steps, a.warmup, route=a.route, full=a.full, clocks=True)
 
     shapes = {}
-    want = [] if a.shapes == "none" else (["C3", "C4", "C5"] if (a.shapes == "auto" and a.workload == "C2" and a.route == "auto") else
+    # auto: the extra shapes ride on the single-GPU headline run only — under torchrun a failure of ONE rank inside an extra shape would leave the
+    # others in a collective and take the headline line with it (every shape has its own multi-GPU line: --workload C3|C4|C5 --full)
+    want = [] if a.shapes == "none" else (["C3", "C4", "C5"] if (a.shapes == "auto" and a.workload == "C2" and a.route == "auto" and world == 1) else
                                           [x for x in a.shapes.split(",") if x in WORKLOADS and a.shapes != "auto"])
     for nm in want:
         t0 = time.perf_counter()

@@ -474,7 +474,8 @@ int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
 // permutation of the 2-bit fields inside each word.
 // ------------------------------------------------------------------------------------------------
 constexpr int DEC8_KBS = 8;   // k-blocks per CTA: 512 samples = 128 packed bytes per record, one cache line
-__global__ void __launch_bounds__(512) decode_2b_tile_kernel(const DecodeArgs a, uint32_t* __restrict__ X2, int NKB) {
+template <bool IDG>      // IDG: the codes are the genotypes (gmap = 0, 1, 2: x itself) — no remapping
+__global__ void __launch_bounds__(512, 3) decode_2b_tile_kernel(const DecodeArgs a, uint32_t* __restrict__ X2, int NKB) {
     const int J = blockIdx.x, kb0 = blockIdx.y * DEC8_KBS;
     const int r = threadIdx.x & 127, ch = threadIdx.x >> 7;
     const int64_t snp = (int64_t)J * 128 + r;
@@ -493,20 +494,37 @@ __global__ void __launch_bounds__(512) decode_2b_tile_kernel(const DecodeArgs a,
     if (staged) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int64_t b0 = (int64_t)kb0 * (QF_KB / 4) + 4 * lane;          // first of this lane's 4 bytes within a record
-        for (int rr = warp; rr < 128; rr += 16) {
-            const int64_t s2 = (int64_t)J * 128 + rr;
-            uint32_t word = 0;
-            if (s2 < a.nsnp) {
-                const uint8_t* rc = a.packed + (a.vmap ? (int64_t)a.vmap[s2] : s2) * a.bpv;
+        // the lane's four bytes of a record through ALIGNED 32-bit loads and a funnel shift (records start at any byte: bpv = ceil(N_raw / 4));
+        // the second word is read only when bytes of this record live in it, so nothing beyond the record's last aligned word is touched.
+        // Eight records per warp, all of their loads in flight before the first use (the loop is latency-bound otherwise)
+        uint32_t w0v[8], w1v[8], shv[8];
+        int64_t leftv[8];
 #pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (b0 + b < a.bpv) word |= (uint32_t)__ldg(rc + b0 + b) << (8 * b);
+        for (int i = 0; i < 8; i++) {
+            const int rr = warp + 16 * i;
+            const int64_t s2 = (int64_t)J * 128 + rr;
+            w0v[i] = w1v[i] = 0u; shv[i] = 0u; leftv[i] = 0;
+            if (s2 < a.nsnp && b0 < a.bpv) {
+                const uint8_t* p = a.packed + (a.vmap ? (int64_t)a.vmap[s2] : s2) * a.bpv + b0;
+                const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+                const uint32_t* pw = reinterpret_cast<const uint32_t*>(p - sh);
+                const int64_t left = a.bpv - b0;                                    // bytes of the record from p on (>= 1)
+                w0v[i] = __ldg(pw);
+                if (sh != 0 && left > (int64_t)(4 - sh)) w1v[i] = __ldg(pw + 1);
+                shv[i] = sh; leftv[i] = left;
             }
-            seg[rr][lane] = word;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t word = __funnelshift_r(w0v[i], w1v[i], 8 * shv[i]);
+            if (leftv[i] < 4) word = leftv[i] > 0 ? (word & ((1u << (8 * (int)leftv[i])) - 1u)) : 0u;
+            seg[warp + 16 * i][lane] = word;
         }
         __syncthreads();
     }
-    for (int kb = kb0; kb < kend; kb++) {
+    // this thread's words: X2[pair][kb][tile][ch][r], 1024 words from one k-block to the next
+    uint32_t* dst = X2 + ((((int64_t)(J >> 1) * NKB + kb0) * 2 + (J & 1)) * 4 + ch) * 128 + r;
+    for (int kb = kb0; kb < kend; kb++, dst += 1024) {
         uint32_t w = 0;              // genotypes of the 16 samples, sample j at bits 2j (the pgen order)
         uint32_t keep = 0xffffffffu; // fields of real, unmasked samples
         const int64_t k0 = (int64_t)kb * QF_KB + ch * 16;
@@ -539,20 +557,26 @@ __global__ void __launch_bounds__(512) decode_2b_tile_kernel(const DecodeArgs a,
             }
         } else keep = 0;
         w &= keep;
-        const uint32_t lo = w & E, hi = (w >> 1) & E;
-        if (lo & hi) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));           // code 3 inside the kept fields: a missing call
-        const uint32_t is0 = ~(lo | hi) & E & (keep & E), is1 = lo & ~hi, is2 = hi & ~lo;
-        uint32_t x = ((is0 & ml[0]) | (is1 & ml[1]) | (is2 & ml[2])) | (((is0 & mh[0]) | (is1 & mh[1]) | (is2 & mh[2])) << 1);
+        const uint32_t lo = w & E, hi = (w >> 1) & E, miss = lo & hi;
+        if (miss) atomicMin(a.missing_flag, (int)(a.snp_offset + snp));           // code 3 inside the kept fields: a missing call
+        uint32_t x;
+        if (IDG) x = w & ~(miss * 3u);
+        else {
+            const uint32_t is0 = ~(lo | hi) & (keep & E), is1 = lo & ~hi, is2 = hi & ~lo;
+            x = ((is0 & ml[0]) | (is1 & ml[1]) | (is2 & ml[2])) | (((is0 & mh[0]) | (is1 & mh[1]) | (is2 & mh[2])) << 1);
+        }
         // field j: bit 2j -> bit 2 (j / 4) + 8 (j % 4): the 4 x 4 transpose of the 2-bit fields
         uint32_t tq = (x ^ (x >> 6)) & 0x00CC00CCu; x ^= tq ^ (tq << 6);
         tq = (x ^ (x >> 12)) & 0x0000F0F0u; x ^= tq ^ (tq << 12);
-        X2[((((int64_t)(J >> 1) * NKB + kb) * 2 + (J & 1)) * 4 + ch) * 128 + r] = x;
+        *dst = x;
     }
 }
 
 int launch_decode_i8(const DecodeArgs& a, uint32_t* X2, int NJ, int NKB, cudaStream_t st) {
     if (NJ <= 0) return 0;
-    decode_2b_tile_kernel<<<dim3((unsigned)NJ, (unsigned)((NKB + DEC8_KBS - 1) / DEC8_KBS)), 512, 0, st>>>(a, X2, NKB);
+    const dim3 grid((unsigned)NJ, (unsigned)((NKB + DEC8_KBS - 1) / DEC8_KBS));
+    if ((a.gmap & 0xffffffu) == 0x020100u) decode_2b_tile_kernel<true><<<grid, 512, 0, st>>>(a, X2, NKB);
+    else decode_2b_tile_kernel<false><<<grid, 512, 0, st>>>(a, X2, NKB);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("decode_i8 launch: %s", cudaGetErrorString(e)); return -3; }
     return 0;

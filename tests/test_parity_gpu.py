@@ -570,6 +570,40 @@ def test_int8_path_four_terms_two_scales_two_codes(fx, orc):
     compare(r8, oracle_run(orc, t, t["codes_raw"]))
 
 
+@pytest.mark.parametrize("n,n_raw,prefix", [(301, 301, True), (130, 257, True), (203, 333, False), (64, 67, True)])
+def test_code_tiles_any_record_alignment(fx, orc, n, n_raw, prefix):
+    """K1q builds its 2-bit code tiles from the records' own 32-bit words: record lengths of any residue mod 4 (every start alignment),
+    records longer than the model's samples (identity-prefix order: the staged path masks the tail), and a gathering order."""
+    from flexlmm_b200 import synth
+    M = 150
+    t = synth.task(n, M, model="domgxe", P=2, n_raw=n_raw, seed=n + n_raw, effect=0.1)
+    if prefix:
+        t["pgen_order"] = np.arange(1, n + 1, dtype=np.int32)
+    r8, st8 = _run(fx, t, True, M)
+    assert st8["int8_path"] == 1
+    codes = t["codes_raw"][:, t["pgen_order"] - 1]
+    compare(r8, oracle_run(orc, t, codes))
+    want = np.array([oracle_run(orc, t, codes, seed=int(sd))["min_pval"] for sd in t["seeds"]])
+    assert_logp_close(r8["min_pval"], want)
+
+
+def test_code_tiles_negative_triple(fx, orc):
+    """A centred genotype coding (x - 1: values -1, 0, 1) is a tile set whose codes are not its values: the expanders' and the
+    epilogue's table path."""
+    from flexlmm_b200 import synth
+    n, M = 333, 140
+    t = synth.task(n, M, model="additive", P=2, seed=77, effect=0.1)
+    cov = t["M0"][:, 2]
+    one = np.ones(n)
+    t["M0"], t["M1"], t["M2"] = (np.column_stack([one, np.full(n, float(v - 1)), cov]) for v in (0, 1, 2))
+    r8, st8 = _run(fx, t, True, M)
+    r64, st64 = _run(fx, t, False, M)
+    assert st8["int8_path"] == 1 and st64["int8_path"] == 0
+    assert np.array_equal(r8["lrt_df"], r64["lrt_df"]) and np.array_equal(r8["pivot"], r64["pivot"])
+    compare(r8, oracle_run(orc, t, t["codes_raw"]))
+    assert_logp_close(r8["min_pval"], r64["min_pval"])
+
+
 def test_int8_path_factor_interaction_and_rare_variants(fx, orc):
     """The reference's test formula shape, y ~ x + I(x==1) + x:group + group with a two-level factor (indicator scale), on
     SNPs many of which have no hom-alt call: there I(x==1) duplicates x exactly and is dropped by the rank rule WITHOUT a
