@@ -1,5 +1,5 @@
 """K2q MMA-issuer cycle split (epilogue wait, TMA wait) via FitModel(verbose=2): python tools/qf_prof.py [batch_tiles] [workload] [snps]
-FLX_QF_PROBE=1|2|3 (timing experiments, results invalid) shows what a smaller operand stream would buy."""
+The timing experiments behind profiles/r02_k2q_issuer_probes.txt (skipped copies, N = 32 MMAs) were compile-time edits of qf.cu and are in git history."""
 import sys, numpy as np
 sys.path.insert(0, ".")
 import torch
