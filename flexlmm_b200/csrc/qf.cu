@@ -17,18 +17,19 @@
 // tensor clocks per SM = 16 TB/s over the chip; profiles/r02_k2q_issuer_probes.txt), the codes make it 20 KB.  A tile set's
 // code c stands for the int8 value vt[c] (vt[0] = 0: missing / masked samples), at most three non-zero values per set.
 //
-// K2q kernel: persistent, warp-specialised, one CTA of 16 warps per SM.
-//   warp 0    : TMA producer — 1-D bulk copies of pre-packed blocks into an 8-stage x 20 KB ring: one digit-plane block (16 KB,
-//               UMMA canonical K-major, no swizzle: 8 x 16 B core matrices) + the code block of a PAIR of SNP tiles (4 KB).
-//   warps 4-7 : expanders — 2-bit codes -> int8 in the UMMA layout, into a 4-slot x 16 KB ring (conflict-free LDS.32 / STS.128: the
-//               code word of (tile, k16 chunk, SNP) expands to the 16 bytes of exactly that core-matrix row), fence.proxy.async.
-//   warps 1-2 : MMA issuers, one per SNP tile of the pair (tcgen05.mma.cta_group::1.kind::i8, M = 128 SNPs, N = 256 rows of T,
-//               K = 32 per instruction, one 128 x 256 s32 accumulator each; a tcgen05.mma costs its issuing thread ~85 clk whatever
-//               its size, one thread cannot feed the pipe); tcgen05.commit frees ring stages and slots.  Warp 1 owns the 512
-//               TMEM columns.  (warp 3 idle: setmaxnreg works on whole warpgroups.)
-//   warps 8-15: epilogue — tcgen05.ld an accumulator 16 rows at a time, multiply by the left vector(s) at those rows,
-//               reduce the 16 rows exactly in s32 (they share one power-of-two scale), scale and sum over the 256 rows
-//               IN THE THREAD (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane, SNP).
+// K2q kernel: persistent, warp-specialised, one CTA of 16 warps per SM (warp ids in scheduling-priority order, lowest first).
+//   warps 0-3  : expanders — 2-bit codes -> int8 in the UMMA layout, warp w owns ring slot w of a 4-slot x 16 KB ring and expands every
+//                fourth stage (conflict-free LDS.32 / STS.128: the code word of (tile, k16 chunk, SNP) expands to the 16 bytes of exactly
+//                that core-matrix row), fence.proxy.async.
+//   warps 4-11 : epilogue (4 per accumulator) — tcgen05.ld an accumulator 16 rows at a time, multiply by the left vector(s) at those rows,
+//                reduce the 16 rows exactly in s32 (they share one power-of-two scale), scale and sum over the 256 rows
+//                IN THE THREAD (thread = TMEM lane = SNP): no cross-lane reduction.  One partial per (row tile, plane, SNP).
+//   warp 12    : TMA producer — 1-D bulk copies of pre-packed blocks into an 8-stage x 20 KB ring: one digit-plane block (16 KB,
+//                UMMA canonical K-major, no swizzle: 8 x 16 B core matrices) + the code block of a PAIR of SNP tiles (4 KB).
+//   warps 13-14: MMA issuers, one per SNP tile of the pair (tcgen05.mma.cta_group::1.kind::i8, M = 128 SNPs, N = 256 rows of T,
+//                K = 32 per instruction, one 128 x 256 s32 accumulator each; a tcgen05.mma costs its issuing thread ~85 clk whatever
+//                its size, one thread cannot feed the pipe); tcgen05.commit frees ring stages and slots.  Warp 13 owns the 512
+//                TMEM columns.  (warp 15 idle: setmaxnreg works on whole warpgroups.)
 // All single-thread roles run their loops warp-wide and elect only the issuing instruction (uniform registers, no R2UR waterfall).
 // Work item = (row tile I of 256 rows, pair of SNP tiles, digit plane q); k runs over the lower-triangular range (all k
 // for a full matrix).
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(QF_THREADS, 1) qf_i8_kernel(const QfArgs g) {
         if (warp < QF_SLOTS) qf_expand_stages(smem, bars, warp, lane, nstages, g.vt_mma);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(QF_EPI_REGS));
-        // ---------------- epilogue: thread = TMEM lane = SNP; warps 8-11 own the first SNP tile of the pair, warps 12-15 the second
+        // ---------------- epilogue: thread = TMEM lane = SNP; the first four warps own the first SNP tile of the pair, the other four the second
         const int quad = warp & 3;
         const int t = (warp - QF_EPI_WARP0) >> 2;
         const int snp_l = quad * 32 + lane;
@@ -704,7 +705,7 @@ int launch_zero_upper(double* Z, int64_t n, int64_t ld, cudaStream_t st) {
 // codes + Q * NB * 64 B of planes for 2 x 128 x (Q NB) x 64 MACs.  The Q planes of the block sit side by side along N in shared
 // memory and in TMEM (plane q of tile t at column 256 t + q NB, Q NB <= 256), so one instruction covers all planes and the A tile
 // is read from shared memory once per K step.
-// Warps: 0 TMA producer, 1-2 MMA issuers, 4-7 expanders, 8-15 epilogue (4 per SNP tile; thread = TMEM lane = SNP).
+// Warps as in K2q: 0-3 expanders, 4-11 epilogue (4 per SNP tile; thread = TMEM lane = SNP), 12 TMA producer, 13-14 MMA issuers.
 // ================================================================================================
 #define XG_TMEM_LD8(v, taddr)                                                                                        \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                          \
