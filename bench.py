@@ -319,7 +319,7 @@ def stage_roofline(w, acc, steps, int8_path, M, handles=1):
     if int8_path:
         passes = max(1, int(round(acc.get("int8_passes", steps) / (steps * handles))))
         na = 2 if w["model"] == "domgxe" else 1
-        put("K1q decode_i8", M * (raw + n256) * na, "GB/s", acc["ms_decode"], hbm, "hbm")
+        put("K1q decode (2-bit records -> 2-bit code tiles)", M * (raw + n256 / 4.0) * na, "GB/s", acc["ms_decode"], hbm, "hbm")
         put("K2q qf_i8 (g'C V^-1 C g, 6 planes x %d pass units)" % passes, 6.0 * n * n * M * passes, "TFLOP/s", acc["ms_whiten"], i8_peak()[0], "tensor(i8)")
         put("K4q (u, b, b* for all seeds, 6 planes) + K3b", 6.0 * 2 * n * (c + 1 + P) * M * s, "TFLOP/s", acc["ms_fit"], i8_peak()[0], "tensor(i8)")
         put("perm_reduce (b*' Sm b* / RSS_f*, max per seed)", 8.0 * M * s * P, "GB/s", acc["ms_perm"], hbm, "hbm")

@@ -477,7 +477,9 @@ int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st) {
 constexpr int DEC8_KBS = 8;   // k-blocks per CTA: 512 samples = 128 packed bytes per record, one cache line
 template <bool IDG>      // IDG: the codes are the genotypes (gmap = 0, 1, 2: x itself) — no remapping
 __global__ void __launch_bounds__(512, 3) decode_2b_tile_kernel(const DecodeArgs a, uint32_t* __restrict__ X2, int NKB) {
-    const int J = blockIdx.x, kb0 = blockIdx.y * DEC8_KBS;
+    // k-block groups fastest: consecutive CTAs read consecutive 128-byte segments of the SAME 128 records (DRAM rows and the sectors of a
+    // misaligned record stay hot), not the same segment of records 160 KB apart
+    const int J = blockIdx.y, kb0 = blockIdx.x * DEC8_KBS;
     const int r = threadIdx.x & 127, ch = threadIdx.x >> 7;
     const int64_t snp = (int64_t)J * 128 + r;
     const bool live = snp < a.nsnp;
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(512, 3) decode_2b_tile_kernel(const DecodeArgs
 
 int launch_decode_i8(const DecodeArgs& a, uint32_t* X2, int NJ, int NKB, cudaStream_t st) {
     if (NJ <= 0) return 0;
-    const dim3 grid((unsigned)NJ, (unsigned)((NKB + DEC8_KBS - 1) / DEC8_KBS));
+    const dim3 grid((unsigned)((NKB + DEC8_KBS - 1) / DEC8_KBS), (unsigned)NJ);
     if ((a.gmap & 0xffffffu) == 0x020100u) decode_2b_tile_kernel<true><<<grid, 512, 0, st>>>(a, X2, NKB);
     else decode_2b_tile_kernel<false><<<grid, 512, 0, st>>>(a, X2, NKB);
     cudaError_t e = cudaGetLastError();
