@@ -142,7 +142,7 @@ struct flx_handle {
     bool fast = false;
     int Q = 6, T256 = 0, NKB = 0;
     // every SNP term is g_t(x) * c_t[sample] with an integer triple g_t (|g| <= 2) and a per-sample scale c_t.  A 0/1 scale (the
-    // indicator column of an x:factor interaction) is folded into the int8 genotype tile as a sample mask, so such terms share the
+    // indicator column of an x:factor interaction) is folded into the genotype code tile as a sample mask, so such terms share the
     // digit planes of the unscaled matrix: a tile set ("alpha") = (triple, mask); a real-valued scale is a "group" with its own planes
     struct QfPass { int mat, amma, ndot, adot[2], slot[2]; };
     static constexpr int MAX_NA = 4;
@@ -869,7 +869,7 @@ static int finalize_setup(flx_handle* h) {
     else {
         // Two ways to lay a design out, tried in turn; the cheaper feasible one (in K2q pass units) wins:
         //   plain  — every distinct per-sample scale is a group with its own digit planes (x + I(x==1) + x:cov: 5 units);
-        //   folded — 0/1 scales (the indicator columns of an x:factor interaction) become sample masks of the int8 genotype tiles,
+        //   folded — 0/1 scales (the indicator columns of an x:factor interaction) become sample masks of the genotype code tiles,
         //            so those terms share the unscaled planes (x + I(x==1) + x:factor with three levels: 8 units instead of the
         //            FP64 route, which costs ~14).
         struct Trial { int why = FLX_FALLBACK_NONE; flx_handle::FastPlan pl; std::vector<std::vector<double>> cvecs; std::vector<std::vector<uint8_t>> masks;
@@ -1181,7 +1181,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
                        const int32_t* out_map_host = nullptr, int64_t M_total = 0) {
     if (M_total < M) M_total = M;
     TileShape ts = make_tile_shape(h->s);
-    if (use_fast) ts.snps = 128;          // int8 tiles hold 128 SNPs whatever the number of terms
+    if (use_fast) ts.snps = 128;          // code tiles hold 128 SNPs whatever the number of terms
     // default batch: one column tile per SM on the FP64 route (the X / W tiles are 8 n_pad bytes per column); four on the int8
     // route, where a tile is 128 n bytes and K1q / K3b / K4q want more SNPs in flight than one tile per SM (K2q is indifferent),
     // capped so that the batch buffers stay below a quarter of the free memory
@@ -1414,7 +1414,7 @@ static int run_batches(flx_handle* h, const int32_t* var_idx, int64_t M, bool wa
             memcpy(da.dos_g, h->dos_g, sizeof(da.dos_g));
         }
         if (use_fast && !decode_only) {
-            // K1q: one int8 tile set per integer triple of the design (x itself, I(x==1), ...)
+            // K1q: one 2-bit code tile set per (integer triple, sample mask) of the design (x itself, I(x==1), ...)
             for (int al = 0; al < h->plan.NA; al++) {
                 uint32_t vt_unused;
                 tile_code_map(h->plan.aval[al], &da.gmap, &vt_unused);

@@ -51,7 +51,7 @@ struct QfArgs {
 };
 int launch_qf(const QfArgs& g, int num_sms, cudaStream_t st);
 
-// K4q (qf.cu): X8 against digit planes of a column block of G = L^-T [Qc | r | R_f]
+// K4q (qf.cu): the code tiles against digit planes of a column block of G = L^-T [Qc | r | R_f]
 struct XgArgs {
     const uint32_t* X2;       // [tile pair][NKB][tile 2][chunk 4][SNP 128] 2-bit code words
     uint32_t vt;              // code -> int8 value table of the tile set
